@@ -1,0 +1,94 @@
+"""Synthetic inputs for the configured workloads.
+
+Pure NumPy, deterministic.  Used by tests, bench.py and smoke(); nothing here is
+solver code.  `msvc_rand` is the MSVC `rand()` LCG (seed 1, RAND_MAX 32767) that
+reference tests/minimal/main.cpp:52-54 and tests/minimal_graph/main.cpp implicitly
+used to produce the golden PNGs.
+"""
+import numpy as np
+
+
+def msvc_rand(n, seed=1):
+    out = np.empty(n, dtype=np.int64)
+    s = seed
+    for i in range(n):
+        s = (s * 214013 + 2531011) & 0xFFFFFFFF
+        out[i] = (s >> 16) & 0x7FFF
+    return out
+
+
+def msvc_rand_fast(n, seed=1):
+    """Vectorised LCG: s_k = a^k s_0 + c (a^k - 1)/(a - 1) mod 2^32, via doubling."""
+    a, c = 214013, 2531011
+    A = np.empty(n + 1, dtype=np.uint64)
+    C = np.empty(n + 1, dtype=np.uint64)
+    A[0], C[0] = 1, 0
+    filled = 1
+    mask = np.uint64(0xFFFFFFFF)
+    A[1], C[1] = a, c
+    filled = 2
+    while filled < n + 1:
+        m = min(filled - 1, n + 1 - filled)
+        # state after (filled-1 + j) steps = compose(step^(filled-1), step^j)
+        Ak, Ck = A[filled - 1], C[filled - 1]
+        A[filled:filled + m] = (A[1:1 + m] * Ak) & mask
+        C[filled:filled + m] = (A[1:1 + m] * Ck + C[1:1 + m]) & mask
+        filled += m
+    s = (A[1:] * np.uint64(seed) + C[1:]) & mask
+    return ((s >> np.uint64(16)) & np.uint64(0x7FFF)).astype(np.int64)
+
+
+def minimal_inputs(W, H, seed=1):
+    """A[i] = float(rand()/RAND_MAX), row-major; X0 = A (tests/minimal/main.cpp:50-60)."""
+    r = msvc_rand_fast(W * H, seed)
+    A = (r.astype(np.float64) / 32767.0).astype(np.float32)
+    return A.copy(), A
+
+
+def minimal_graph_inputs(N, seed=1):
+    r = msvc_rand_fast(N, seed)
+    A = (r.astype(np.float64) / 32767.0).astype(np.float32)
+    v0 = np.arange(N - 1, dtype=np.int32)
+    v1 = v0 + 1
+    return A.copy(), A, v0, v1
+
+
+def image_warping_inputs(W, H, seed=1, w_fit=100.0, w_reg=0.01):
+    """Config 2 synthetic shape: UrShape=(x,y), Offset0=UrShape, Angle0=0,
+    Mask=0 except a seeded ~10% of pixels in discs (=1, excluded) and the outermost
+    image ring (=1, so the at-output and residualwise forms of the energy agree on the
+    border, see DESIGN.md "ghost residuals"); Constraints=-1 except the second ring
+    pinned in place and an 8x8 lattice of handles displaced by a smooth ramp."""
+    rng = np.random.RandomState(seed)
+    ys, xs = np.mgrid[0:H, 0:W]
+    ur = np.stack([xs, ys], axis=-1).astype(np.float32)
+    offset = ur.copy()
+    angle = np.zeros((H, W), np.float32)
+    mask = np.zeros((H, W), np.float32)
+    ndisc = 12
+    rad = max(2, int(np.sqrt(0.10 * W * H / (np.pi * ndisc))))
+    for _ in range(ndisc):
+        cx, cy = rng.randint(0, W), rng.randint(0, H)
+        mask[(xs - cx) ** 2 + (ys - cy) ** 2 <= rad * rad] = 1.0
+    mask[0, :] = mask[-1, :] = 1.0
+    mask[:, 0] = mask[:, -1] = 1.0
+    cons = -np.ones((H, W, 2), np.float32)
+    ring = np.zeros((H, W), bool)
+    ring[1, 1:-1] = ring[-2, 1:-1] = True
+    ring[1:-1, 1] = ring[1:-1, -2] = True
+    cons[ring] = ur[ring]
+    gx = np.linspace(W * 0.15, W * 0.85, 8).astype(int)
+    gy = np.linspace(H * 0.15, H * 0.85, 8).astype(int)
+    for j, y in enumerate(gy):
+        for i, x in enumerate(gx):
+            s = np.sin(np.pi * (i + 1) / 9.0) * np.sin(np.pi * (j + 1) / 9.0)
+            cons[y, x, 0] = x + 15.0 * s * (W / 2048.0 if W > 256 else 0.25)
+            cons[y, x, 1] = y - 10.0 * s * (H / 2048.0 if H > 256 else 0.25)
+    return dict(Offset=offset.reshape(-1, 2), Angle=angle.reshape(-1), UrShape=ur.reshape(-1, 2),
+                Constraints=cons.reshape(-1, 2), Mask=mask.reshape(-1),
+                w_fitSqrt=np.float32(np.sqrt(w_fit)), w_regSqrt=np.float32(np.sqrt(w_reg)))
+
+
+def image_warping_params(d):
+    return [d["Offset"], d["Angle"], d["UrShape"], d["Constraints"], d["Mask"],
+            np.array([d["w_fitSqrt"]], np.float32), np.array([d["w_regSqrt"]], np.float32)]
