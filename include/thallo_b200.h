@@ -1,0 +1,53 @@
+/* thallo_b200 extension entry points (C ABI, plain pointers and sizes).
+ *
+ * These are the seam the north-star names: "per-energy residual and partial-derivative
+ * device functions are emitted as CUDA C++ and JIT-compiled for sm_100a (NVRTC through a
+ * thin C-ABI shim called from the host)".  In the reference the equivalent hand-over is
+ * in-process Lua: ProblemSpec:Functions registers the generated `fmap` tables
+ * (API/src/thallo.t:444-456,3468-3501) and gauss_newton.t:115 consumes them, then
+ * util.makeGPUFunctions hands the kernels to terralib.cudacompile (util.t:797-927,
+ * cuda_util.t:470).  A Terra/Lua (or Python) host calls ThalloB200_ProblemDefineFromSource
+ * instead of that path; everything after it is the unchanged Thallo.h API.
+ */
+#pragma once
+#include "Thallo.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Define a problem from an already-lowered energy: `descriptor` is the line-based plan
+ * descriptor and `cuda_source` the generated translation unit (both NUL-terminated text,
+ * see DESIGN.md "front-end seam").  Replaces thallo.t:444-456 + util.t:868. */
+Thallo_Problem* ThalloB200_ProblemDefineFromSource(Thallo_State* state, const char* descriptor,
+                                                   const char* cuda_source, const char* solverkind);
+
+/* Compile only: NVRTC the source for sm_100a without touching a GPU.  Returns 0 on success,
+ * and the size of the cubin in *cubin_size; the log (NUL-terminated) is copied into log
+ * (up to log_capacity bytes).  Used by the CPU-side build check. */
+int ThalloB200_CompileOnly(const char* cuda_source, char* log, unsigned long log_capacity, unsigned long* cubin_size);
+
+/* Stream all solver work is issued on (a cudaStream_t); default is the legacy default
+ * stream like the reference (util.t:769-772). */
+void ThalloB200_SetStream(Thallo_State* state, void* cuda_stream);
+
+/* Number of kernel launches issued by this plan since creation (for bench accounting). */
+unsigned long long ThalloB200_PlanLaunchCount(Thallo_State* state, Thallo_Plan* plan);
+
+/* Linear (PCG) iterations executed in the most recent nonlinear step and in total. */
+int ThalloB200_PlanLastLinearIterations(Thallo_State* state, Thallo_Plan* plan);
+unsigned long long ThalloB200_PlanTotalLinearIterations(Thallo_State* state, Thallo_Plan* plan);
+
+/* Copy solver vector `name` ("delta","r","p","Ap_X","preconditioner","z","b","CtC") to host memory
+ * (count reals of the plan's precision).  Test hook. Returns number of reals copied. */
+long long ThalloB200_PlanReadVector(Thallo_State* state, Thallo_Plan* plan, const char* name, void* host_dst, long long count);
+
+/* Last error message of this thread ("" if none). */
+const char* ThalloB200_LastError(void);
+
+/* Library version string. */
+const char* ThalloB200_Version(void);
+
+#ifdef __cplusplus
+}
+#endif

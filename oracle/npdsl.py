@@ -157,12 +157,13 @@ def _unary(x, f, df):
 
 
 def _select(c, a, b):
-    cv = c.v
-    if isinstance(a, Vec) or isinstance(b, Vec):
-        n = len(a) if isinstance(a, Vec) else len(b)
+    if isinstance(a, Vec) or isinstance(b, Vec) or isinstance(c, Vec):
+        n = max(len(v) for v in (a, b, c) if isinstance(v, Vec))
         aa = a.c if isinstance(a, Vec) else [a] * n
         bb = b.c if isinstance(b, Vec) else [b] * n
-        return Vec([_select(c, x, y) for x, y in zip(aa, bb)])
+        cc = c.c if isinstance(c, Vec) else [c] * n
+        return Vec([_select(z, x, y) for z, x, y in zip(cc, aa, bb)])
+    cv = c.v
     ref = a if isinstance(a, Dual) else (b if isinstance(b, Dual) else None)
     dt = np.result_type(ref.val) if ref is not None else np.float64
     A = a if isinstance(a, Dual) else Dual(np.asarray(a, dtype=dt))

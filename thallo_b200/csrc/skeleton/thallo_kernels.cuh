@@ -1,0 +1,587 @@
+// thallo_b200 solver skeleton, part 2: accessors, reductions and the GN/LM + PCG kernels.
+// Included *after* the generated per-energy device functions (namespace th).
+//
+// Kernel-by-kernel correspondence with reference API/src/gauss_newton.t:
+//   th_init_uw            PCGInit1 unknownwise :678-710 fused with the LM diagonal set-up
+//                         (PCGSaveSSq :929-934, computeCtC thallo.t:3911-3937, PCGFinalizeDiagonal :936-969)
+//   th_evaljtf_g<i>       PCGInit1 residualwise :998-1004
+//   th_init_finish        PCGInit1_Finish :712-731 (+ the same LM diagonal set-up)
+//   th_step1_uw           PCGStep1 unknownwise :734-752 / computeAdelta :755-762
+//   th_applyjtj_g<i>      PCGStep1 residualwise :1006-1016 / computeAdelta :1058-1065
+//   th_step1_finish       PCGStep1_Finish :774-799
+//   th_step2              PCGStep2 :801-843     th_step2_first/second  :845-886
+//   th_step3              PCGStep3 :889-899 + scalar hand-over :1665 + LM zeta test :1666-1686
+//   th_update             PCGLinearUpdate :901-906     th_copy_x  savePreviousUnknowns/revertUpdate/copyUnknownwise :908-927
+//   th_cost_g<i>          computeCost :1067-1079       th_modelcost_g<i>  computeModelCost :1088-1095
+// Reductions: warp shuffle -> shared memory -> one partial per block -> the last block to
+// finish sums the partials in a fixed order (deterministic), replacing the reference's
+// one float atomic per warp (util.t:39-50, cuda_util.t:430-449) and its per-iteration memsets.
+#pragma once
+
+#define TH_BLOCK 256
+
+// ------------------------------------------------------------------ index helpers
+template <class Dom> struct ThIdx {
+    int c[TH_MAXD];
+    long long lin;
+    __device__ __forceinline__ bool from_linear(long long l) {
+        lin = l;
+        const long long n = Dom::D0 * Dom::D1 * Dom::D2;
+        if (l >= n) return false;
+        c[0] = (int)(l % Dom::D0);
+        c[1] = (int)((l / Dom::D0) % Dom::D1);
+        c[2] = (int)(l / (Dom::D0 * Dom::D1));
+        return true;
+    }
+    __device__ __forceinline__ bool from_coords(int x, int y, int z) {
+        c[0] = x; c[1] = y; c[2] = z;
+        lin = x + Dom::D0 * (y + Dom::D1 * (long long)z);
+        return x < Dom::D0 && y < Dom::D1 && z < Dom::D2;
+    }
+};
+
+// Unknownwise launch geometry: 1-D 256, 2-D 32x8, 3-D 8x8x4 threads per block
+// (the reference uses 256 / 16x16 / 8x8x4, util.t:715-725; 32-wide rows coalesce better).
+template <class Dom> __device__ __forceinline__ bool th_uw_index(ThIdx<Dom>& i) {
+    if (Dom::ND == 1) return i.from_linear((long long)blockIdx.x * blockDim.x + threadIdx.x);
+    return i.from_coords(blockIdx.x * blockDim.x + threadIdx.x, blockIdx.y * blockDim.y + threadIdx.y,
+                         blockIdx.z * blockDim.z + threadIdx.z);
+}
+
+// ------------------------------------------------------------------ global-memory accessor
+// Bounds-checked loads return 0 out of bounds (thallo.t:876-882); `vec` reads the
+// unknown-shaped vector argument (P / Delta).
+template <class Dom> struct GAcc {
+    ThIdx<Dom> i;
+    const real* __restrict__ v;
+    __device__ __forceinline__ GAcc(const ThIdx<Dom>& idx, const real* vec) : i(idx), v(vec) {}
+
+    template <int D> __device__ __forceinline__ int coord() const { return i.c[D]; }
+
+    template <int L0, int H0, int L1, int H1, int L2, int H2> __device__ __forceinline__ bool inb() const {
+        bool ok = true;
+        if (L0 < 0) ok = ok && (i.c[0] + L0 >= 0);
+        if (H0 > 0) ok = ok && (i.c[0] + H0 < Dom::D0);
+        if (Dom::ND > 1) {
+            if (L1 < 0) ok = ok && (i.c[1] + L1 >= 0);
+            if (H1 > 0) ok = ok && (i.c[1] + H1 < Dom::D1);
+        }
+        if (Dom::ND > 2) {
+            if (L2 < 0) ok = ok && (i.c[2] + L2 >= 0);
+            if (H2 > 0) ok = ok && (i.c[2] + H2 < Dom::D2);
+        }
+        return ok;
+    }
+    template <int O0, int O1, int O2> __device__ __forceinline__ long long elem() const {
+        return i.lin + O0 + Dom::D0 * (O1 + Dom::D1 * (long long)O2);
+    }
+    template <int SLOT, class CT, int C, int CH, int O0, int O1, int O2>
+    __device__ __forceinline__ real img(const Params& P) const {
+        if ((O0 | O1 | O2) != 0) { if (!inb<O0, O0, O1, O1, O2, O2>()) return (real)0; }
+        return ThLoad<CT, C, CH>::ld(P.ptr[SLOT], elem<O0, O1, O2>());
+    }
+    template <int K, int CH, int O0, int O1, int O2> __device__ __forceinline__ real vec() const {
+        if ((O0 | O1 | O2) != 0) { if (!inb<O0, O0, O1, O1, O2, O2>()) return (real)0; }
+        return ThLoad<real, TH_UIMG[K].channels, CH>::ld(v + TH_UIMG[K].offset, elem<O0, O1, O2>());
+    }
+    template <int K, int CH, int O0, int O1, int O2> __device__ __forceinline__ long long ucol() const {
+        if ((O0 | O1 | O2) != 0) { if (!inb<O0, O0, O1, O1, O2, O2>()) return -1; }
+        return TH_UIMG[K].offset + elem<O0, O1, O2>() * TH_UIMG[K].channels + CH;
+    }
+    // sparse (graph) accesses: the index array lives in ptr slot SP and is indexed by this element
+    template <int SP> __device__ __forceinline__ long long sidx(const Params& P) const {
+        return (long long)__ldg(((const int*)P.ptr[SP]) + i.lin);
+    }
+    template <int SLOT, class CT, int C, int CH, int SP> __device__ __forceinline__ real simg(const Params& P) const {
+        return ThLoad<CT, C, CH>::ld(P.ptr[SLOT], sidx<SP>(P));
+    }
+    template <int K, int CH, int SP> __device__ __forceinline__ real svec(const Params& P) const {
+        return ThLoad<real, TH_UIMG[K].channels, CH>::ld(v + TH_UIMG[K].offset, sidx<SP>(P));
+    }
+    template <int K, int CH, int SP> __device__ __forceinline__ long long sucol(const Params& P) const {
+        return TH_UIMG[K].offset + sidx<SP>(P) * TH_UIMG[K].channels + CH;
+    }
+    // bilinear sample, floor/ceil lerp with zero outside (thallo.t:899-907)
+    template <int SLOT> __device__ __forceinline__ real samp(const Params& P, real x, real y) const {
+        const real* im = (const real*)P.ptr[SLOT];
+        const int x0 = (int)th_floor(x), x1 = (int)th_ceil(x);
+        const int y0 = (int)th_floor(y), y1 = (int)th_ceil(y);
+        const real xn = x - (real)x0, yn = y - (real)y0;
+        auto get = [&](int xx, int yy) -> real {
+            return (xx >= 0 && xx < Dom::D0 && yy >= 0 && yy < Dom::D1) ? __ldg(im + xx + Dom::D0 * (long long)yy) : (real)0;
+        };
+        const real u = ((real)1 - xn) * get(x0, y0) + xn * get(x1, y0);
+        const real b = ((real)1 - xn) * get(x0, y1) + xn * get(x1, y1);
+        return ((real)1 - yn) * u + yn * b;
+    }
+};
+
+// ------------------------------------------------------------------ scatter sink (atomics)
+// WHICH selects the target vector (0: r / Ap / Adelta, 1: preconditioner diagonal);
+// out-of-bounds targets are dropped (thallo.t:3355-3390).
+template <class Dom> struct GScatter {
+    ThIdx<Dom> i;
+    real* t0; real* t1;
+    __device__ __forceinline__ GScatter(const ThIdx<Dom>& idx, real* a, real* b) : i(idx), t0(a), t1(b) {}
+    template <int WHICH, int K, int CH, int O0, int O1, int O2> __device__ __forceinline__ void add(real val) {
+        const int x = i.c[0] + O0, y = i.c[1] + O1, z = i.c[2] + O2;
+        bool ok = x >= 0 && x < Dom::D0;
+        if (Dom::ND > 1) ok = ok && y >= 0 && y < Dom::D1;
+        if (Dom::ND > 2) ok = ok && z >= 0 && z < Dom::D2;
+        if (!ok) return;
+        const long long e = i.lin + O0 + Dom::D0 * (O1 + Dom::D1 * (long long)O2);
+        atomicAdd((WHICH ? t1 : t0) + TH_UIMG[K].offset + e * TH_UIMG[K].channels + CH, val);
+    }
+    template <int WHICH, int K, int CH, int SP> __device__ __forceinline__ void sadd(const Params& P, real val) {
+        const long long e = (long long)__ldg(((const int*)P.ptr[SP]) + i.lin);
+        atomicAdd((WHICH ? t1 : t0) + TH_UIMG[K].offset + e * TH_UIMG[K].channels + CH, val);
+    }
+};
+
+// ------------------------------------------------------------------ deterministic block/grid reduction
+__device__ __forceinline__ double th_warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Every thread of every block calls this with K per-thread values.  partials holds
+// K * gridsize doubles.  Returns true (in all threads of exactly one block, the last to
+// arrive) with tot[k] = sum over blocks in block order.
+template <int K> __device__ __forceinline__ bool th_grid_reduce(double (&val)[K], double (&tot)[K], double* partials,
+                                                               unsigned int* ticket) {
+    __shared__ double sm[K][32];
+    __shared__ bool last;
+    const int tid = threadIdx.x + blockDim.x * (threadIdx.y + blockDim.y * threadIdx.z);
+    const int nthreads = blockDim.x * blockDim.y * blockDim.z;
+    const int lane = tid & 31, warp = tid >> 5, nwarps = (nthreads + 31) >> 5;
+    const unsigned int nblocks = gridDim.x * gridDim.y * gridDim.z;
+    const unsigned int bid = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        const double w = th_warp_sum(val[k]);
+        if (lane == 0) sm[k][warp] = w;
+    }
+    __syncthreads();
+    if (warp == 0) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            double w = lane < nwarps ? sm[k][lane] : 0.0;
+            w = th_warp_sum(w);
+            if (lane == 0) partials[(size_t)k * nblocks + bid] = w;
+        }
+    }
+    if (tid == 0) {
+        __threadfence();
+        const unsigned int t = atomicAdd(ticket, 1u);
+        last = (t == nblocks - 1);
+    }
+    __syncthreads();
+    if (!last) return false;
+    __threadfence();
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        double s = 0.0;
+        for (unsigned int b = tid; b < nblocks; b += nthreads) s += __ldcg(partials + (size_t)k * nblocks + b);
+        s = th_warp_sum(s);
+        __syncthreads();
+        if (lane == 0) sm[k][warp] = s;
+        __syncthreads();
+        double w = lane < nwarps ? sm[k][lane] : 0.0;
+        w = th_warp_sum(w);
+        tot[k] = __shfl_sync(0xffffffffu, w, 0);
+    }
+    if (tid == 0) *ticket = 0u;
+    return true;
+}
+
+__device__ __forceinline__ real th_guarded_invert(real d) {     // GuardedInvertType.CERES, gauss_newton.t:641-648
+    const real s = (real)1 + th_sqrt(d);
+    return (real)1 / (s * s);
+}
+
+__device__ __forceinline__ real th_alpha(const ThScalars* S) {   // safeDivideIfNotLM, gauss_newton.t:226-234
+    const real num = (real)S->rz[S->it & 1], den = (real)S->aD;
+#if TH_LM
+    return num / den;
+#else
+    return den != (real)0 ? num / den : (real)0;
+#endif
+}
+__device__ __forceinline__ real th_beta(const ThScalars* S) {
+    const real num = (real)S->rz[(S->it + 1) & 1], den = (real)S->rz[S->it & 1];
+#if TH_LM
+    return num / den;
+#else
+    return den != (real)0 ? num / den : (real)0;
+#endif
+}
+
+// Shared tail of both PCGInit forms: given the gradient entry g (=J^T F) and the true
+// diagonal d (=diag J^T J) of one unknown scalar, produce r, preconditioner, p (and in LM
+// CtC, b, SSq) and return r*p.
+__device__ __forceinline__ real th_init_scalar(const Params& P, const Vecs& V, long long off, real g, real d,
+                                               real pre_if_off, int first_nonlinear) {
+    const real r = -g;
+    real pre = TH_USEPRE ? th_guarded_invert(d) : pre_if_off;
+#if TH_LM
+    real ssq = pre;
+    if (first_nonlinear) V.SSq[off] = pre; else ssq = V.SSq[off];
+    const real radius = P.trust_region_radius;
+    const real ctc_raw = d / radius;
+    const real mult = ((real)1 / ssq) / radius;
+    const real ctc = th_fmin(th_fmax(ctc_raw, P.min_lm_diagonal * mult), P.max_lm_diagonal * mult);
+    pre = (real)1 / (ctc + radius * ctc_raw);
+    V.CtC[off] = ctc;
+    V.b[off] = r;
+#endif
+    const real p = pre * r;
+    V.delta[off] = (real)0;
+    V.r[off] = r;
+    V.pre[off] = pre;
+    V.p[off] = p;
+    return r * p;
+}
+__device__ __forceinline__ void th_zero_scalar(const Vecs& V, long long off) {
+    V.delta[off] = (real)0; V.r[off] = (real)0; V.pre[off] = (real)0; V.p[off] = (real)0;
+    V.z[off] = (real)0; V.Ap[off] = (real)0;
+#if TH_LM
+    V.CtC[off] = (real)0; V.b[off] = (real)0; V.Adelta[off] = (real)0;
+#endif
+}
+__device__ __forceinline__ void th_begin_linear(ThScalars* S, double rz0) {
+    S->rz[0] = rz0; S->rz[1] = 0.0; S->aD = 0.0; S->q = 0.0; S->Q0 = 0.0;
+    S->it = 0; S->done = 0; S->lin_done = 0;
+}
+
+// ================================================================== at-output (unknownwise) kernels
+#if TH_AT_OUTPUT
+extern "C" __global__ void __launch_bounds__(TH_BLOCK)
+th_init_uw(const __grid_constant__ Params P, const __grid_constant__ Vecs V, ThScalars* S, double* partials, int first_nonlinear) {
+    ThIdx<th::dom_uw> idx;
+    double acc[1] = {0.0};
+    if (th_uw_index(idx)) {
+        GAcc<th::dom_uw> a(idx, nullptr);
+        const bool ex = th::exclude_u0(a, P);
+        real g[TH_U], d[TH_U];
+        if (!ex) th::evalJTF_uw(a, P, g, d);
+        real dot = (real)0;
+        int j = 0;
+#pragma unroll
+        for (int k = 0; k < TH_NUM_UIMG; ++k) {
+#pragma unroll
+            for (int ch = 0; ch < TH_UIMG[k].channels; ++ch, ++j) {
+                const long long off = TH_UIMG[k].offset + idx.lin * TH_UIMG[k].channels + ch;
+                if (ex) th_zero_scalar(V, off);
+                else dot += th_init_scalar(P, V, off, g[j], d[j], (real)0.25, first_nonlinear);   // d:=1 -> G(1)=0.25, gauss_newton.t:693-696
+            }
+        }
+        acc[0] = (double)dot;
+    }
+    double tot[1];
+    if (th_grid_reduce<1>(acc, tot, partials, &S->ticket[0])) {
+        if (threadIdx.x + threadIdx.y + threadIdx.z == 0) th_begin_linear(S, tot[0]);
+    }
+}
+
+// which = 0: Ap = (JtJ [+CtC]) p with alphaDenominator = <p,Ap>;  which = 1: Adelta = (JtJ [+CtC]) delta
+extern "C" __global__ void __launch_bounds__(TH_BLOCK)
+th_step1_uw(const __grid_constant__ Params P, const __grid_constant__ Vecs V, ThScalars* S, double* partials, int which) {
+    if (S->done) return;
+    const real* __restrict__ in = which ? V.delta : V.p;
+    real* __restrict__ out = which ? V.Adelta : V.Ap;
+    ThIdx<th::dom_uw> idx;
+    double acc[1] = {0.0};
+    if (th_uw_index(idx)) {
+        GAcc<th::dom_uw> a(idx, in);
+        if (!th::exclude_u0(a, P)) {
+            real o[TH_U];
+            th::applyJTJ_uw(a, P, o);
+            real dot = (real)0;
+            int j = 0;
+#pragma unroll
+            for (int k = 0; k < TH_NUM_UIMG; ++k) {
+#pragma unroll
+                for (int ch = 0; ch < TH_UIMG[k].channels; ++ch, ++j) {
+                    const long long off = TH_UIMG[k].offset + idx.lin * TH_UIMG[k].channels + ch;
+                    const real pv = in[off];
+                    real val = o[j];
+#if TH_LM
+                    val += V.CtC[off] * pv;
+#endif
+                    out[off] = val;
+                    dot += pv * val;
+                }
+            }
+            acc[0] = (double)dot;
+        }
+    }
+    if (which) return;
+    double tot[1];
+    if (th_grid_reduce<1>(acc, tot, partials, &S->ticket[1])) {
+        if (threadIdx.x + threadIdx.y + threadIdx.z == 0) S->aD = tot[0];
+    }
+}
+#endif  // TH_AT_OUTPUT
+
+// ================================================================== flat vector kernels
+// Excluded unknowns hold zeros in every solver vector (written by the init kernels), so
+// these streaming kernels need no mask: 0 stays 0 and contributes 0 to every dot product.
+extern "C" __global__ void __launch_bounds__(TH_BLOCK)
+th_step2(const __grid_constant__ Vecs V, ThScalars* S, double* partials) {
+    if (S->done) return;
+    const real alpha = th_alpha(S);
+    double acc[2] = {0.0, 0.0};
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < TH_NUNK; i += (long long)gridDim.x * blockDim.x) {
+        const real p = V.p[i];
+        const real delta = V.delta[i] + alpha * p;
+        V.delta[i] = delta;
+        const real r = V.r[i] - alpha * V.Ap[i];
+        V.r[i] = r;
+        const real z = TH_USEPRE ? V.pre[i] * r : r;
+        V.z[i] = z;
+        acc[0] += (double)(z * r);
+#if TH_LM
+        acc[1] += (double)((real)0.5 * (delta * (r + V.b[i])));
+#endif
+    }
+    double tot[2];
+    if (th_grid_reduce<2>(acc, tot, partials, &S->ticket[2])) {
+        if (threadIdx.x == 0) { S->rz[(S->it + 1) & 1] = tot[0]; S->q = tot[1]; }
+    }
+}
+
+extern "C" __global__ void __launch_bounds__(TH_BLOCK)
+th_step2_first(const __grid_constant__ Vecs V, ThScalars* S) {
+    if (S->done) return;
+    const real alpha = th_alpha(S);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < TH_NUNK; i += (long long)gridDim.x * blockDim.x)
+        V.delta[i] = V.delta[i] + alpha * V.p[i];
+}
+
+// r = b - A delta; add_ctc: A delta still lacks the CtC*delta term (residualwise / materialized schedules)
+extern "C" __global__ void __launch_bounds__(TH_BLOCK)
+th_step2_second(const __grid_constant__ Vecs V, ThScalars* S, double* partials, int add_ctc) {
+    if (S->done) return;
+    double acc[2] = {0.0, 0.0};
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < TH_NUNK; i += (long long)gridDim.x * blockDim.x) {
+        const real delta = V.delta[i];
+        real Ax = V.Adelta[i];
+        if (add_ctc) Ax += V.CtC[i] * delta;
+        const real b = V.b[i];
+        const real r = b - Ax;
+        V.r[i] = r;
+        const real z = TH_USEPRE ? V.pre[i] * r : r;
+        V.z[i] = z;
+        acc[0] += (double)(z * r);
+        acc[1] += (double)((real)0.5 * (delta * (r + b)));
+    }
+    double tot[2];
+    if (th_grid_reduce<2>(acc, tot, partials, &S->ticket[2])) {
+        if (threadIdx.x == 0) { S->rz[(S->it + 1) & 1] = tot[0]; S->q = tot[1]; }
+    }
+}
+
+extern "C" __global__ void __launch_bounds__(TH_BLOCK)
+th_step3(const __grid_constant__ Vecs V, ThScalars* S, real q_tolerance, ThHostFlags* hf, int epoch) {
+    if (S->done) return;
+    const real beta = th_beta(S);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < TH_NUNK; i += (long long)gridDim.x * blockDim.x)
+        V.p[i] = V.z[i] + beta * V.p[i];
+    // the last block to finish closes the iteration: numerator hand-over, LM zeta test
+    __shared__ bool last;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        last = atomicAdd(&S->ticket[3], 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (last && threadIdx.x == 0) {
+        S->ticket[3] = 0u;
+        const int it = S->it;
+        S->it = it + 1;
+        S->lin_done = it + 1;
+#if TH_LM
+        const real Q1 = (real)S->q, Q0 = (real)S->Q0;
+        if (!th_finite(Q1)) S->done = 1;
+        else {
+            const real zeta = (real)(it + 1) * (Q1 - Q0) / Q1;
+            if (!th_finite(zeta) || zeta < q_tolerance) S->done = 1;
+            else S->Q0 = (double)Q1;
+        }
+#endif
+        // progress report to the host through mapped pinned memory: lets the host stop
+        // issuing iterations after an LM early exit without ever synchronising
+        // (the reference blocks on a 4-byte cudaMemcpy every iteration, gauss_newton.t:1667)
+        if (hf) {
+            *(volatile long long*)&hf->progress = ((long long)epoch << 32) | (long long)(it + 1);
+            if (S->done) *(volatile int*)&hf->done_epoch = epoch;
+            __threadfence_system();
+        }
+    }
+}
+
+// ------------------------------------------------------------------ per-unknown-image dispatch for flat kernels
+template <int K> struct ThExclude;
+#define TH_EXCL_CASE(K) \
+    template <> struct ThExclude<K> { static __device__ __forceinline__ bool get(long long e, const Params& P) { \
+        ThIdx<th::dom_u##K> i; i.from_linear(e); GAcc<th::dom_u##K> a(i, nullptr); return th::exclude_u##K(a, P); } };
+TH_EXCL_CASE(0)
+#if TH_NUM_UIMG > 1
+TH_EXCL_CASE(1)
+#endif
+#if TH_NUM_UIMG > 2
+TH_EXCL_CASE(2)
+#endif
+#if TH_NUM_UIMG > 3
+TH_EXCL_CASE(3)
+#endif
+#if TH_NUM_UIMG > 4
+#error "more than 4 unknown images: extend TH_EXCL_CASE"
+#endif
+
+template <int K> __device__ __forceinline__ bool th_excluded_rec(long long f, const Params& P) {
+    if (f < TH_UIMG[K].offset + TH_UIMG[K].elements * TH_UIMG[K].channels)
+        return ThExclude<K>::get((f - TH_UIMG[K].offset) / TH_UIMG[K].channels, P);
+    if (K + 1 < TH_NUM_UIMG) return th_excluded_rec<(K + 1 < TH_NUM_UIMG ? K + 1 : K)>(f, P);
+    return false;
+}
+__device__ __forceinline__ bool th_excluded(long long f, const Params& P) { return th_excluded_rec<0>(f, P); }
+template <int K> __device__ __forceinline__ real* th_xptr_rec(long long f, const Params& P) {
+    if (f < TH_UIMG[K].offset + TH_UIMG[K].elements * TH_UIMG[K].channels)
+        return ((real*)P.ptr[TH_UIMG[K].ptr_slot]) + (f - TH_UIMG[K].offset);
+    if (K + 1 < TH_NUM_UIMG) return th_xptr_rec<(K + 1 < TH_NUM_UIMG ? K + 1 : K)>(f, P);
+    return nullptr;
+}
+
+// X += delta, honouring exclude so that excluded caller-owned unknowns are never written
+extern "C" __global__ void __launch_bounds__(TH_BLOCK)
+th_update(const __grid_constant__ Params P, const __grid_constant__ Vecs V) {
+    for (long long f = (long long)blockIdx.x * blockDim.x + threadIdx.x; f < TH_NUNK; f += (long long)gridDim.x * blockDim.x) {
+        if (th_excluded(f, P)) continue;
+        real* x = th_xptr_rec<0>(f, P);
+        *x = *x + V.delta[f];
+    }
+}
+// dir 0: buf = X (savePreviousUnknowns / initX); dir 1: X = buf (revertUpdate / reset_unknowns)
+extern "C" __global__ void __launch_bounds__(TH_BLOCK)
+th_copy_x(const __grid_constant__ Params P, real* buf, int dir) {
+    for (long long f = (long long)blockIdx.x * blockDim.x + threadIdx.x; f < TH_NUNK; f += (long long)gridDim.x * blockDim.x) {
+        if (th_excluded(f, P)) continue;
+        real* x = th_xptr_rec<0>(f, P);
+        if (dir) *x = buf[f]; else buf[f] = *x;
+    }
+}
+
+// ================================================================== residualwise-schedule unknown passes
+// After the scatter kernels: V.r holds -J^T F, V.pre holds diag(J^T J) (raw).
+extern "C" __global__ void __launch_bounds__(TH_BLOCK)
+th_init_finish(const __grid_constant__ Params P, const __grid_constant__ Vecs V, ThScalars* S, double* partials, int first_nonlinear) {
+    double acc[1] = {0.0};
+    for (long long f = (long long)blockIdx.x * blockDim.x + threadIdx.x; f < TH_NUNK; f += (long long)gridDim.x * blockDim.x) {
+        if (th_excluded(f, P)) { th_zero_scalar(V, f); continue; }
+        acc[0] += (double)th_init_scalar(P, V, f, -V.r[f], V.pre[f], (real)1, first_nonlinear);   // pre := 1 when off, gauss_newton.t:718-722
+    }
+    double tot[1];
+    if (th_grid_reduce<1>(acc, tot, partials, &S->ticket[0])) {
+        if (threadIdx.x == 0) th_begin_linear(S, tot[0]);
+    }
+}
+
+// which = 0: finish Ap (LM: += CtC p) and alphaDenominator; which = 1: only mask Adelta
+extern "C" __global__ void __launch_bounds__(TH_BLOCK)
+th_step1_finish(const __grid_constant__ Params P, const __grid_constant__ Vecs V, ThScalars* S, double* partials, int which) {
+    if (S->done) return;
+    double acc[1] = {0.0};
+    real* __restrict__ out = which ? V.Adelta : V.Ap;
+    for (long long f = (long long)blockIdx.x * blockDim.x + threadIdx.x; f < TH_NUNK; f += (long long)gridDim.x * blockDim.x) {
+        if (th_excluded(f, P)) { out[f] = (real)0; continue; }
+        if (which) continue;
+        const real p = V.p[f];
+        real ap = out[f];
+#if TH_LM
+        ap += V.CtC[f] * p;
+        out[f] = ap;
+#endif
+        acc[0] += (double)(p * ap);
+    }
+    if (which) return;
+    double tot[1];
+    if (th_grid_reduce<1>(acc, tot, partials, &S->ticket[1])) {
+        if (threadIdx.x == 0) S->aD = tot[0];
+    }
+}
+
+// ================================================================== per-residual-group kernels
+#define TH_GROUP_KERNELS(G)                                                                                         \
+    extern "C" __global__ void __launch_bounds__(TH_BLOCK)                                                          \
+    th_cost_g##G(const __grid_constant__ Params P, ThScalars* S, double* partials, int first) {                     \
+        ThIdx<th::dom_g##G> idx;                                                                                    \
+        double acc[1] = {0.0};                                                                                      \
+        if (idx.from_linear((long long)blockIdx.x * blockDim.x + threadIdx.x)) {                                    \
+            GAcc<th::dom_g##G> a(idx, nullptr);                                                                     \
+            acc[0] = (double)th::cost_g##G(a, P);                                                                   \
+        }                                                                                                           \
+        double tot[1];                                                                                              \
+        if (th_grid_reduce<1>(acc, tot, partials, &S->ticket[4])) {                                                 \
+            if (threadIdx.x == 0) S->cost = (first ? 0.0 : S->cost) + tot[0];                                       \
+        }                                                                                                           \
+    }                                                                                                               \
+    extern "C" __global__ void __launch_bounds__(TH_BLOCK)                                                          \
+    th_modelcost_g##G(const __grid_constant__ Params P, const __grid_constant__ Vecs V, ThScalars* S,               \
+                      double* partials, int first) {                                                                \
+        ThIdx<th::dom_g##G> idx;                                                                                    \
+        double acc[1] = {0.0};                                                                                      \
+        if (idx.from_linear((long long)blockIdx.x * blockDim.x + threadIdx.x)) {                                    \
+            GAcc<th::dom_g##G> a(idx, V.delta);                                                                     \
+            acc[0] = (double)th::modelcost_g##G(a, P);                                                              \
+        }                                                                                                           \
+        double tot[1];                                                                                              \
+        if (th_grid_reduce<1>(acc, tot, partials, &S->ticket[4])) {                                                 \
+            if (threadIdx.x == 0) S->modelcost = (first ? 0.0 : S->modelcost) + tot[0];                             \
+        }                                                                                                           \
+    }                                                                                                               \
+    extern "C" __global__ void __launch_bounds__(TH_BLOCK)                                                          \
+    th_evaljtf_g##G(const __grid_constant__ Params P, const __grid_constant__ Vecs V) {                             \
+        ThIdx<th::dom_g##G> idx;                                                                                    \
+        if (idx.from_linear((long long)blockIdx.x * blockDim.x + threadIdx.x)) {                                    \
+            GAcc<th::dom_g##G> a(idx, nullptr);                                                                     \
+            GScatter<th::dom_g##G> s(idx, V.r, V.pre);                                                              \
+            th::evalJTF_g##G(a, P, s);                                                                              \
+        }                                                                                                           \
+    }                                                                                                               \
+    extern "C" __global__ void __launch_bounds__(TH_BLOCK)                                                          \
+    th_applyjtj_g##G(const __grid_constant__ Params P, const __grid_constant__ Vecs V, const ThScalars* S, int which) { \
+        if (S->done) return;                                                                                        \
+        ThIdx<th::dom_g##G> idx;                                                                                    \
+        if (idx.from_linear((long long)blockIdx.x * blockDim.x + threadIdx.x)) {                                    \
+            GAcc<th::dom_g##G> a(idx, which ? V.delta : V.p);                                                       \
+            GScatter<th::dom_g##G> s(idx, which ? V.Adelta : V.Ap, nullptr);                                        \
+            th::applyJTJ_g##G(a, P, s);                                                                             \
+        }                                                                                                           \
+    }                                                                                                               \
+    extern "C" __global__ void __launch_bounds__(TH_BLOCK)                                                          \
+    th_residuals_g##G(const __grid_constant__ Params P, real* out) {                                                \
+        ThIdx<th::dom_g##G> idx;                                                                                    \
+        if (idx.from_linear((long long)blockIdx.x * blockDim.x + threadIdx.x)) {                                    \
+            GAcc<th::dom_g##G> a(idx, nullptr);                                                                     \
+            real r[TH_GROUPS[G].nterms];                                                                            \
+            th::residuals_g##G(a, P, r);                                                                            \
+            for (int t = 0; t < TH_GROUPS[G].nterms; ++t) out[idx.lin * TH_GROUPS[G].nterms + t] = r[t];            \
+        }                                                                                                           \
+    }                                                                                                               \
+    extern "C" __global__ void __launch_bounds__(TH_BLOCK)                                                          \
+    th_computej_g##G(const __grid_constant__ Params P, real* vals, long long* cols) {                               \
+        ThIdx<th::dom_g##G> idx;                                                                                    \
+        if (idx.from_linear((long long)blockIdx.x * blockDim.x + threadIdx.x)) {                                    \
+            GAcc<th::dom_g##G> a(idx, nullptr);                                                                     \
+            real v[TH_GROUPS[G].nnz > 0 ? TH_GROUPS[G].nnz : 1];                                                    \
+            long long c[TH_GROUPS[G].nnz > 0 ? TH_GROUPS[G].nnz : 1];                                               \
+            th::computeJ_g##G(a, P, v, c);                                                                          \
+            for (int t = 0; t < TH_GROUPS[G].nnz; ++t) {                                                            \
+                vals[idx.lin * TH_GROUPS[G].nnz + t] = v[t];                                                        \
+                cols[idx.lin * TH_GROUPS[G].nnz + t] = c[t];                                                        \
+            }                                                                                                       \
+        }                                                                                                           \
+    }
+TH_GROUP_LIST(TH_GROUP_KERNELS)

@@ -1,0 +1,142 @@
+// thallo_b200 solver skeleton, part 1: types, math, plan-wide tables.
+// Included by every generated per-energy translation unit *before* the generated
+// device functions (namespace th).  Compiled by NVRTC (no host headers available)
+// or nvcc for sm_100a.
+//
+// Reference roles replaced: API/src/util.t:152-199 (gpuMath), :203-301 (Vector),
+// API/src/precision.t:3-7 (thallo_float), thallo.t:245-258 (ProblemParameters).
+#pragma once
+
+#if TH_DOUBLE
+typedef double real;
+#else
+typedef float real;
+#endif
+typedef real th_real;
+typedef float th_float;
+typedef unsigned char th_uchar;
+typedef int th_int;
+
+#define TH_INF ((real)__int_as_float(0x7f800000))
+#define TH_NAN ((real)__int_as_float(0x7fffffff))
+#define TH_MAXD 3
+
+// Problem parameters as the generated code sees them: device pointers by slot
+// (images, unknowns, sparse index arrays) and scalar Params by slot; LM scalars
+// appended (thallo.t:1584-1589).
+struct Params {
+    void* ptr[TH_NPTR];
+    real sc[TH_NSC];
+    real trust_region_radius;
+    real radius_decrease_factor;
+    real min_lm_diagonal;
+    real max_lm_diagonal;
+};
+
+// Solver vectors (gauss_newton.t:282-309 PlanData): every one is a flat array of
+// TH_NUNK reals, unknown images back to back, AoS per element.
+struct Vecs {
+    real* delta; real* r; real* b; real* Adelta; real* z; real* p; real* Ap;
+    real* CtC; real* pre; real* SSq;
+};
+
+// Device-resident scalars.  rz[] double-buffers the CG numerator so that no
+// device-to-device copy is needed between iterations (the reference copies
+// scanBetaNumerator -> scanAlphaNumerator, gauss_newton.t:1665).
+struct ThScalars {
+    double rz[2];
+    double aD;
+    double q;
+    double Q0;
+    double cost;
+    double modelcost;
+    double spare;
+    unsigned int ticket[8];
+    int it;
+    int done;
+    int lin_done;
+    int pad;
+};
+
+// Host-visible progress flags (pinned, mapped).
+struct ThHostFlags { long long progress; int done_epoch; int pad; };
+
+struct ThUImg { int channels; long long offset; int ptr_slot; int ndim; int dim[TH_MAXD]; long long elements; };
+struct ThGroup { int ndim; int dim[TH_MAXD]; int nterms; int nnz; };
+__device__ constexpr ThUImg TH_UIMG[TH_NUM_UIMG] = TH_UIMG_TABLE;
+__device__ constexpr ThGroup TH_GROUPS[TH_NGROUPS] = TH_GROUP_TABLE;
+__device__ constexpr long long TH_DIMS[TH_NDIMS] = TH_DIM_SIZES;
+
+// ---- math (IEEE-accurate device functions; no fast-math)
+__device__ __forceinline__ float th_sqrt(float x) { return sqrtf(x); }
+__device__ __forceinline__ double th_sqrt(double x) { return sqrt(x); }
+__device__ __forceinline__ float th_sin(float x) { return sinf(x); }
+__device__ __forceinline__ double th_sin(double x) { return sin(x); }
+__device__ __forceinline__ float th_cos(float x) { return cosf(x); }
+__device__ __forceinline__ double th_cos(double x) { return cos(x); }
+__device__ __forceinline__ float th_tan(float x) { return tanf(x); }
+__device__ __forceinline__ double th_tan(double x) { return tan(x); }
+__device__ __forceinline__ float th_exp(float x) { return expf(x); }
+__device__ __forceinline__ double th_exp(double x) { return exp(x); }
+__device__ __forceinline__ float th_log(float x) { return logf(x); }
+__device__ __forceinline__ double th_log(double x) { return log(x); }
+__device__ __forceinline__ float th_abs(float x) { return x >= 0.0f ? x : -x; }     // ad.t:810
+__device__ __forceinline__ double th_abs(double x) { return x >= 0.0 ? x : -x; }
+__device__ __forceinline__ float th_asin(float x) { return asinf(x); }
+__device__ __forceinline__ double th_asin(double x) { return asin(x); }
+__device__ __forceinline__ float th_acos(float x) { return acosf(x); }
+__device__ __forceinline__ double th_acos(double x) { return acos(x); }
+__device__ __forceinline__ float th_atan(float x) { return atanf(x); }
+__device__ __forceinline__ double th_atan(double x) { return atan(x); }
+__device__ __forceinline__ float th_sinh(float x) { return sinhf(x); }
+__device__ __forceinline__ double th_sinh(double x) { return sinh(x); }
+__device__ __forceinline__ float th_cosh(float x) { return coshf(x); }
+__device__ __forceinline__ double th_cosh(double x) { return cosh(x); }
+__device__ __forceinline__ float th_tanh(float x) { return tanhf(x); }
+__device__ __forceinline__ double th_tanh(double x) { return tanh(x); }
+__device__ __forceinline__ float th_pow(float x, float y) { return powf(x, y); }
+__device__ __forceinline__ double th_pow(double x, double y) { return pow(x, y); }
+__device__ __forceinline__ float th_fmin(float a, float b) { return fminf(a, b); }
+__device__ __forceinline__ double th_fmin(double a, double b) { return fmin(a, b); }
+__device__ __forceinline__ float th_fmax(float a, float b) { return fmaxf(a, b); }
+__device__ __forceinline__ double th_fmax(double a, double b) { return fmax(a, b); }
+__device__ __forceinline__ float th_floor(float x) { return floorf(x); }
+__device__ __forceinline__ double th_floor(double x) { return floor(x); }
+__device__ __forceinline__ float th_ceil(float x) { return ceilf(x); }
+__device__ __forceinline__ double th_ceil(double x) { return ceil(x); }
+__device__ __forceinline__ bool th_finite(float x) { return isfinite(x); }
+__device__ __forceinline__ bool th_finite(double x) { return isfinite(x); }
+
+// integer power by repeated multiplication (ad.t:737-760 genpow)
+template <int N> __device__ __forceinline__ real th_powi(real a) {
+    real r = (real)1;
+#pragma unroll
+    for (int i = 0; i < N; ++i) r = r * a;
+    return r;
+}
+
+// ---- element loads: AoS pixels; 2- and 4-channel pixels are loaded as vectors
+// (thallo.t:758,788-797), everything else scalar by scalar.
+template <class CT, int C, int CH> struct ThLoad {
+    static __device__ __forceinline__ real ld(const void* base, long long e) {
+        return (real)__ldg(((const CT*)base) + e * C + CH);
+    }
+};
+template <int CH> struct ThLoad<float, 2, CH> {
+    static __device__ __forceinline__ real ld(const void* base, long long e) {
+        const float2 v = __ldg(((const float2*)base) + e);
+        return (real)(CH == 0 ? v.x : v.y);
+    }
+};
+template <int CH> struct ThLoad<float, 4, CH> {
+    static __device__ __forceinline__ real ld(const void* base, long long e) {
+        const float4 v = __ldg(((const float4*)base) + e);
+        return (real)(CH == 0 ? v.x : (CH == 1 ? v.y : (CH == 2 ? v.z : v.w)));
+    }
+};
+template <int CH> struct ThLoad<double, 2, CH> {
+    static __device__ __forceinline__ real ld(const void* base, long long e) {
+        const double2 v = __ldg(((const double2*)base) + e);
+        return (real)(CH == 0 ? v.x : v.y);
+    }
+};

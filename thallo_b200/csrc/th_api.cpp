@@ -1,0 +1,208 @@
+// C ABI of thallo_b200: the twelve Thallo.h entry points (reference
+// API/release/include/Thallo.h:41-106, forwarders createwrapper.t:226-232) plus the
+// extension seam declared in include/thallo_b200.h.
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <sstream>
+#include <string>
+#include <vector>
+
+#include "../../include/thallo_b200.h"
+#include "th_plan.h"
+
+using namespace thallo;
+
+struct Thallo_Problem {
+    std::string filename, kind;
+    bool from_source = false;
+    std::string descriptor, source;
+    bool deleted = false;
+};
+struct Thallo_State {
+    StateOptions opts;
+    std::vector<Thallo_Problem*> problems;
+};
+struct Thallo_Plan {
+    Plan* plan;
+};
+
+static thread_local std::string g_last_error;
+static void set_error(const std::string& s) {
+    g_last_error = s;
+    fprintf(stderr, "thallo_b200: %s\n", s.c_str());
+}
+
+static std::string read_all(const std::string& path) {
+    std::ifstream f(path, std::ios::binary);
+    std::stringstream ss;
+    ss << f.rdbuf();
+    return ss.str();
+}
+
+// Runs the energy front end as a child process:  <python> -m thallo_b200.frontend ...
+// (the reference evaluates the .t file inside its embedded Lua VM at ProblemPlan time,
+// thallo.t:1359-1373,1384-1434; we have no VM in the library, so the front end is a tool).
+static bool run_frontend(const Thallo_Problem* pr, const StateOptions& o, const unsigned int* dims, int ndims,
+                         std::string& desc, std::string& src, int* ndims_out) {
+    const char* py = getenv("THALLO_B200_PYTHON");
+    std::string root = getenv("THALLO_B200_ROOT") ? getenv("THALLO_B200_ROOT") : library_dir() + "/../..";
+    char tmpl[] = "/tmp/thallo_b200_XXXXXX";
+    if (!mkdtemp(tmpl)) { set_error("mkdtemp failed"); return false; }
+    std::string out(tmpl);
+    std::ostringstream cmd;
+    cmd << "PYTHONPATH='" << root << "':\"$PYTHONPATH\" " << (py ? py : "python3") << " -m thallo_b200.frontend"
+        << " --energy '" << pr->filename << "' --kind " << pr->kind << " --double " << (o.init.doublePrecision ? 1 : 0)
+        << " --out '" << out << "'";
+    if (ndims_out) cmd << " --query-ndims";
+    else {
+        cmd << " --dims ";
+        for (int i = 0; i < ndims; ++i) cmd << (i ? "," : "") << dims[i];
+    }
+    if (getenv("THALLO_LM_AS_COMMITTED")) cmd << " --lm-as-committed";
+    cmd << " > '" << out << "/log.txt' 2>&1";
+    int rc = system(cmd.str().c_str());
+    bool ok = false;
+    if (rc != 0) {
+        set_error("energy front end failed for '" + pr->filename + "':\n" + read_all(out + "/log.txt"));
+    } else if (ndims_out) {
+        *ndims_out = atoi(read_all(out + "/ndims.txt").c_str());
+        ok = *ndims_out > 0;
+    } else {
+        desc = read_all(out + "/plan.desc");
+        src = read_all(out + "/energy.cu");
+        ok = !desc.empty() && !src.empty();
+        if (!ok) set_error("energy front end produced no output for '" + pr->filename + "'");
+    }
+    std::string rm = "rm -rf '" + out + "'";
+    if (system(rm.c_str()) != 0) {}
+    return ok;
+}
+
+extern "C" {
+
+Thallo_State* Thallo_NewState(Thallo_InitializationParameters params) {
+    Thallo_State* s = new Thallo_State();
+    s->opts.init = params;
+    if (params.cpuOnly) set_error("cpuOnly=1 requested: thallo_b200 has no CPU backend; plans will run on the GPU");
+    return s;
+}
+
+Thallo_Problem* Thallo_ProblemDefine(Thallo_State* state, const char* filename, const char* solverkind) {
+    if (!state || !filename || !solverkind) return nullptr;
+    if (strcmp(solverkind, "gauss_newton") != 0 && strcmp(solverkind, "levenberg_marquardt") != 0) {
+        set_error(std::string("unknown solver kind '") + solverkind + "' (thallo.t:74)");
+        return nullptr;
+    }
+    Thallo_Problem* p = new Thallo_Problem();
+    p->filename = filename;
+    p->kind = solverkind;
+    state->problems.push_back(p);
+    return p;
+}
+
+Thallo_Problem* ThalloB200_ProblemDefineFromSource(Thallo_State* state, const char* descriptor, const char* cuda_source,
+                                                   const char* solverkind) {
+    if (!state || !descriptor || !cuda_source || !solverkind) return nullptr;
+    Thallo_Problem* p = new Thallo_Problem();
+    p->from_source = true;
+    p->descriptor = descriptor;
+    p->source = cuda_source;
+    p->kind = solverkind;
+    state->problems.push_back(p);
+    return p;
+}
+
+void Thallo_ProblemDelete(Thallo_State* state, Thallo_Problem* problem) {
+    (void)state;
+    if (problem) problem->deleted = true;   // tombstone only, like thallo.t:5954-5961
+}
+
+Thallo_Plan* Thallo_ProblemPlan(Thallo_State* state, Thallo_Problem* problem, unsigned int* dimensions) {
+    if (!state || !problem || problem->deleted) return nullptr;
+    std::string desc_text, src;
+    if (problem->from_source) {
+        desc_text = problem->descriptor;
+        src = problem->source;
+    } else {
+        int nd = 0;
+        if (!run_frontend(problem, state->opts, nullptr, 0, desc_text, src, &nd)) return nullptr;
+        if (!run_frontend(problem, state->opts, dimensions, nd, desc_text, src, nullptr)) return nullptr;
+    }
+    PlanDesc d;
+    std::string err;
+    if (!parse_descriptor(desc_text, d, err)) { set_error(err); return nullptr; }
+    if (problem->from_source && dimensions) {
+        for (size_t i = 0; i < d.dims.size(); ++i)
+            if ((long long)dimensions[i] != d.dims[i]) {
+                set_error("dimensions passed to Thallo_ProblemPlan differ from the ones the energy was lowered for");
+                return nullptr;
+            }
+    }
+    if ((d.is_double ? 1 : 0) != (state->opts.init.doublePrecision ? 1 : 0)) {
+        set_error("energy was lowered for a different precision than the state's doublePrecision");
+        return nullptr;
+    }
+    Plan* plan = new Plan(&state->opts, d, src);
+    if (!plan->ok()) {
+        set_error(plan->error());
+        delete plan;
+        return nullptr;
+    }
+    Thallo_Plan* h = new Thallo_Plan();
+    h->plan = plan;
+    return h;
+}
+
+void Thallo_PlanFree(Thallo_State* state, Thallo_Plan* plan) {
+    (void)state;
+    if (!plan) return;
+    delete plan->plan;
+    delete plan;
+}
+
+void Thallo_SetSolverParameter(Thallo_State*, Thallo_Plan* plan, const char* name, void* value) {
+    if (plan && name && value) plan->plan->set_parameter(name, value);
+}
+void Thallo_GetSolverParameter(Thallo_State*, Thallo_Plan* plan, const char* name, void* value) {
+    if (plan && name && value) plan->plan->get_parameter(name, value);
+}
+void Thallo_ProblemSolve(Thallo_State*, Thallo_Plan* plan, void** problemparams) { plan->plan->solve(problemparams); }
+void Thallo_ProblemInit(Thallo_State*, Thallo_Plan* plan, void** problemparams) { plan->plan->init(problemparams); }
+int Thallo_ProblemStep(Thallo_State*, Thallo_Plan* plan, void** problemparams) { return plan->plan->step(problemparams); }
+double Thallo_ProblemCurrentCost(Thallo_State*, Thallo_Plan* plan) { return plan->plan->cost(); }
+void Thallo_GetPerformanceSummary(Thallo_State*, Thallo_Plan* plan, Thallo_PerformanceSummary* summary) {
+    if (plan && summary) plan->plan->summary(summary);
+}
+
+int ThalloB200_CompileOnly(const char* cuda_source, char* log, unsigned long log_capacity, unsigned long* cubin_size) {
+    std::vector<char> cubin;
+    std::string clog;
+    const bool ok = compile_cubin(cuda_source ? cuda_source : "", skeleton_dir(), cubin, clog);
+    if (log && log_capacity) {
+        strncpy(log, clog.c_str(), log_capacity - 1);
+        log[log_capacity - 1] = 0;
+    }
+    if (cubin_size) *cubin_size = (unsigned long)cubin.size();
+    return ok ? 0 : 1;
+}
+
+void ThalloB200_SetStream(Thallo_State* state, void* cuda_stream) {
+    if (state) state->opts.stream = (cudaStream_t)cuda_stream;
+}
+unsigned long long ThalloB200_PlanLaunchCount(Thallo_State*, Thallo_Plan* plan) { return plan ? plan->plan->launches : 0; }
+int ThalloB200_PlanLastLinearIterations(Thallo_State*, Thallo_Plan* plan) { return plan ? plan->plan->last_linear_iterations : 0; }
+unsigned long long ThalloB200_PlanTotalLinearIterations(Thallo_State*, Thallo_Plan* plan) {
+    return plan ? plan->plan->total_linear_iterations : 0;
+}
+long long ThalloB200_PlanReadVector(Thallo_State*, Thallo_Plan* plan, const char* name, void* host_dst, long long count) {
+    return plan ? plan->plan->read_vector(name, host_dst, count) : 0;
+}
+const char* ThalloB200_LastError(void) { return g_last_error.c_str(); }
+const char* ThalloB200_Version(void) { return "thallo_b200 0.1.0 (sm_100a)"; }
+
+}  // extern "C"

@@ -1,0 +1,511 @@
+#include "th_plan.h"
+
+#include <sched.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <sstream>
+
+namespace thallo {
+
+// ------------------------------------------------------------------ errors (exit like the reference, cuda_util.t:103-118)
+static void fatal_cuda(cudaError_t e, const char* what) {
+    fprintf(stderr, "thallo_b200: CUDA error %d (%s) in %s\n", (int)e, cudaGetErrorString(e), what);
+    exit((int)e ? (int)e : 1);
+}
+#define CD(x) do { cudaError_t _e = (x); if (_e != cudaSuccess) fatal_cuda(_e, #x); } while (0)
+static void fatal_cu(CUresult r, const char* what) {
+    const char* s = nullptr;
+    if (DriverApi::get().GetErrorString) DriverApi::get().GetErrorString(r, &s);
+    fprintf(stderr, "thallo_b200: driver error %d (%s) in %s\n", (int)r, s ? s : "?", what);
+    exit(1);
+}
+#define CU(x) do { CUresult _r = (x); if (_r != CUDA_SUCCESS) fatal_cu(_r, #x); } while (0)
+
+// ------------------------------------------------------------------ descriptor
+bool parse_descriptor(const std::string& text, PlanDesc& d, std::string& err) {
+    std::istringstream in(text);
+    std::string line;
+    while (std::getline(in, line)) {
+        if (line.empty()) continue;
+        std::istringstream ls(line);
+        std::string key;
+        ls >> key;
+        if (key == "name") ls >> d.name;
+        else if (key == "kind") ls >> d.kind;
+        else if (key == "lm") { int v; ls >> v; d.lm = v != 0; }
+        else if (key == "real") { std::string v; ls >> v; d.is_double = (v == "double"); }
+        else if (key == "usepreconditioner") { int v; ls >> v; d.usepre = v != 0; }
+        else if (key == "schedule") { ls >> d.schedule; d.at_output = (d.schedule == "at_output"); }
+        else if (key == "dims") { int n; ls >> n; d.dims.resize(n); for (auto& x : d.dims) ls >> x; }
+        else if (key == "nunk") ls >> d.nunk;
+        else if (key == "ptrs") { int n; ls >> n; d.ptr_pidx.resize(n); for (auto& x : d.ptr_pidx) ls >> x; }
+        else if (key == "scalars") {
+            int n; ls >> n;
+            for (int i = 0; i < n; ++i) {
+                std::string tok; ls >> tok;
+                size_t c = tok.find(':');
+                if (c == std::string::npos) { err = "bad scalar token " + tok; return false; }
+                d.scalars.push_back({atoi(tok.substr(0, c).c_str()), tok.substr(c + 1)});
+            }
+        } else if (key == "unknown") {
+            UnknownDesc u; int nd;
+            ls >> u.name >> u.channels >> u.offset >> u.pidx >> u.elements >> nd;
+            u.dims.resize(nd); for (auto& x : u.dims) ls >> x;
+            d.unknowns.push_back(u);
+        } else if (key == "group") {
+            GroupDesc g; int nd;
+            ls >> g.name >> g.count >> g.nterms >> g.materialize >> g.nnz >> nd;
+            g.domain.resize(nd); for (auto& x : g.domain) ls >> x;
+            std::string bar; ls >> bar;
+            int v; while (ls >> v) g.row_nnz.push_back(v);
+            d.groups.push_back(g);
+        } else if (key == "U") ls >> d.U;
+        else if (key == "uw_dims") { int n; ls >> n; d.uw_dims.resize(n); for (auto& x : d.uw_dims) ls >> x; }
+        if (ls.fail() && !ls.eof()) { err = "malformed descriptor line: " + line; return false; }
+    }
+    if (d.nunk <= 0 || d.unknowns.empty() || d.groups.empty()) { err = "descriptor lacks unknowns or residual groups"; return false; }
+    if (d.kind != "gauss_newton" && d.kind != "levenberg_marquardt") { err = "solver kind must be gauss_newton or levenberg_marquardt"; return false; }
+    return true;
+}
+
+// ------------------------------------------------------------------ plan
+static const char* kVecNames[12] = {"delta", "r", "b", "Adelta", "z", "p", "Ap_X", "CtC", "preconditioner", "SSq", "prevX", "initX"};
+enum { V_DELTA, V_R, V_B, V_ADELTA, V_Z, V_P, V_AP, V_CTC, V_PRE, V_SSQ, V_PREVX, V_INITX };
+
+void Plan::log(const char* fmt, ...) const {
+    if (opts_->init.verbosityLevel <= 0) return;
+    va_list ap;
+    va_start(ap, fmt);
+    vprintf(fmt, ap);
+    va_end(ap);
+}
+
+Plan::Plan(const StateOptions* opts, const PlanDesc& desc, const std::string& source) : opts_(opts), d_(desc) {
+    real_size_ = d_.is_double ? 8 : 4;
+    const DriverApi& api = DriverApi::get();
+    if (!api.ok) { error_ = "no CUDA device / driver available: thallo_b200 has no CPU fallback"; return; }
+    std::vector<char> cubin;
+    std::string clog;
+    if (!compile_cubin(source, skeleton_dir(), cubin, clog)) { error_ = "NVRTC compilation failed:\n" + clog; return; }
+    if (opts_->init.verbosityLevel > 1 && !clog.empty()) printf("%s\n", clog.c_str());
+    CUresult r = api.ModuleLoadData(&module_, cubin.data());
+    if (r != CUDA_SUCCESS) { error_ = "cuModuleLoadData failed (" + std::to_string((int)r) + ")"; return; }
+
+    // solver vectors: one allocation, 12 unknown-sized vectors (gauss_newton.t:1963-2071)
+    vec_stride_ = ((size_t)d_.nunk * real_size_ + 255) / 256 * 256;
+    CD(cudaMalloc((void**)&vec_block_, vec_stride_ * 12));
+    CD(cudaMemsetAsync(vec_block_, 0, vec_stride_ * 12, stream()));
+    for (int i = 0; i < 12; ++i) vecs_[i] = vec_block_ + vec_stride_ * i;
+    CD(cudaMalloc(&d_scalars_, sizeof(HScalars)));
+    CD(cudaMemsetAsync(d_scalars_, 0, sizeof(HScalars), stream()));
+    CD(cudaHostAlloc((void**)&h_scalars_, sizeof(HScalars), cudaHostAllocDefault));
+    CD(cudaHostAlloc((void**)&h_flags_, sizeof(HHostFlags), cudaHostAllocMapped));
+    h_flags_->progress = 0; h_flags_->done_epoch = -1;
+    CD(cudaHostGetDevicePointer(&d_flags_, (void*)h_flags_, 0));
+
+    int sms = 148;
+    int dev = 0;
+    CD(cudaGetDevice(&dev));
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const long long want = (d_.nunk + 255) / 256;
+    flat_grid_ = (unsigned)std::max(1LL, std::min<long long>(want, (long long)sms * 8));
+    // partial sums: up to 2 values per block of the largest grid
+    long long maxblocks = flat_grid_;
+    if (d_.at_output) {
+        long long b = 1;
+        if (d_.uw_dims.size() == 1) b = (d_.uw_dims[0] + 255) / 256;
+        else if (d_.uw_dims.size() == 2) b = ((d_.uw_dims[0] + 31) / 32) * ((d_.uw_dims[1] + 7) / 8);
+        else b = ((d_.uw_dims[0] + 7) / 8) * ((d_.uw_dims[1] + 7) / 8) * ((d_.uw_dims[2] + 3) / 4);
+        maxblocks = std::max(maxblocks, b);
+    }
+    for (auto& g : d_.groups) maxblocks = std::max(maxblocks, (g.count + 255) / 256);
+    CD(cudaMalloc((void**)&d_partials_, sizeof(double) * 2 * (size_t)maxblocks));
+
+    // kernel-argument images of the device structs
+    const size_t nptr = std::max<size_t>(1, d_.ptr_pidx.size()), nsc = std::max<size_t>(1, d_.scalars.size());
+    size_t psz = nptr * 8 + (nsc + 4) * real_size_;
+    psz = (psz + 7) / 8 * 8;
+    params_buf_.assign(psz, 0);
+    vecs_buf_.assign(10 * sizeof(void*), 0);
+    memcpy(vecs_buf_.data(), vecs_, 10 * sizeof(void*));
+    sp_ = SolverParameters();
+    ok_ = true;
+}
+
+Plan::~Plan() {
+    if (vec_block_) cudaFree(vec_block_);
+    if (d_scalars_) cudaFree(d_scalars_);
+    if (d_partials_) cudaFree(d_partials_);
+    if (h_scalars_) cudaFreeHost(h_scalars_);
+    if (h_flags_) cudaFreeHost((void*)h_flags_);
+    for (auto* v : {&ev_total_, &ev_iter_, &ev_setup_, &ev_linear_, &ev_finish_})
+        for (auto& s : *v) { if (s.a) cudaEventDestroy(s.a); if (s.b) cudaEventDestroy(s.b); }
+    if (module_ && DriverApi::get().ok) DriverApi::get().ModuleUnload(module_);
+}
+
+CUfunction Plan::fn(const std::string& name) {
+    auto it = fns_.find(name);
+    if (it != fns_.end()) return it->second;
+    CUfunction f = nullptr;
+    CUresult r = DriverApi::get().ModuleGetFunction(&f, module_, name.c_str());
+    if (r != CUDA_SUCCESS) {
+        fprintf(stderr, "thallo_b200: kernel %s missing from the compiled plan\n", name.c_str());
+        exit(1);
+    }
+    fns_[name] = f;
+    return f;
+}
+
+void Plan::launch(CUfunction f, dim3 grid, dim3 block, void** args) {
+    CU(DriverApi::get().LaunchKernel(f, grid.x, grid.y, grid.z, block.x, block.y, block.z, 0, (CUstream)stream(), args, nullptr));
+    ++launches;
+}
+void Plan::launch_flat(CUfunction f, void** args) { launch(f, dim3(flat_grid_), dim3(256), args); }
+void Plan::launch_uw(CUfunction f, void** args) {
+    const auto& u = d_.uw_dims;
+    if (u.size() == 1) launch(f, dim3((unsigned)((u[0] + 255) / 256)), dim3(256), args);
+    else if (u.size() == 2) launch(f, dim3((unsigned)((u[0] + 31) / 32), (unsigned)((u[1] + 7) / 8)), dim3(32, 8), args);
+    else launch(f, dim3((unsigned)((u[0] + 7) / 8), (unsigned)((u[1] + 7) / 8), (unsigned)((u[2] + 3) / 4)), dim3(8, 8, 4), args);
+}
+void Plan::launch_group(CUfunction f, int g, void** args) {
+    launch(f, dim3((unsigned)((d_.groups[g].count + 255) / 256)), dim3(256), args);
+}
+void Plan::clear(void* p) { CD(cudaMemsetAsync(p, 0, (size_t)d_.nunk * real_size_, stream())); }
+
+// util.initParameters, util.t:609-643: images / sparse = device pointers, scalars read through host pointers
+void Plan::bind(void** params) {
+    char* buf = params_buf_.data();
+    const size_t nptr = std::max<size_t>(1, d_.ptr_pidx.size()), nsc = std::max<size_t>(1, d_.scalars.size());
+    for (size_t i = 0; i < d_.ptr_pidx.size(); ++i) memcpy(buf + 8 * i, &params[d_.ptr_pidx[i]], 8);
+    char* sc = buf + 8 * nptr;
+    for (size_t i = 0; i < d_.scalars.size(); ++i) {
+        const void* hp = params[d_.scalars[i].pidx];
+        double v = 0;
+        const std::string& t = d_.scalars[i].ctype;
+        if (t == "float") v = *(const float*)hp;
+        else if (t == "double") v = *(const double*)hp;
+        else if (t == "int") v = *(const int*)hp;
+        else if (t == "uchar") v = *(const unsigned char*)hp;
+        if (d_.is_double) memcpy(sc + 8 * i, &v, 8);
+        else { float f = (float)v; memcpy(sc + 4 * i, &f, 4); }
+    }
+    (void)nsc;
+    write_lm_params();
+}
+void Plan::write_lm_params() {
+    const size_t nptr = std::max<size_t>(1, d_.ptr_pidx.size()), nsc = std::max<size_t>(1, d_.scalars.size());
+    char* lm = params_buf_.data() + 8 * nptr + real_size_ * nsc;
+    const double v[4] = {radius_, decrease_factor_, sp_.min_lm_diagonal, sp_.max_lm_diagonal};
+    for (int i = 0; i < 4; ++i) {
+        if (d_.is_double) memcpy(lm + 8 * i, &v[i], 8);
+        else { float f = (float)v[i]; memcpy(lm + 4 * i, &f, 4); }
+    }
+}
+
+void Plan::read_scalars() {
+    CD(cudaMemcpyAsync(h_scalars_, d_scalars_, sizeof(HScalars), cudaMemcpyDeviceToHost, stream()));
+    CD(cudaStreamSynchronize(stream()));
+}
+
+// computeCost, gauss_newton.t:1128-1136
+double Plan::compute_cost() {
+    void* P = params_buf_.data();
+    for (size_t g = 0; g < d_.groups.size(); ++g) {
+        int first = g == 0;
+        void* args[] = {P, &d_scalars_, &d_partials_, &first};
+        launch_group(fn("th_cost_g" + std::to_string(g)), (int)g, args);
+    }
+    read_scalars();
+    return round_real(h_scalars_->cost);
+}
+
+void Plan::span_begin(Span& s) {
+    if (!s.a) { CD(cudaEventCreate(&s.a)); CD(cudaEventCreate(&s.b)); }
+    CD(cudaEventRecord(s.a, stream()));
+}
+void Plan::span_end(Span& s, std::vector<Span>& into) {
+    CD(cudaEventRecord(s.b, stream()));
+    into.push_back(s);
+    s = Span();
+}
+
+static void accumulate(Thallo_PerformanceEntry& e, const std::vector<double>& ms) {
+    e = Thallo_PerformanceEntry{};
+    if (ms.empty()) return;
+    e.count = (unsigned)ms.size();
+    double mn = ms[0], mx = ms[0], sum = 0;
+    for (double v : ms) { mn = std::min(mn, v); mx = std::max(mx, v); sum += v; }
+    const double mean = sum / ms.size();
+    double var = 0;
+    for (double v : ms) var += (v - mean) * (v - mean);
+    e.minMS = mn; e.maxMS = mx; e.meanMS = mean;
+    e.stddevMS = ms.size() > 1 ? std::sqrt(var / (ms.size() - 1)) : 0.0;
+}
+// Timer:evaluate, util.t:516-541: five buckets
+void Plan::evaluate_timers() {
+    struct B { std::vector<Span>* v; Thallo_PerformanceEntry* e; } bs[] = {
+        {&ev_total_, &perf_.total}, {&ev_iter_, &perf_.nonlinearIteration}, {&ev_setup_, &perf_.nonlinearSetup},
+        {&ev_linear_, &perf_.linearSolve}, {&ev_finish_, &perf_.nonlinearResolve}};
+    for (auto& b : bs) {
+        std::vector<double> ms;
+        for (auto& s : *b.v) {
+            float t = 0;
+            if (cudaEventElapsedTime(&t, s.a, s.b) == cudaSuccess) ms.push_back(t);
+            cudaEventDestroy(s.a); cudaEventDestroy(s.b);
+        }
+        b.v->clear();
+        accumulate(*b.e, ms);
+    }
+}
+
+// init, gauss_newton.t:1166-1198
+void Plan::init(void** params) {
+    finalized_ = false;
+    initialized_ = true;
+    t_start_ = std::chrono::steady_clock::now();
+    for (auto* v : {&ev_total_, &ev_iter_, &ev_setup_, &ev_linear_, &ev_finish_}) {
+        for (auto& s : *v) { cudaEventDestroy(s.a); cudaEventDestroy(s.b); }
+        v->clear();
+    }
+    span_begin(cur_total_);
+    sp_.nIter = 0;
+    radius_ = round_real(sp_.trust_region_radius);
+    decrease_factor_ = round_real(sp_.radius_decrease_factor);
+    bind(params);
+    // solver vectors start from zero so that excluded unknowns stay zero everywhere
+    CD(cudaMemsetAsync(vec_block_, 0, vec_stride_ * 10, stream()));
+    prev_cost_ = compute_cost();
+    {   // initX = X (copyUnknownwise)
+        int dir = 0;
+        void* args[] = {params_buf_.data(), &vecs_[V_INITX], &dir};
+        launch_flat(fn("th_copy_x"), args);
+    }
+    log("Initial cost: %g\nInitial cost x 2: %g\n", prev_cost_, 2.0 * prev_cost_);
+}
+
+// finalize, gauss_newton.t:1200-1212
+void Plan::finalize() {
+    prev_cost_ = compute_cost();
+    log("final cost=%g\n", prev_cost_);
+    CD(cudaStreamSynchronize(stream()));
+    if (cur_total_.a) span_end(cur_total_, ev_total_);
+    CD(cudaStreamSynchronize(stream()));
+    evaluate_timers();
+    finalized_ = true;
+}
+
+double Plan::cost() {   // gauss_newton.t:1787-1793
+    if (!finalized_) prev_cost_ = compute_cost();
+    return prev_cost_;
+}
+
+void Plan::linear_iteration(int l) {
+    void* P = params_buf_.data();
+    void* V = vecs_buf_.data();
+    int zero = 0, one = 1;
+    if (d_.at_output) {
+        void* a[] = {P, V, &d_scalars_, &d_partials_, &zero};
+        launch_uw(fn("th_step1_uw"), a);
+    } else {
+        clear(vecs_[V_AP]);
+        for (size_t g = 0; g < d_.groups.size(); ++g) {
+            if (d_.groups[g].materialize) continue;   // TODO(next): CSR path for materialized groups
+            void* a[] = {P, V, &d_scalars_, &zero};
+            launch_group(fn("th_applyjtj_g" + std::to_string(g)), (int)g, a);
+        }
+        void* a[] = {P, V, &d_scalars_, &d_partials_, &zero};
+        launch_flat(fn("th_step1_finish"), a);
+    }
+    if (d_.lm && ((l + 1) % sp_.residual_reset_period) == 0) {   // gauss_newton.t:1653-1660
+        {
+            void* a[] = {V, &d_scalars_};
+            launch_flat(fn("th_step2_first"), a);
+        }
+        int add_ctc = 0;
+        if (d_.at_output) {
+            void* a[] = {P, V, &d_scalars_, &d_partials_, &one};
+            launch_uw(fn("th_step1_uw"), a);
+        } else {
+            clear(vecs_[V_ADELTA]);
+            for (size_t g = 0; g < d_.groups.size(); ++g) {
+                if (d_.groups[g].materialize) continue;
+                void* a[] = {P, V, &d_scalars_, &one};
+                launch_group(fn("th_applyjtj_g" + std::to_string(g)), (int)g, a);
+            }
+            void* a[] = {P, V, &d_scalars_, &d_partials_, &one};
+            launch_flat(fn("th_step1_finish"), a);
+            add_ctc = 1;
+        }
+        void* a[] = {V, &d_scalars_, &d_partials_, &add_ctc};
+        launch_flat(fn("th_step2_second"), a);
+    } else {
+        void* a[] = {V, &d_scalars_, &d_partials_};
+        launch_flat(fn("th_step2"), a);
+    }
+    {
+        float qf = sp_.q_tolerance;
+        double qd = sp_.q_tolerance;
+        void* a[] = {V, &d_scalars_, d_.is_double ? (void*)&qd : (void*)&qf, &d_flags_, &epoch_};
+        launch_flat(fn("th_step3"), a);
+    }
+}
+
+// step, gauss_newton.t:1545-1785
+int Plan::step(void** params) {
+    bind(params);
+    if (sp_.nIter >= sp_.nIterations) { finalize(); return 0; }
+    void* P = params_buf_.data();
+    void* V = vecs_buf_.data();
+    span_begin(cur_iter_);
+    span_begin(cur_phase_);
+    ++epoch_;
+    int first = sp_.nIter == 0;
+    if (d_.at_output) {
+        void* a[] = {P, V, &d_scalars_, &d_partials_, &first};
+        launch_uw(fn("th_init_uw"), a);
+    } else {
+        clear(vecs_[V_R]);
+        clear(vecs_[V_PRE]);
+        for (size_t g = 0; g < d_.groups.size(); ++g) {
+            void* a[] = {P, V};
+            launch_group(fn("th_evaljtf_g" + std::to_string(g)), (int)g, a);
+        }
+        void* a[] = {P, V, &d_scalars_, &d_partials_, &first};
+        launch_flat(fn("th_init_finish"), a);
+    }
+    span_end(cur_phase_, ev_setup_);
+    span_begin(cur_phase_);
+    const int depth = 4;   // LM: how far the host may run ahead of the device's progress report
+    for (int l = 0; l < sp_.lIterations; ++l) {
+        if (d_.lm) {
+            bool stop = false;
+            for (;;) {
+                if (h_flags_->done_epoch == epoch_) { stop = true; break; }
+                const long long pr = h_flags_->progress;
+                const int done_iters = (int)(pr >> 32) == epoch_ ? (int)(pr & 0xffffffff) : 0;
+                if (l - done_iters < depth) break;
+                sched_yield();
+            }
+            if (stop) break;
+        }
+        linear_iteration(l);
+    }
+    span_end(cur_phase_, ev_linear_);
+    span_begin(cur_phase_);
+    int zero = 0;
+    if (d_.lm) {   // computeModelCostChange + savePreviousUnknowns, gauss_newton.t:1694-1697
+        for (size_t g = 0; g < d_.groups.size(); ++g) {
+            int f = g == 0;
+            void* a[] = {P, V, &d_scalars_, &d_partials_, &f};
+            launch_group(fn("th_modelcost_g" + std::to_string(g)), (int)g, a);
+        }
+        void* a[] = {P, &vecs_[V_PREVX], &zero};
+        launch_flat(fn("th_copy_x"), a);
+    }
+    {
+        void* a[] = {P, V};
+        launch_flat(fn("th_update"), a);   // PCGLinearUpdate
+    }
+    int ret = 1;
+    if (d_.lm) {
+        const double new_cost = compute_cost();   // also brings modelcost and lin_done back
+        last_linear_iterations = h_scalars_->lin_done;
+        total_linear_iterations += (unsigned long long)h_scalars_->lin_done;
+        const double model_cost = round_real(h_scalars_->modelcost);
+        const double model_cost_change = round_real(prev_cost_ - model_cost);
+        const double cost_change = round_real(prev_cost_ - new_cost);
+        const double relative_decrease = round_real(cost_change / model_cost_change);
+        log(" cost=%g model_cost=%g new cost=%g lin=%d rel=%g\n", prev_cost_, model_cost, new_cost, last_linear_iterations, relative_decrease);
+        if (cost_change >= 0 && relative_decrease > round_real(sp_.min_relative_decrease)) {
+            const double abs_tol = round_real(prev_cost_ * round_real(sp_.function_tolerance));
+            if (cost_change <= abs_tol) {
+                log("\nFunction tolerance reached (%g < %g), exiting\n", cost_change, abs_tol);
+                span_end(cur_phase_, ev_finish_);
+                span_end(cur_iter_, ev_iter_);
+                finalize();
+                return 0;
+            }
+            const double tmp_factor = 1.0 - std::pow(2.0 * relative_decrease - 1.0, 3.0);
+            radius_ = round_real(radius_ / std::fmax(1.0 / 3.0, tmp_factor));
+            radius_ = round_real(std::fmin(radius_, (double)round_real(sp_.max_trust_region_radius)));
+            decrease_factor_ = 2.0;
+            prev_cost_ = new_cost;
+        } else {
+            int one = 1;
+            void* a[] = {P, &vecs_[V_PREVX], &one};
+            launch_flat(fn("th_copy_x"), a);   // revertUpdate
+            radius_ = round_real(radius_ / decrease_factor_);
+            decrease_factor_ = round_real(2.0 * decrease_factor_);
+            if (radius_ < round_real(sp_.min_trust_region_radius)) {
+                log("\nTrust_region_radius is less than the min (%g), exiting\n", radius_);
+                sp_.trust_region_radius = 10e4f;   // gauss_newton.t:1741
+                span_end(cur_phase_, ev_finish_);
+                span_end(cur_iter_, ev_iter_);
+                finalize();
+                return 0;
+            }
+            log("REVERT\n");
+        }
+        sp_.trust_region_radius = (float)radius_;
+        log(" trust_region_radius=%g\n", radius_);
+    } else {
+        last_linear_iterations = sp_.lIterations;
+        total_linear_iterations += (unsigned long long)sp_.lIterations;
+    }
+    sp_.nIter += 1;
+    span_end(cur_phase_, ev_finish_);
+    span_end(cur_iter_, ev_iter_);
+    if (sp_.max_solver_time_in_seconds > 0.0f) {
+        CD(cudaStreamSynchronize(stream()));
+        const double el = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start_).count();
+        if (el > sp_.max_solver_time_in_seconds) {
+            log("\nTime exceeded max (%g > %g), exiting\n", el, (double)sp_.max_solver_time_in_seconds);
+            finalize();
+            return 0;
+        }
+    }
+    return ret;
+}
+
+void Plan::solve(void** params) {   // thallo.t:5980-5983
+    init(params);
+    while (step(params)) {}
+}
+
+// setSolverParameter / getSolverParameter, gauss_newton.t:1828-1862
+#define TH_PARAMS(X) \
+    X(min_relative_decrease, float) X(min_trust_region_radius, float) X(max_trust_region_radius, float) \
+    X(q_tolerance, float) X(function_tolerance, float) X(trust_region_radius, float) X(radius_decrease_factor, float) \
+    X(min_lm_diagonal, float) X(max_lm_diagonal, float) X(max_solver_time_in_seconds, float) \
+    X(residual_reset_period, int) X(nIter, int) X(nIterations, int) X(lIterations, int)
+
+void Plan::set_parameter(const char* name, const void* value) {
+#define X(f, T) if (strcmp(#f, name) == 0) { sp_.f = *(const T*)value; return; }
+    TH_PARAMS(X)
+#undef X
+    log("Warning: tried to set nonexistent solver parameter %s\n", name);
+}
+void Plan::get_parameter(const char* name, void* value) {
+#define X(f, T) if (strcmp(#f, name) == 0) { *(T*)value = sp_.f; return; }
+    TH_PARAMS(X)
+#undef X
+    log("Warning: tried to get nonexistent solver parameter %s\n", name);
+}
+
+long long Plan::read_vector(const char* name, void* dst, long long count) {
+    for (int i = 0; i < 12; ++i) {
+        if (strcmp(name, kVecNames[i]) == 0) {
+            const long long n = std::min<long long>(count, d_.nunk);
+            CD(cudaMemcpyAsync(dst, vecs_[i], (size_t)n * real_size_, cudaMemcpyDeviceToHost, stream()));
+            CD(cudaStreamSynchronize(stream()));
+            return n;
+        }
+    }
+    return 0;
+}
+
+}  // namespace thallo

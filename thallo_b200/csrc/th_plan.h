@@ -1,0 +1,143 @@
+// Host side of the GN/LM + PCG solver: plan data, parameter binding, the outer loop.
+// Restates the roles of reference API/src/gauss_newton.t:200-323 (SolverParameters,
+// HostData, PlanData), :1128-1212 (cost, init, finalize), :1545-1785 (step),
+// :1806-1862 (solver parameters), util.t:456-595 (Timer) -- as a C++ class driving
+// JIT-compiled kernels through the driver API.
+#pragma once
+#include <chrono>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/Thallo.h"
+#include "th_jit.h"
+
+namespace thallo {
+
+struct UnknownDesc { std::string name; int channels = 0; long long offset = 0; int pidx = 0; long long elements = 0; std::vector<int> dims; };
+struct GroupDesc { std::string name; long long count = 0; int nterms = 0; int materialize = 0; int nnz = 0; std::vector<int> domain; std::vector<int> row_nnz; };
+struct ScalarDesc { int pidx; std::string ctype; };
+
+struct PlanDesc {
+    std::string name, kind, schedule;
+    bool lm = false, is_double = false, usepre = false, at_output = false;
+    std::vector<long long> dims;
+    long long nunk = 0;
+    std::vector<int> ptr_pidx;
+    std::vector<ScalarDesc> scalars;
+    std::vector<UnknownDesc> unknowns;
+    std::vector<GroupDesc> groups;
+    int U = 0;
+    std::vector<long long> uw_dims;
+};
+bool parse_descriptor(const std::string& text, PlanDesc& d, std::string& err);
+
+struct SolverParameters {   // gauss_newton.t:200-216, defaults :41-55
+    float min_relative_decrease = 1e-3f;
+    float min_trust_region_radius = 1e-32f;
+    float max_trust_region_radius = 1e16f;
+    float q_tolerance = 0.0001f;
+    float function_tolerance = 0.000001f;
+    float trust_region_radius = 1e4f;
+    float radius_decrease_factor = 2.0f;
+    float min_lm_diagonal = 1e-6f;
+    float max_lm_diagonal = 1e32f;
+    float max_solver_time_in_seconds = 0.f;
+    int residual_reset_period = 10;
+    int nIter = 0;
+    int nIterations = 10;
+    int lIterations = 10;
+};
+
+struct StateOptions {
+    Thallo_InitializationParameters init{};
+    cudaStream_t stream = nullptr;
+};
+
+// mirrors the device structs in skeleton/thallo_prelude.cuh
+struct HScalars {
+    double rz[2], aD, q, Q0, cost, modelcost, spare;
+    unsigned int ticket[8];
+    int it, done, lin_done, pad;
+};
+struct HHostFlags { volatile long long progress; volatile int done_epoch; int pad; };
+
+class Plan {
+public:
+    Plan(const StateOptions* opts, const PlanDesc& desc, const std::string& source);
+    ~Plan();
+    bool ok() const { return ok_; }
+    const std::string& error() const { return error_; }
+
+    void init(void** params);
+    int step(void** params);
+    void solve(void** params);
+    double cost();
+    void set_parameter(const char* name, const void* value);
+    void get_parameter(const char* name, void* value);
+    void summary(Thallo_PerformanceSummary* s) const { *s = perf_; }
+    long long read_vector(const char* name, void* dst, long long count);
+
+    unsigned long long launches = 0;
+    int last_linear_iterations = 0;
+    unsigned long long total_linear_iterations = 0;
+    const PlanDesc& desc() const { return d_; }
+
+private:
+    struct Fn { CUfunction f = nullptr; };
+    CUfunction fn(const std::string& name);
+    void launch(CUfunction f, dim3 grid, dim3 block, void** args);
+    void launch_flat(CUfunction f, void** args);
+    void launch_uw(CUfunction f, void** args);
+    void launch_group(CUfunction f, int g, void** args);
+    void bind(void** params);
+    void write_lm_params();
+    double compute_cost();
+    void read_scalars();
+    void finalize();
+    void clear(void* p);
+    void linear_iteration(int l);
+    void rec(cudaEvent_t& e);
+    void log(const char* fmt, ...) const;
+
+    const StateOptions* opts_;
+    PlanDesc d_;
+    bool ok_ = false;
+    std::string error_;
+    CUmodule module_ = nullptr;
+    std::map<std::string, CUfunction> fns_;
+    size_t real_size_ = 4;
+    cudaStream_t stream() const { return opts_->stream; }
+
+    // device state
+    char* vec_block_ = nullptr;
+    size_t vec_stride_ = 0;
+    void* vecs_[12] = {};          // delta r b Adelta z p Ap CtC pre SSq prevX initX
+    void* d_scalars_ = nullptr;
+    double* d_partials_ = nullptr;
+    HScalars* h_scalars_ = nullptr;    // pinned
+    HHostFlags* h_flags_ = nullptr;    // pinned + mapped
+    void* d_flags_ = nullptr;
+    std::vector<char> params_buf_;
+    std::vector<char> vecs_buf_;
+    unsigned int flat_grid_ = 1;
+    int epoch_ = 0;
+
+    // host state (HostData)
+    SolverParameters sp_;
+    double radius_ = 1e4, decrease_factor_ = 2.0;   // kept in the plan's precision via round()
+    double prev_cost_ = 0;
+    bool finalized_ = false, initialized_ = false;
+    Thallo_PerformanceSummary perf_{};
+    std::chrono::steady_clock::time_point t_start_;
+
+    struct Span { cudaEvent_t a = nullptr, b = nullptr; };
+    std::vector<Span> ev_total_, ev_iter_, ev_setup_, ev_linear_, ev_finish_;
+    Span cur_total_, cur_iter_, cur_phase_;
+    void span_begin(Span& s);
+    void span_end(Span& s, std::vector<Span>& into);
+    void evaluate_timers();
+    double round_real(double v) const { return d_.is_double ? v : (double)(float)v; }
+};
+
+}  // namespace thallo

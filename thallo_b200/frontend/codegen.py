@@ -1,0 +1,549 @@
+"""Lowering of a ProblemSpec to per-energy CUDA C++ device functions + a plan descriptor.
+
+This is the replacement for the reference's CUDA-emitting backend
+(API/src/thallo.t:2288-3455 `createfunction`, operator builders :3531-3949,
+schedule selection :4096-4134).  Same math, different shape:
+
+  * The reference differentiates a residual template and *shifts* it to every
+    position from which it touches unknown x00 (`createjtjcentered` :3603-3667,
+    `createjtfcentered` :3669-3712).  Here the unknownwise operators are emitted
+    residual-centric: for every (term, shift s) whose instance at x0+s touches x0,
+    compute Jp once and multiply by each partial.  Instances whose position x0+s
+    lies outside the residual domain are dropped (see DESIGN.md "ghost residuals").
+  * Residualwise functions follow createjtfResidualwise :3867-3908,
+    createapplyjtjResidualwise :3536-3569, createmodelcostResidualwise :3845-3865,
+    createcost :3939-3949, createcomputejResidualwise :3792-3805.
+  * No instruction scheduling: the DAG is emitted in topological order as SSA
+    temporaries and nvcc/NVRTC does the rest.
+
+Generated functions are templates over an accessor `A` (how images / vector
+arguments are read: global memory with bounds checks, or TMA-staged shared-memory
+tiles) and a scatter sink `S` (how contributions are accumulated), both supplied
+by the hand-written skeleton in csrc/skeleton/.
+"""
+from . import ad
+from .dsl import ImageAccess, Bounds, IndexValue, Param, VecArg
+
+MAXD = 3
+
+
+class Lowered:
+    """Result of lowering: CUDA source of the per-energy functions and the descriptor."""
+
+    def __init__(self):
+        self.source = ""
+        self.desc = {}
+
+
+def _domain_of(L, exprs):
+    dims, sparse = set(), False
+    for e in exprs:
+        for v in ad.variables(e):
+            k = v.key
+            if isinstance(k, (ImageAccess, VecArg)):
+                for c in k.index:
+                    if c[0] == "d":
+                        dims.add(c[1])
+                    else:
+                        dims.add(c[2]); sparse = True
+            elif isinstance(k, Bounds):
+                for (d, lo, hi) in k.ranges:
+                    dims.add(d)
+            elif isinstance(k, IndexValue):
+                dims.add(k.dim)
+    return tuple(sorted(dims)), sparse
+
+
+def _shift_key(k, s):
+    """Shift a variable key by s: dict dim_idx -> offset."""
+    if isinstance(k, (ImageAccess, VecArg)):
+        comps = []
+        for c in k.index:
+            if c[0] == "d":
+                comps.append(("d", c[1], c[2] + s.get(c[1], 0)))
+            else:
+                assert s.get(c[2], 0) == 0, "cannot shift a sparse access"
+                comps.append(c)
+        return k._replace(index=tuple(comps))
+    if isinstance(k, Bounds):
+        return Bounds(tuple((d, lo + s.get(d, 0), hi + s.get(d, 0)) for (d, lo, hi) in k.ranges))
+    if isinstance(k, IndexValue):
+        return IndexValue(k.dim, k.off + s.get(k.dim, 0))
+    return k
+
+
+def shift(e, s, memo=None):
+    if not any(s.values()):
+        return e
+    return ad.substitute(e, lambda v: ad.var(_shift_key(v.key, s), v.type), memo)
+
+
+def _inb(s):
+    rng = tuple(sorted((d, o, o) for d, o in s.items() if o != 0))
+    if not rng:
+        return ad.const(True)
+    return ad.var(Bounds(rng), ad.BOOL)
+
+
+class _Term:
+    def __init__(self, L, exp):
+        self.exp = exp
+        ukeys = set(im.name for im in L.images if im.kind == "unknown")
+        self.unknowns = ad.variables(exp, lambda v: isinstance(v.key, ImageAccess) and v.key.image in ukeys)
+        memo = {}
+        self.partials = [ad.derivative(exp, u) for u in self.unknowns]
+        # keep only structurally non-zero partials
+        keep = [(u, p) for u, p in zip(self.unknowns, self.partials) if not p.is_const(0.0)]
+        self.unknowns = [u for u, _ in keep]
+        self.partials = [p for _, p in keep]
+
+    def jp(self, arg):
+        r = ad.const(0.0)
+        for u, p in zip(self.unknowns, self.partials):
+            k = u.key
+            r = r + p * ad.var(VecArg(arg, k.image, k.index, k.channel))
+        return r
+
+
+class Emitter:
+    """Emit a set of root expressions as straight-line CUDA statements."""
+
+    def __init__(self, gen):
+        self.gen = gen
+        self.lines = []
+        self.names = {}
+
+    def ref(self, e):
+        if e.kind == "const":
+            if e.type == ad.BOOL:
+                return "true" if e.value else "false"
+            return self.gen.lit(e.value)
+        return self.names[e.id]
+
+    def emit(self, roots):
+        for n in ad.toposort(roots):
+            if n.kind == "const" or n.id in self.names:
+                continue
+            name = ("b%d" if n.type == ad.BOOL else "t%d") % n.id
+            ty = "bool" if n.type == ad.BOOL else "real"
+            self.lines.append("const %s %s = %s;" % (ty, name, self.rhs(n)))
+            self.names[n.id] = name
+        return [self.ref(r) for r in roots]
+
+    def rhs(self, n):
+        g = self.gen
+        if n.kind == "var":
+            return g.var_rhs(n.key)
+        a = [self.ref(x) for x in n.args]
+        op = n.op
+        if op == "add": return "%s + %s" % (a[0], a[1])
+        if op == "sub": return "%s - %s" % (a[0], a[1])
+        if op == "mul": return "%s * %s" % (a[0], a[1])
+        if op == "powc":
+            c = n.const
+            if c > 0:
+                return "th_powi<%d>(%s)" % (c, a[0])
+            return "%s / th_powi<%d>(%s)" % (g.lit(1.0), -c, a[0])
+        if op == "pow": return "th_pow(%s, %s)" % (a[0], a[1])
+        if op == "select": return "(%s ? %s : %s)" % (a[0], a[1], a[2])
+        if op == "and": return "(%s && %s)" % (a[0], a[1])
+        if op == "or": return "(%s || %s)" % (a[0], a[1])
+        if op == "not": return "!%s" % a[0]
+        cmpops = dict(eq="==", neq="!=", less="<", greater=">", lesseq="<=", greatereq=">=")
+        if op in cmpops: return "(%s %s %s)" % (a[0], cmpops[op], a[1])
+        if op == "sample":
+            im = g.image(n.const[0])
+            return "a.template samp<%d>(P, %s, %s)" % (g.ptr_slot[im.name], a[0], a[1])
+        return "th_%s(%s)" % (op, a[0])
+
+
+class Generator:
+    def __init__(self, L, name, kind, double=False, schedule="auto", lm_as_committed=False):
+        self.L, self.name = L, name
+        self.double = bool(double)
+        self.lm = (kind == "levenberg_marquardt") and not lm_as_committed
+        self.kind = kind
+        self.images = {im.name: im for im in L.images}
+        self.sparses = {s.name: s for s in L.sparses}
+        self.unknowns = sorted([im for im in L.images if im.kind == "unknown"], key=lambda i: i.pidx)
+        assert self.unknowns, "energy declares no unknowns"
+        # parameter slots
+        self.ptr_slot, self.ptr_pidx = {}, []
+        for obj in sorted(list(L.images) + list(L.sparses), key=lambda o: o.pidx):
+            self.ptr_slot[obj.name] = len(self.ptr_pidx)
+            self.ptr_pidx.append(obj.pidx)
+        self.sc_slot, self.sc_defs = {}, []
+        for p in sorted(L.params, key=lambda p: p.pidx):
+            self.sc_slot[p.name] = len(self.sc_defs)
+            self.sc_defs.append((p.pidx, p.ctype))
+        # unknown vector layout: images back to back, AoS per element (thallo.t:1102-1126)
+        self.uoff, off = {}, 0
+        for k, im in enumerate(self.unknowns):
+            self.uoff[im.name] = off
+            off += im.cardinality
+        self.nunk = off
+        self.uidx = {im.name: k for k, im in enumerate(self.unknowns)}
+        # groups
+        self.groups = []
+        for g in L.residuals.groups:
+            terms = [_Term(L, t) for t in g.terms]
+            dom, sparse = _domain_of(L, [t.exp for t in terms])
+            self.groups.append(dict(name=g.name, terms=terms, domain=dom, sparse=sparse,
+                                    materialize=g.J.materialize))
+        udoms = set(tuple(d.idx for d in im.dims) for im in self.unknowns)
+        can_at_output = (len(udoms) == 1 and all((not g["sparse"]) and g["domain"] == next(iter(udoms))
+                                                 for g in self.groups)
+                         and not any(g["materialize"] for g in self.groups))
+        if schedule == "auto":
+            schedule = "at_output" if can_at_output else "residualwise"
+        if schedule == "at_output":
+            assert can_at_output, "compute_at_output needs every residual domain to equal the unknown domain"
+        self.schedule = schedule
+        self.udomain = next(iter(udoms)) if len(udoms) == 1 else None
+
+    # ---- small helpers
+    def image(self, name):
+        return self.images[name]
+
+    def lit(self, v):
+        s = repr(float(v))
+        if s in ("inf", "-inf", "nan"):
+            return {"inf": "TH_INF", "-inf": "(-TH_INF)", "nan": "TH_NAN"}[s]
+        return s if self.double else s + "f"
+
+    def _offs(self, index, domain):
+        o = [0] * MAXD
+        for c in index:
+            pos = domain.index(c[1])
+            o[pos] = c[2]
+        return o
+
+    def var_rhs(self, k):
+        dom = self._dom
+        if isinstance(k, ImageAccess):
+            im = self.images[k.image]
+            slot = self.ptr_slot[im.name]
+            if k.index[0][0] == "s":
+                sp = self.ptr_slot[k.index[0][1]]
+                return "a.template simg<%d, th_%s, %d, %d, %d>(P)" % (slot, im.ctype, im.channels, k.channel, sp)
+            assert tuple(c[1] for c in k.index) == tuple(dom), \
+                "image %s is indexed by dims %s inside a function over dims %s" % (im.name, [c[1] for c in k.index], dom)
+            o = self._offs(k.index, dom)
+            return "a.template img<%d, th_%s, %d, %d, %d, %d, %d>(P)" % (slot, im.ctype, im.channels, k.channel, o[0], o[1], o[2])
+        if isinstance(k, VecArg):
+            im = self.images[k.image]
+            if k.index[0][0] == "s":
+                sp = self.ptr_slot[k.index[0][1]]
+                return "a.template svec<%d, %d, %d>(P)" % (self.uidx[im.name], k.channel, sp)
+            o = self._offs(k.index, dom)
+            return "a.template vec<%d, %d, %d, %d, %d>()" % (self.uidx[im.name], k.channel, o[0], o[1], o[2])
+        if isinstance(k, Bounds):
+            lo, hi = [0] * MAXD, [0] * MAXD
+            for (d, l, h) in k.ranges:
+                pos = dom.index(d)
+                lo[pos], hi[pos] = l, h
+            return "a.template inb<%d, %d, %d, %d, %d, %d>()" % (lo[0], hi[0], lo[1], hi[1], lo[2], hi[2])
+        if isinstance(k, IndexValue):
+            return "(real)(a.template coord<%d>() + (%d))" % (dom.index(k.dim), k.off)
+        if isinstance(k, Param):
+            return "P.sc[%d]" % self.sc_slot[k.name]
+        raise NotImplementedError(k)
+
+    def _fn(self, sig, roots, outs, dom, pre_lines=()):
+        """One device function: emit `roots`, then `outs(refs)` statements."""
+        self._dom = dom
+        em = Emitter(self)
+        refs = em.emit(roots)
+        body = list(pre_lines) + em.lines + outs(refs)
+        return sig + " {\n    " + "\n    ".join(body) + "\n}\n"
+
+    def _scatter_stmt(self, which, key, ref, dom):
+        im = self.images[key.image]
+        k = self.uidx[im.name]
+        if key.index[0][0] == "s":
+            return "s.template sadd<%d, %d, %d, %d>(P, %s);" % (which, k, key.channel, self.ptr_slot[key.index[0][1]], ref)
+        o = self._offs(key.index, dom)
+        return "s.template add<%d, %d, %d, %d, %d, %d>(%s);" % (which, k, key.channel, o[0], o[1], o[2], ref)
+
+    # ---- unknownwise (at-output) functions
+    def _instances(self):
+        """(term, shift, [(slot j, partial shifted)], Jp shifted builder) for every residual
+        instance that touches the unknown at x0."""
+        out = []
+        terms = [t for g in self.groups for t in g["terms"]]
+        slot_of, j = {}, 0
+        for im in self.unknowns:
+            for ch in range(im.channels):
+                slot_of[(im.name, ch)] = j
+                j += 1
+        self.U = j
+        for t in terms:
+            by_shift = {}
+            for u, p in zip(t.unknowns, t.partials):
+                k = u.key
+                s = tuple(sorted((c[1], -c[2]) for c in k.index))
+                by_shift.setdefault(s, []).append((slot_of[(k.image, k.channel)], p))
+            for s, lst in by_shift.items():
+                out.append((t, dict(s), lst))
+        return out
+
+    def gen_unknownwise(self):
+        dom = self.udomain
+        src = []
+        inst = self._instances()
+        U = self.U
+        zero = ad.const(0.0)
+        # evalJTF: g_j = sum partial*F, d_j = sum partial^2  (createjtfcentered)
+        g = [zero] * U
+        d = [zero] * U
+        for t, s, lst in inst:
+            memo = {}
+            cond = _inb(s)
+            F = shift(t.exp, s, memo)
+            for j, p in lst:
+                ps = shift(p, s, memo)
+                g[j] = g[j] + ad.select(cond, ps * F, 0.0)
+                d[j] = d[j] + ad.select(cond, ps * ps, 0.0)
+        src.append(self._fn(
+            "template <class A> __device__ __forceinline__ void evalJTF_uw(const A& a, const Params& P, real* __restrict__ g, real* __restrict__ d)",
+            g + d,
+            lambda r: ["g[%d] = %s;" % (j, r[j]) for j in range(U)] + ["d[%d] = %s;" % (j, r[U + j]) for j in range(U)],
+            dom))
+        # applyJTJ: out_j = sum partial * Jp   (createjtjcentered, residual-centric)
+        out = [zero] * U
+        for t, s, lst in inst:
+            memo = {}
+            cond = _inb(s)
+            jp = shift(t.jp("P"), s, memo)
+            for j, p in lst:
+                ps = shift(p, s, memo)
+                out[j] = out[j] + ad.select(cond, ps * jp, 0.0)
+        src.append(self._fn(
+            "template <class A> __device__ __forceinline__ void applyJTJ_uw(const A& a, const Params& P, real* __restrict__ out)",
+            out, lambda r: ["out[%d] = %s;" % (j, r[j]) for j in range(U)], dom))
+        self.uw_roots = dict(g=g, d=d, out=out)        # kept for the NumPy interpreter (frontend/interp.py)
+        # halo radius per image / vector argument for the tile-staged variant
+        self.halo = self._halos(out)
+        return "\n".join(src)
+
+    def _halos(self, roots):
+        """Per accessed image (by ptr slot) and per unknown-vector image: max |offset| per dim."""
+        img, vec = {}, {}
+        for e in roots:
+            for v in ad.variables(e):
+                k = v.key
+                if isinstance(k, (ImageAccess, VecArg)) and k.index[0][0] == "d":
+                    tgt = vec if isinstance(k, VecArg) else img
+                    cur = tgt.setdefault(k.image, [0] * MAXD)
+                    for pos, c in enumerate(k.index):
+                        cur[pos] = max(cur[pos], abs(c[2]))
+        return dict(img=img, vec=vec)
+
+    def gen_exclude(self):
+        src = []
+        for k, im in enumerate(self.unknowns):
+            dom = tuple(d.idx for d in im.dims)
+            e = ad.const(False)          # one predicate per index space (thallo.t:5536-5538,5618-5624)
+            for other in self.unknowns:
+                if tuple(x.idx for x in other.dims) == dom and other.exclude is not None:
+                    e = ad.or_(e, other.exclude)
+            src.append(self._fn(
+                "template <class A> __device__ __forceinline__ bool exclude_u%d(const A& a, const Params& P)" % k,
+                [e], lambda r: ["return %s;" % r[0]], dom))
+        return "\n".join(src)
+
+    # ---- residualwise functions (per group)
+    def gen_group(self, gi, g):
+        dom = g["domain"]
+        terms = g["terms"]
+        src = []
+        half = ad.const(0.5)
+        # cost
+        c = ad.const(0.0)
+        for t in terms:
+            c = c + t.exp * t.exp
+        src.append(self._fn(
+            "template <class A> __device__ __forceinline__ real cost_g%d(const A& a, const Params& P)" % gi,
+            [half * c], lambda r: ["return %s;" % r[0]], dom))
+        # residual values (for tests / debugging)
+        src.append(self._fn(
+            "template <class A> __device__ __forceinline__ void residuals_g%d(const A& a, const Params& P, real* __restrict__ out)" % gi,
+            [t.exp for t in terms], lambda r: ["out[%d] = %s;" % (i, x) for i, x in enumerate(r)], dom))
+        # model cost: 1/2 sum (F + J delta)^2
+        m = ad.const(0.0)
+        for t in terms:
+            rm = t.exp + t.jp("Delta")
+            m = m + rm * rm
+        src.append(self._fn(
+            "template <class A> __device__ __forceinline__ real modelcost_g%d(const A& a, const Params& P)" % gi,
+            [half * m], lambda r: ["return %s;" % r[0]], dom))
+        # evalJTF scatter: R[u] += -partial*F ; Pre[u] += partial^2
+        tg, tgmap = [], {}
+        for t in terms:
+            for u, p in zip(t.unknowns, t.partials):
+                key = u.key
+                if key not in tgmap:
+                    tgmap[key] = [ad.const(0.0), ad.const(0.0)]
+                    tg.append(key)
+                tgmap[key][0] = tgmap[key][0] + (-1.0) * p * t.exp
+                tgmap[key][1] = tgmap[key][1] + p * p
+        roots = [tgmap[k][0] for k in tg] + [tgmap[k][1] for k in tg]
+        n = len(tg)
+        src.append(self._fn(
+            "template <class A, class S> __device__ __forceinline__ void evalJTF_g%d(const A& a, const Params& P, S& s)" % gi,
+            roots,
+            lambda r: [self._scatter_stmt(0, tg[i], r[i], dom) for i in range(n)] +
+                      [self._scatter_stmt(1, tg[i], r[n + i], dom) for i in range(n)], dom))
+        # applyJTJ scatter: Ap[u] += partial*Jp
+        tmap = {}
+        for t in terms:
+            jp = t.jp("P")
+            for u, p in zip(t.unknowns, t.partials):
+                tmap[u.key] = tmap.get(u.key, ad.const(0.0)) + p * jp
+        roots = [tmap[k] for k in tg]
+        src.append(self._fn(
+            "template <class A, class S> __device__ __forceinline__ void applyJTJ_g%d(const A& a, const Params& P, S& s)" % gi,
+            roots, lambda r: [self._scatter_stmt(0, tg[i], r[i], dom) for i in range(n)], dom))
+        # computeJ: partials term-major, unknown-minor; columns via accessor
+        vals, cols = [], []
+        for t in terms:
+            for u, p in zip(t.unknowns, t.partials):
+                vals.append(p)
+                cols.append(u.key)
+        g["nnz_per_elem"] = len(vals)
+        g["row_nnz"] = [len(t.unknowns) for t in terms]
+
+        def col_stmt(i, key):
+            im = self.images[key.image]
+            k = self.uidx[im.name]
+            if key.index[0][0] == "s":
+                return "cols[%d] = a.template sucol<%d, %d, %d>(P);" % (i, k, key.channel, self.ptr_slot[key.index[0][1]])
+            o = self._offs(key.index, dom)
+            return "cols[%d] = a.template ucol<%d, %d, %d, %d, %d>();" % (i, k, key.channel, o[0], o[1], o[2])
+        src.append(self._fn(
+            "template <class A> __device__ __forceinline__ void computeJ_g%d(const A& a, const Params& P, real* __restrict__ vals, long long* __restrict__ cols)" % gi,
+            vals, lambda r: ["vals[%d] = %s;" % (i, x) for i, x in enumerate(r)] +
+                            [col_stmt(i, k) for i, k in enumerate(cols)], dom))
+        g["targets"] = tg
+        return "\n".join(src)
+
+    # ---- whole translation unit
+    def generate(self):
+        L = self.L
+        out = Lowered()
+        hdr = []
+        hdr.append("// generated by thallo_b200.frontend.codegen for energy '%s' (%s)" % (self.name, self.kind))
+        hdr.append("#define TH_DOUBLE %d" % int(self.double))
+        hdr.append("#define TH_LM %d" % int(self.lm))
+        hdr.append("#define TH_USEPRE %d" % int(L.usepreconditioner))
+        hdr.append("#define TH_AT_OUTPUT %d" % int(self.schedule == "at_output"))
+        hdr.append("#define TH_NUM_UIMG %d" % len(self.unknowns))
+        hdr.append("#define TH_NUNK %dLL" % self.nunk)
+        hdr.append("#define TH_NPTR %d" % max(1, len(self.ptr_pidx)))
+        hdr.append("#define TH_NSC %d" % max(1, len(self.sc_defs)))
+        hdr.append("#define TH_NGROUPS %d" % len(self.groups))
+        hdr.append("#define TH_NDIMS %d" % len(L.dims))
+        hdr.append("#define TH_DIM_SIZES {%s}" % ", ".join(str(d.size) for d in L.dims))
+        # unknown image table: channels, flat offset, ptr slot, ndim, dim indices
+        rows = []
+        for im in self.unknowns:
+            di = [d.idx for d in im.dims] + [0] * (MAXD - len(im.dims))
+            rows.append("{%d, %dLL, %d, %d, {%d, %d, %d}, %dLL}" % (im.channels, self.uoff[im.name], self.ptr_slot[im.name],
+                                                                   len(im.dims), di[0], di[1], di[2], im.elements))
+        hdr.append("#define TH_UIMG_TABLE {%s}" % ", ".join(rows))
+        body = []
+        body.append(self.gen_exclude())
+        if self.schedule == "at_output":
+            dom = self.udomain
+            hdr.append("#define TH_UW_NDIM %d" % len(dom))
+            hdr.append("#define TH_UW_DIMS {%s}" % ", ".join(str(L.dims[d].size) for d in dom))
+            body.append(self.gen_unknownwise())
+            hdr.append("#define TH_U %d" % self.U)
+        gl = []
+        for gi, g in enumerate(self.groups):
+            body.append(self.gen_group(gi, g))
+            gl.append("X(%d)" % gi)
+        hdr.append("#define TH_GROUP_LIST(X) %s" % " ".join(gl))
+        # group domain table
+        rows = []
+        for g in self.groups:
+            dom = list(g["domain"]) + [0] * (MAXD - len(g["domain"]))
+            rows.append("{%d, {%d, %d, %d}, %d, %d}" % (len(g["domain"]), dom[0], dom[1], dom[2], len(g["terms"]), g["nnz_per_elem"]))
+        hdr.append("#define TH_GROUP_TABLE {%s}" % ", ".join(rows))
+        doms = []
+
+        def dom_struct(nm, dimidx):
+            sz = [L.dims[x].size for x in dimidx] + [1] * (MAXD - len(dimidx))
+            return ("struct %s { static constexpr int ND = %d; static constexpr long long D0 = %d, D1 = %d, D2 = %d; };"
+                    % (nm, len(dimidx), sz[0], sz[1], sz[2]))
+        for k, im in enumerate(self.unknowns):
+            doms.append(dom_struct("dom_u%d" % k, [x.idx for x in im.dims]))
+        if self.schedule == "at_output":
+            doms.append(dom_struct("dom_uw", list(self.udomain)))
+        for gi, g in enumerate(self.groups):
+            doms.append(dom_struct("dom_g%d" % gi, list(g["domain"])))
+        src = ("\n".join(hdr) + "\n#include \"thallo_prelude.cuh\"\nnamespace th {\n" + "\n".join(doms) + "\n"
+               + "\n".join(body) + "\n} // namespace th\n#include \"thallo_kernels.cuh\"\n")
+        out.source = src
+        # ---- descriptor
+        d = dict(
+            name=self.name, kind=self.kind, lm=int(self.lm), real="double" if self.double else "float",
+            usepreconditioner=int(L.usepreconditioner), schedule=self.schedule,
+            dims=[dd.size for dd in L.dims], dim_names=[dd.name for dd in L.dims],
+            nunk=self.nunk, ptr_pidx=self.ptr_pidx, sc_defs=self.sc_defs,
+            unknowns=[dict(name=im.name, channels=im.channels, offset=self.uoff[im.name], pidx=im.pidx,
+                           elements=im.elements, dims=[x.idx for x in im.dims]) for im in self.unknowns],
+            groups=[dict(name=g["name"], domain=list(g["domain"]), nterms=len(g["terms"]),
+                         count=_prod(L.dims[x].size for x in g["domain"]), materialize=int(g["materialize"]),
+                         nnz_per_elem=g["nnz_per_elem"], row_nnz=g["row_nnz"]) for g in self.groups],
+        )
+        if self.schedule == "at_output":
+            d["U"] = self.U
+            d["uw_dims"] = [L.dims[x].size for x in self.udomain]
+            d["halo_img"] = {k: v for k, v in self.halo["img"].items()}
+            d["halo_vec"] = {k: v for k, v in self.halo["vec"].items()}
+        out.desc = d
+        return out
+
+
+def _prod(it):
+    r = 1
+    for x in it:
+        r *= x
+    return r
+
+
+def descriptor_text(d):
+    """Line-based serialisation read by csrc/plan_desc.cpp (no JSON parser in the C library)."""
+    ln = []
+    ln.append("name %s" % d["name"])
+    ln.append("kind %s" % d["kind"])
+    ln.append("lm %d" % d["lm"])
+    ln.append("real %s" % d["real"])
+    ln.append("usepreconditioner %d" % d["usepreconditioner"])
+    ln.append("schedule %s" % d["schedule"])
+    ln.append("dims %d %s" % (len(d["dims"]), " ".join(map(str, d["dims"]))))
+    ln.append("nunk %d" % d["nunk"])
+    ln.append("ptrs %d %s" % (len(d["ptr_pidx"]), " ".join(map(str, d["ptr_pidx"]))))
+    ln.append("scalars %d %s" % (len(d["sc_defs"]), " ".join("%d:%s" % (p, t) for p, t in d["sc_defs"])))
+    for u in d["unknowns"]:
+        ln.append("unknown %s %d %d %d %d %d %s" % (u["name"], u["channels"], u["offset"], u["pidx"], u["elements"],
+                                                   len(u["dims"]), " ".join(map(str, u["dims"]))))
+    for g in d["groups"]:
+        ln.append("group %s %d %d %d %d %d %s | %s" % (g["name"], g["count"], g["nterms"], g["materialize"], g["nnz_per_elem"],
+                                                      len(g["domain"]), " ".join(map(str, g["domain"])),
+                                                      " ".join(map(str, g["row_nnz"]))))
+    if d["schedule"] == "at_output":
+        ln.append("U %d" % d["U"])
+        ln.append("uw_dims %d %s" % (len(d["uw_dims"]), " ".join(map(str, d["uw_dims"]))))
+    return "\n".join(ln) + "\n"
+
+
+def lower(define, dims, kind="gauss_newton", name="energy", double=False, schedule="auto",
+          lm_as_committed=False, **define_kwargs):
+    from .dsl import build_spec
+    L = build_spec(define, dims, **define_kwargs)
+    gen = Generator(L, name, kind, double, schedule, lm_as_committed)
+    out = gen.generate()
+    out.generator = gen
+    return out

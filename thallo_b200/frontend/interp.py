@@ -1,0 +1,140 @@
+"""NumPy interpreter for lowered expression DAGs (host-side check of the lowering logic:
+shifted residual instances, bounds handling, partials) -- evaluates exactly the roots the
+CUDA emitter prints, vectorised over the unknown domain.  Used by the CPU test-suite to
+compare the generated unknownwise operators with the oracle's J-based products before any
+GPU time is spent; it is not part of the solve path.
+"""
+import numpy as np
+
+from . import ad
+from .dsl import ImageAccess, Bounds, IndexValue, Param, VecArg
+
+
+def _shifted(arr, offs):
+    out = np.zeros_like(arr)
+    nd = len(offs)
+    src, dst = [], []
+    for axis in range(nd):
+        o = offs[nd - 1 - axis]
+        n = arr.shape[axis]
+        if abs(o) >= n:
+            return out
+        if o >= 0:
+            src.append(slice(o, n)); dst.append(slice(0, n - o))
+        else:
+            src.append(slice(0, n + o)); dst.append(slice(-o, n))
+    out[tuple(dst)] = arr[tuple(src)]
+    return out
+
+
+class Interp:
+    def __init__(self, gen, params, dom, vec=None, dtype=np.float64):
+        self.gen, self.params, self.dom, self.vec, self.dt = gen, params, list(dom), vec, dtype
+        L = gen.L
+        self.shape = tuple(L.dims[d].size for d in reversed(self.dom))
+        grids = np.meshgrid(*[np.arange(n) for n in self.shape], indexing="ij")
+        self.coord = {d: grids[len(self.dom) - 1 - i] for i, d in enumerate(self.dom)}
+        self.cache = {}
+
+    def _offs(self, index):
+        o = [0] * len(self.dom)
+        for c in index:
+            o[self.dom.index(c[1])] = c[2]
+        return o
+
+    def _image(self, name):
+        im = self.gen.images[name]
+        a = np.asarray(self.params[im.pidx]).astype(self.dt).reshape(self.shape + (im.channels,))
+        return a
+
+    def var(self, k):
+        g = self.gen
+        if isinstance(k, ImageAccess):
+            assert k.index[0][0] == "d", "sparse accesses are not interpreted"
+            return _shifted(self._image(k.image), self._offs(k.index))[..., k.channel]
+        if isinstance(k, VecArg):
+            im = g.images[k.image]
+            off = g.uoff[k.image]
+            a = self.vec[off:off + im.cardinality].astype(self.dt).reshape(self.shape + (im.channels,))
+            return _shifted(a, self._offs(k.index))[..., k.channel]
+        if isinstance(k, Bounds):
+            ok = np.ones(self.shape, bool)
+            for (d, lo, hi) in k.ranges:
+                n = g.L.dims[d].size
+                c = self.coord[d]
+                ok &= (c + lo >= 0) & (c + hi < n)
+            return ok
+        if isinstance(k, IndexValue):
+            return (self.coord[k.dim] + k.off).astype(self.dt)
+        if isinstance(k, Param):
+            pd = [p for p in g.L.params if p.name == k.name][0]
+            return self.dt(np.asarray(self.params[pd.pidx]).reshape(-1)[0])
+        raise NotImplementedError(k)
+
+    def eval(self, roots):
+        val = self.cache
+        for n in ad.toposort(roots):
+            if n.id in val:
+                continue
+            if n.kind == "const":
+                val[n.id] = bool(n.value) if n.type == ad.BOOL else self.dt(n.value)
+            elif n.kind == "var":
+                val[n.id] = self.var(n.key)
+            else:
+                a = [val[x.id] for x in n.args]
+                op = n.op
+                with np.errstate(all="ignore"):
+                    if op == "add": r = a[0] + a[1]
+                    elif op == "sub": r = a[0] - a[1]
+                    elif op == "mul": r = a[0] * a[1]
+                    elif op == "powc": r = a[0] ** n.const if n.const > 0 else 1.0 / (a[0] ** (-n.const))
+                    elif op == "pow": r = a[0] ** a[1]
+                    elif op == "select": r = np.where(a[0], a[1], a[2])
+                    elif op == "and": r = np.logical_and(a[0], a[1])
+                    elif op == "or": r = np.logical_or(a[0], a[1])
+                    elif op == "not": r = np.logical_not(a[0])
+                    elif op in ("eq", "neq", "less", "greater", "lesseq", "greatereq"):
+                        f = dict(eq=np.equal, neq=np.not_equal, less=np.less, greater=np.greater,
+                                 lesseq=np.less_equal, greatereq=np.greater_equal)[op]
+                        r = f(a[0], a[1])
+                    elif op == "sample":
+                        r = self._sample(n.const[0], a[0], a[1])
+                    else:
+                        r = getattr(np, dict(abs="abs", asin="arcsin", acos="arccos", atan="arctan").get(op, op))(a[0])
+                val[n.id] = r
+        return [np.broadcast_to(val[r.id], self.shape) for r in roots]
+
+    def _sample(self, name, x, y):
+        data = self._image(name)[..., 0]
+        H, W = data.shape
+
+        def get(ix, iy):
+            inb = (ix >= 0) & (ix < W) & (iy >= 0) & (iy < H)
+            return np.where(inb, data[np.clip(iy, 0, H - 1), np.clip(ix, 0, W - 1)], 0.0)
+        x0, x1 = np.floor(x).astype(np.int64), np.ceil(x).astype(np.int64)
+        y0, y1 = np.floor(y).astype(np.int64), np.ceil(y).astype(np.int64)
+        xn, yn = x - x0, y - y0
+        u = (1 - xn) * get(x0, y0) + xn * get(x1, y0)
+        b = (1 - xn) * get(x0, y1) + xn * get(x1, y1)
+        return (1 - yn) * u + yn * b
+
+
+def unknownwise(gen, params, vec=None, dtype=np.float64):
+    """Evaluate the generated at-output operators.  Returns (g, d, out) as flat vectors in the
+    solver's unknown layout; `out` is None when no vector argument is given."""
+    it = Interp(gen, params, gen.udomain, vec, dtype)
+    U = gen.U
+    roots = gen.uw_roots["g"] + gen.uw_roots["d"] + (gen.uw_roots["out"] if vec is not None else [])
+    vals = it.eval(roots)
+
+    def pack(lst):
+        flat = np.zeros(gen.nunk, dtype)
+        j = 0
+        for im in gen.unknowns:
+            a = np.stack([lst[j + ch] for ch in range(im.channels)], axis=-1)
+            flat[gen.uoff[im.name]:gen.uoff[im.name] + im.cardinality] = a.reshape(-1)
+            j += im.channels
+        return flat
+    g, d = pack(vals[:U]), pack(vals[U:2 * U])
+    out = pack(vals[2 * U:]) if vec is not None else None
+    return g, d, out
