@@ -42,6 +42,11 @@ unsigned long long ThalloB200_PlanTotalLinearIterations(Thallo_State* state, Tha
  * (count reals of the plan's precision).  Test hook. Returns number of reals copied. */
 long long ThalloB200_PlanReadVector(Thallo_State* state, Thallo_Plan* plan, const char* name, void* host_dst, long long count);
 
+/* Per-kernel device times accumulated since plan creation when the state was created with
+ * timingLevel >= 2 (the reference wraps every launch in an event pair at that level,
+ * util.t:774-790).  Writes "kernel_name launches total_ms\n" lines; returns bytes written. */
+long long ThalloB200_PlanKernelTimes(Thallo_State* state, Thallo_Plan* plan, char* buf, long long capacity);
+
 /* Last error message of this thread ("" if none). */
 const char* ThalloB200_LastError(void);
 

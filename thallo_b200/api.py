@@ -75,6 +75,8 @@ def lib():
     L.ThalloB200_PlanTotalLinearIterations.restype, L.ThalloB200_PlanTotalLinearIterations.argtypes = C.c_ulonglong, [vp, vp]
     L.ThalloB200_PlanReadVector.restype = C.c_longlong
     L.ThalloB200_PlanReadVector.argtypes = [vp, vp, cp, vp, C.c_longlong]
+    L.ThalloB200_PlanKernelTimes.restype = C.c_longlong
+    L.ThalloB200_PlanKernelTimes.argtypes = [vp, vp, C.c_char_p, C.c_longlong]
     L.ThalloB200_LastError.restype, L.ThalloB200_LastError.argtypes = cp, []
     L.ThalloB200_Version.restype, L.ThalloB200_Version.argtypes = cp, []
     _lib = L
@@ -195,6 +197,16 @@ class ThalloSolver:
 
     def total_linear_iterations(self):
         return int(self.L.ThalloB200_PlanTotalLinearIterations(self.state, self.plan))
+
+    def kernel_times(self):
+        """{kernel name: (launches, total device ms)}; needs timing >= 2."""
+        buf = C.create_string_buffer(1 << 16)
+        self.L.ThalloB200_PlanKernelTimes(self.state, self.plan, buf, len(buf))
+        out = {}
+        for ln in buf.value.decode().splitlines():
+            name, cnt, ms = ln.split()
+            out[name] = (int(cnt), float(ms))
+        return out
 
     def read_vector(self, name, count):
         import numpy as np

@@ -4,6 +4,7 @@
 #include <sys/stat.h>
 #include <unistd.h>
 
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -201,6 +202,14 @@ unsigned long long ThalloB200_PlanTotalLinearIterations(Thallo_State*, Thallo_Pl
 }
 long long ThalloB200_PlanReadVector(Thallo_State*, Thallo_Plan* plan, const char* name, void* host_dst, long long count) {
     return plan ? plan->plan->read_vector(name, host_dst, count) : 0;
+}
+long long ThalloB200_PlanKernelTimes(Thallo_State*, Thallo_Plan* plan, char* buf, long long capacity) {
+    if (!plan || !buf || capacity <= 0) return 0;
+    const std::string t = plan->plan->kernel_times();
+    const long long n = std::min<long long>((long long)t.size(), capacity - 1);
+    memcpy(buf, t.data(), (size_t)n);
+    buf[n] = 0;
+    return n;
 }
 const char* ThalloB200_LastError(void) { return g_last_error.c_str(); }
 const char* ThalloB200_Version(void) { return "thallo_b200 0.1.0 (sm_100a)"; }

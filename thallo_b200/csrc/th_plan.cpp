@@ -144,6 +144,8 @@ Plan::~Plan() {
     if (h_flags_) cudaFreeHost((void*)h_flags_);
     for (auto* v : {&ev_total_, &ev_iter_, &ev_setup_, &ev_linear_, &ev_finish_})
         for (auto& s : *v) { if (s.a) cudaEventDestroy(s.a); if (s.b) cudaEventDestroy(s.b); }
+    for (auto& k : kstats_) for (auto& s : k.pending) { cudaEventDestroy(s.a); cudaEventDestroy(s.b); }
+    for (auto& s : event_pool_) { cudaEventDestroy(s.a); cudaEventDestroy(s.b); }
     if (module_ && DriverApi::get().ok) DriverApi::get().ModuleUnload(module_);
 }
 
@@ -157,12 +159,46 @@ CUfunction Plan::fn(const std::string& name) {
         exit(1);
     }
     fns_[name] = f;
+    kstat_index_[f] = (int)kstats_.size();
+    kstats_.push_back(KernelStat());
+    kstats_.back().name = name;
     return f;
 }
 
 void Plan::launch(CUfunction f, dim3 grid, dim3 block, void** args) {
+    const bool timed = opts_->init.timingLevel >= 2;   // per-kernel events, util.t:774-790
+    Span s;
+    if (timed) {
+        if (!event_pool_.empty()) { s = event_pool_.back(); event_pool_.pop_back(); }
+        else { CD(cudaEventCreate(&s.a)); CD(cudaEventCreate(&s.b)); }
+        CD(cudaEventRecord(s.a, stream()));
+    }
     CU(DriverApi::get().LaunchKernel(f, grid.x, grid.y, grid.z, block.x, block.y, block.z, 0, (CUstream)stream(), args, nullptr));
     ++launches;
+    if (timed) {
+        CD(cudaEventRecord(s.b, stream()));
+        KernelStat& k = kstats_[kstat_index_[f]];
+        k.pending.push_back(s);
+        if (k.pending.size() >= 4096) resolve_kernel_events();
+    }
+}
+void Plan::resolve_kernel_events() {
+    CD(cudaStreamSynchronize(stream()));
+    for (auto& k : kstats_) {
+        for (auto& s : k.pending) {
+            float t = 0;
+            if (cudaEventElapsedTime(&t, s.a, s.b) == cudaSuccess) { k.ms += t; ++k.count; }
+            event_pool_.push_back(s);
+        }
+        k.pending.clear();
+    }
+}
+std::string Plan::kernel_times() {
+    resolve_kernel_events();
+    std::ostringstream o;
+    o.precision(9);
+    for (auto& k : kstats_) if (k.count) o << k.name << " " << k.count << " " << k.ms << "\n";
+    return o.str();
 }
 void Plan::launch_flat(CUfunction f, void** args) { launch(f, dim3(flat_grid_), dim3(256), args); }
 void Plan::launch_uw(CUfunction f, void** args) {

@@ -77,6 +77,8 @@ public:
     void get_parameter(const char* name, void* value);
     void summary(Thallo_PerformanceSummary* s) const { *s = perf_; }
     long long read_vector(const char* name, void* dst, long long count);
+    // per-kernel device times (timingLevel >= 2, like util.t:774-790): "name count total_ms\n" lines
+    std::string kernel_times();
 
     unsigned long long launches = 0;
     int last_linear_iterations = 0;
@@ -132,6 +134,11 @@ private:
     std::chrono::steady_clock::time_point t_start_;
 
     struct Span { cudaEvent_t a = nullptr, b = nullptr; };
+    struct KernelStat { std::string name; unsigned long long count = 0; double ms = 0; std::vector<Span> pending; };
+    std::map<CUfunction, int> kstat_index_;
+    std::vector<KernelStat> kstats_;
+    std::vector<Span> event_pool_;
+    void resolve_kernel_events();
     std::vector<Span> ev_total_, ev_iter_, ev_setup_, ev_linear_, ev_finish_;
     Span cur_total_, cur_iter_, cur_phase_;
     void span_begin(Span& s);
