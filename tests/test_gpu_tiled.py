@@ -1,0 +1,131 @@
+"""Parity of the tiled at-output schedule (th_pcg_a: TMA-staged shared-memory tiles, fused
+p-update, hoisted invariants; th_pcg_b) against the oracle, through the C ABI.  Covers the TMA
+and the cooperative-load variants, partial tiles, 3-D domains, sampled images, float64, and
+bit-equality between the variants (they perform the same arithmetic on the same values).
+Tolerances: 1e-5 relative on every cost of the trajectory in float32, 1e-10 in float64."""
+import os
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+
+import energies
+from oracle.solver import OracleSolver
+from thallo_b200 import workloads as wl
+
+pytestmark = pytest.mark.gpu
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def _trajectory_oracle(name, dims, kind, params, dtype, nit, lit):
+    o = OracleSolver(energies.load(name), dims, kind, dtype, "at_output")
+    o.set("nIterations", nit); o.set("lIterations", lit)
+    o.init(params)
+    costs = [o.current_cost()]
+    while o.step(params):
+        costs.append(o.current_cost())
+    costs.append(o.current_cost())
+    return o, costs
+
+
+def _trajectory_gpu(name, dims, kind, params, nptr, dtype, nit, lit, **kw):
+    from thallo_b200.api import ThalloSolver
+    dp = [dev(p) if i in nptr else p for i, p in enumerate(params)]
+    s = ThalloSolver(dims, name, kind, double=(dtype == np.float64), **kw)
+    s.set_parameters(nIterations=nit, lIterations=lit)
+    s.init(dp)
+    costs, lin = [s.current_cost()], []
+    while s.step():
+        costs.append(s.current_cost())
+        lin.append(s.last_linear_iterations())
+    costs.append(s.current_cost())
+    return s, costs, lin, dp
+
+
+def _close(c, cref, tol, floor):
+    assert len(c) == len(cref), (c, cref)
+    for a, b in zip(c, cref):
+        assert abs(a - b) <= tol * max(abs(b), floor), (c, cref)
+
+
+def _iw_params(W, H, dtype):
+    p = wl.image_warping_params(wl.image_warping_inputs(W, H))
+    return [np.array(x, dtype=dtype) if i < 5 else x for i, x in enumerate(p)]
+
+
+@pytest.mark.parametrize("kind", ["gauss_newton", "levenberg_marquardt"])
+@pytest.mark.parametrize("size", [(100, 83), (75, 50)])       # partial tiles; 75 -> rows not 16-byte aligned -> cooperative loads
+def test_image_warping_tiled_matches_oracle(kind, size):
+    W, H = size
+    o, cref = _trajectory_oracle("image_warping", [W, H], kind, _iw_params(W, H, np.float32), np.float32, 5, 35)
+    s, c, lin, dp = _trajectory_gpu("image_warping", [W, H], kind, _iw_params(W, H, np.float32), range(5), np.float32, 5, 35)
+    assert s.lowered.desc["tiled"] == 1 and s.lowered.desc["ncoef"] == 2
+    _close(c, cref, 1e-5, 1e-3)
+    if kind == "levenberg_marquardt":
+        assert lin == [it["n_lin"] for it in o.trace][:len(lin)]
+
+
+def test_tma_and_cooperative_load_variants_are_bit_identical():
+    W, H = 96, 72
+    outs = []
+    for no_tma in (False, True):
+        if no_tma:
+            os.environ["THALLO_B200_NO_TMA"] = "1"
+        try:
+            s, c, lin, dp = _trajectory_gpu("image_warping", [W, H], "levenberg_marquardt", _iw_params(W, H, np.float32),
+                                            range(5), np.float32, 4, 30)
+        finally:
+            os.environ.pop("THALLO_B200_NO_TMA", None)
+        outs.append((c, lin, dp[0].cpu().numpy().copy(), dp[1].cpu().numpy().copy()))
+    assert outs[0][0] == outs[1][0] and outs[0][1] == outs[1][1]
+    assert np.array_equal(outs[0][2], outs[1][2]) and np.array_equal(outs[0][3], outs[1][3])
+
+
+def test_hoisted_invariants_do_not_change_results():
+    """cos/sin of the angle read from the precomputed coefficient image are the same bits as
+    recomputing them at every tap."""
+    W, H = 64, 48
+    outs = []
+    for hoist in (True, False):
+        s, c, lin, dp = _trajectory_gpu("image_warping", [W, H], "gauss_newton", _iw_params(W, H, np.float32), range(5),
+                                        np.float32, 3, 20, define_kwargs=dict(hoist=hoist))
+        assert s.lowered.desc["ncoef"] == (2 if hoist else 0)
+        outs.append((c, dp[0].cpu().numpy().copy()))
+    _close(outs[0][0], outs[1][0], 1e-6, 1e-3)
+    assert np.abs(outs[0][1] - outs[1][1]).max() < 1e-4
+
+
+def test_image_warping_tiled_f64():
+    W, H = 68, 44
+    o, cref = _trajectory_oracle("image_warping", [W, H], "levenberg_marquardt", _iw_params(W, H, np.float64), np.float64, 5, 40)
+    s, c, lin, dp = _trajectory_gpu("image_warping", [W, H], "levenberg_marquardt", _iw_params(W, H, np.float64), range(5),
+                                    np.float64, 5, 40)
+    _close(c, cref, 1e-10, 1e-6)
+    assert lin == [it["n_lin"] for it in o.trace][:len(lin)]
+
+
+@pytest.mark.parametrize("kind", ["gauss_newton", "levenberg_marquardt"])
+def test_volumetric_3d_tiled_matches_oracle(kind):
+    W, H, D = 12, 10, 9
+    po = wl.volumetric_params(wl.volumetric_inputs(W, H, D))
+    o, cref = _trajectory_oracle("volumetric_mesh_deformation", [W, H, D], kind, po, np.float32, 4, 25)
+    pg = wl.volumetric_params(wl.volumetric_inputs(W, H, D))
+    s, c, lin, dp = _trajectory_gpu("volumetric_mesh_deformation", [W, H, D], kind, pg, range(4), np.float32, 4, 25)
+    assert s.lowered.desc["tiled"] == 1 and s.lowered.desc["ncoef"] == 6
+    _close(c, cref, 1e-5, 1e-3)
+    assert np.abs(dp[0].cpu().numpy() - po[0]).max() < 2e-3
+
+
+def test_optical_flow_tiled_matches_oracle():
+    W, H = 64, 40
+    po = wl.optical_flow_params(wl.optical_flow_inputs(W, H))
+    o, cref = _trajectory_oracle("optical_flow", [W, H], "gauss_newton", po, np.float32, 2, 30)
+    pg = wl.optical_flow_params(wl.optical_flow_inputs(W, H))
+    s, c, lin, dp = _trajectory_gpu("optical_flow", [W, H], "gauss_newton", pg, range(2, 7), np.float32, 2, 30)
+    assert s.lowered.desc["tiled"] == 1
+    _close(c, cref, 1e-5, 1e-3)
+    assert np.abs(dp[2].cpu().numpy() - po[2]).max() < 2e-3

@@ -9,8 +9,13 @@
 //   th_step1_uw           PCGStep1 unknownwise :734-752 / computeAdelta :755-762
 //   th_applyjtj_g<i>      PCGStep1 residualwise :1006-1016 / computeAdelta :1058-1065
 //   th_step1_finish       PCGStep1_Finish :774-799
-//   th_step2              PCGStep2 :801-843     th_step2_first/second  :845-886
-//   th_step3              PCGStep3 :889-899 + scalar hand-over :1665 + LM zeta test :1666-1686
+//   th_pcg_b              PCGStep2 :801-843 (vectorised; in the tiled schedule it also closes the iteration)
+//   th_step2_first/second :845-886
+//   th_step3              PCGStep3 :889-899 + scalar hand-over :1665 + LM zeta test :1666-1686 (untiled schedules)
+//   th_pcg_a              tiled schedule: PCGStep3 of the previous iteration fused with PCGStep1 of this one --
+//                         p = z + beta p is formed in a TMA-staged shared-memory tile (with halo) and J^T J p
+//                         is gathered from that tile; th_precompute_coef hoists the PCG-invariant
+//                         transcendental sub-expressions of J out of the inner loop
 //   th_update             PCGLinearUpdate :901-906     th_copy_x  savePreviousUnknowns/revertUpdate/copyUnknownwise :908-927
 //   th_cost_g<i>          computeCost :1067-1079       th_modelcost_g<i>  computeModelCost :1088-1095
 // Reductions: warp shuffle -> shared memory -> one partial per block -> the last block to
@@ -217,6 +222,17 @@ __device__ __forceinline__ real th_beta(const ThScalars* S) {
 #endif
 }
 
+// beta as seen by th_pcg_a of iteration `it` (> 0): the previous iteration has been closed, so the
+// newest numerator sits in rz[it&1] and the one before in rz[(it+1)&1].
+__device__ __forceinline__ real th_beta_prev(const ThScalars* S) {
+    const real num = (real)S->rz[S->it & 1], den = (real)S->rz[(S->it + 1) & 1];
+#if TH_LM
+    return num / den;
+#else
+    return den != (real)0 ? num / den : (real)0;
+#endif
+}
+
 // Shared tail of both PCGInit forms: given the gradient entry g (=J^T F) and the true
 // diagonal d (=diag J^T J) of one unknown scalar, produce r, preconditioner, p (and in LM
 // CtC, b, SSq) and return r*p.
@@ -239,12 +255,19 @@ __device__ __forceinline__ real th_init_scalar(const Params& P, const Vecs& V, l
     V.delta[off] = (real)0;
     V.r[off] = r;
     V.pre[off] = pre;
+#if TH_TILED
+    V.z[off] = p;      // the first th_pcg_a of the linear solve takes p := z (beta = 0)
+#else
     V.p[off] = p;
+#endif
     return r * p;
 }
 __device__ __forceinline__ void th_zero_scalar(const Vecs& V, long long off) {
     V.delta[off] = (real)0; V.r[off] = (real)0; V.pre[off] = (real)0; V.p[off] = (real)0;
     V.z[off] = (real)0; V.Ap[off] = (real)0;
+#if TH_TILED
+    V.p2[off] = (real)0;
+#endif
 #if TH_LM
     V.CtC[off] = (real)0; V.b[off] = (real)0; V.Adelta[off] = (real)0;
 #endif
@@ -327,27 +350,104 @@ th_step1_uw(const __grid_constant__ Params P, const __grid_constant__ Vecs V, Th
 // ================================================================== flat vector kernels
 // Excluded unknowns hold zeros in every solver vector (written by the init kernels), so
 // these streaming kernels need no mask: 0 stays 0 and contributes 0 to every dot product.
+#if TH_DOUBLE
+typedef double4 real4;
+#else
+typedef float4 real4;
+#endif
+
+// current search direction: the tiled schedule ping-pongs p between V.p and V.p2 (iteration `it`
+// reads buffer it&1 and writes buffer (it+1)&1, see th_pcg_a); the other schedules keep V.p.
+__device__ __forceinline__ real* th_pcur(const Vecs& V, const ThScalars* S) {
+#if TH_TILED
+    return ((S->it + 1) & 1) ? V.p2 : V.p;
+#else
+    return V.p;
+#endif
+}
+
+// End of a PCG iteration, executed by one thread of the last block to finish: the numerator
+// hand-over (gauss_newton.t:1665, here just the parity of `it`), the LM zeta test (:1666-1686)
+// and the progress report to the host through mapped pinned memory, which lets the host stop
+// issuing iterations after an LM early exit without ever synchronising (the reference blocks on
+// a 4-byte cudaMemcpy every iteration, gauss_newton.t:1667).
+__device__ __forceinline__ void th_close_iteration(ThScalars* S, real q_tolerance, ThHostFlags* hf, int epoch) {
+    const int it = S->it;
+    S->it = it + 1;
+    S->lin_done = it + 1;
+#if TH_LM
+    const real Q1 = (real)S->q, Q0 = (real)S->Q0;
+    if (!th_finite(Q1)) S->done = 1;
+    else {
+        const real zeta = (real)(it + 1) * (Q1 - Q0) / Q1;
+        if (!th_finite(zeta) || zeta < q_tolerance) S->done = 1;
+        else S->Q0 = (double)Q1;
+    }
+#endif
+    if (hf) {
+        *(volatile long long*)&hf->progress = ((long long)epoch << 32) | (long long)(it + 1);
+        if (S->done) *(volatile int*)&hf->done_epoch = epoch;
+        __threadfence_system();
+    }
+}
+
+// PCGStep2: alpha = rz/aD; delta += alpha p; r -= alpha Ap; z = M r; <z,r>; LM: q = 1/2 <delta, r + b>.
+// Pure streaming: 128-bit loads of every operand first, then the stores (the vectors never alias,
+// but the compiler cannot know that through the pointer table).
+#define TH_B_LANE(c)                                                             \
+    {                                                                            \
+        const real dn_ = dl.c + alpha * p.c;                                     \
+        const real rn_ = r.c - alpha * ap.c;                                     \
+        const real z_ = TH_USEPRE ? pre.c * rn_ : rn_;                           \
+        dl.c = dn_; r.c = rn_; zz.c = z_;                                        \
+        acc[0] += (double)(z_ * rn_);                                            \
+        if (TH_LM) acc[1] += (double)((real)0.5 * (dn_ * (rn_ + bb.c)));         \
+    }
 extern "C" __global__ void __launch_bounds__(TH_BLOCK)
-th_step2(const __grid_constant__ Vecs V, ThScalars* S, double* partials) {
+th_pcg_b(const __grid_constant__ Vecs V, ThScalars* S, double* partials, real q_tolerance, ThHostFlags* hf, int epoch) {
     if (S->done) return;
     const real alpha = th_alpha(S);
+    const real* __restrict__ pp = th_pcur(V, S);
+    real* __restrict__ vd = V.delta;
+    real* __restrict__ vr = V.r;
+    real* __restrict__ vz = V.z;
+    const real* __restrict__ vap = V.Ap;
+    const real* __restrict__ vpre = V.pre;
+    const real* __restrict__ vb = V.b;
     double acc[2] = {0.0, 0.0};
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < TH_NUNK; i += (long long)gridDim.x * blockDim.x) {
-        const real p = V.p[i];
-        const real delta = V.delta[i] + alpha * p;
-        V.delta[i] = delta;
-        const real r = V.r[i] - alpha * V.Ap[i];
-        V.r[i] = r;
-        const real z = TH_USEPRE ? V.pre[i] * r : r;
-        V.z[i] = z;
-        acc[0] += (double)(z * r);
-#if TH_LM
-        acc[1] += (double)((real)0.5 * (delta * (r + V.b[i])));
-#endif
+    const long long n4 = TH_NUNK / 4;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const long long gtid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    for (long long i = gtid; i < n4; i += stride) {
+        const real4 p = ((const real4*)pp)[i];
+        real4 dl = ((const real4*)vd)[i];
+        real4 r = ((const real4*)vr)[i];
+        const real4 ap = ((const real4*)vap)[i];
+        real4 pre, bb, zz;
+        if (TH_USEPRE) pre = ((const real4*)vpre)[i];
+        if (TH_LM) bb = ((const real4*)vb)[i];
+        TH_B_LANE(x) TH_B_LANE(y) TH_B_LANE(z) TH_B_LANE(w)
+        ((real4*)vd)[i] = dl;
+        ((real4*)vr)[i] = r;
+        ((real4*)vz)[i] = zz;
+    }
+    for (long long i = n4 * 4 + gtid; i < TH_NUNK; i += stride) {
+        const real pv = pp[i];
+        const real dn = vd[i] + alpha * pv;
+        const real rn = vr[i] - alpha * vap[i];
+        const real zv = TH_USEPRE ? vpre[i] * rn : rn;
+        vd[i] = dn; vr[i] = rn; vz[i] = zv;
+        acc[0] += (double)(zv * rn);
+        if (TH_LM) acc[1] += (double)((real)0.5 * (dn * (rn + vb[i])));
     }
     double tot[2];
     if (th_grid_reduce<2>(acc, tot, partials, &S->ticket[2])) {
-        if (threadIdx.x == 0) { S->rz[(S->it + 1) & 1] = tot[0]; S->q = tot[1]; }
+        if (threadIdx.x == 0) {
+            S->rz[(S->it + 1) & 1] = tot[0]; S->q = tot[1];
+#if TH_TILED
+            th_close_iteration(S, q_tolerance, hf, epoch);
+#endif
+        }
     }
 }
 
@@ -355,13 +455,15 @@ extern "C" __global__ void __launch_bounds__(TH_BLOCK)
 th_step2_first(const __grid_constant__ Vecs V, ThScalars* S) {
     if (S->done) return;
     const real alpha = th_alpha(S);
+    const real* __restrict__ pp = th_pcur(V, S);
+    real* __restrict__ vd = V.delta;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < TH_NUNK; i += (long long)gridDim.x * blockDim.x)
-        V.delta[i] = V.delta[i] + alpha * V.p[i];
+        vd[i] = vd[i] + alpha * pp[i];
 }
 
 // r = b - A delta; add_ctc: A delta still lacks the CtC*delta term (residualwise / materialized schedules)
 extern "C" __global__ void __launch_bounds__(TH_BLOCK)
-th_step2_second(const __grid_constant__ Vecs V, ThScalars* S, double* partials, int add_ctc) {
+th_step2_second(const __grid_constant__ Vecs V, ThScalars* S, double* partials, int add_ctc, real q_tolerance, ThHostFlags* hf, int epoch) {
     if (S->done) return;
     double acc[2] = {0.0, 0.0};
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < TH_NUNK; i += (long long)gridDim.x * blockDim.x) {
@@ -369,26 +471,34 @@ th_step2_second(const __grid_constant__ Vecs V, ThScalars* S, double* partials, 
         real Ax = V.Adelta[i];
         if (add_ctc) Ax += V.CtC[i] * delta;
         const real b = V.b[i];
+        const real pre = TH_USEPRE ? V.pre[i] : (real)1;
         const real r = b - Ax;
+        const real z = TH_USEPRE ? pre * r : r;
         V.r[i] = r;
-        const real z = TH_USEPRE ? V.pre[i] * r : r;
         V.z[i] = z;
         acc[0] += (double)(z * r);
         acc[1] += (double)((real)0.5 * (delta * (r + b)));
     }
     double tot[2];
     if (th_grid_reduce<2>(acc, tot, partials, &S->ticket[2])) {
-        if (threadIdx.x == 0) { S->rz[(S->it + 1) & 1] = tot[0]; S->q = tot[1]; }
+        if (threadIdx.x == 0) {
+            S->rz[(S->it + 1) & 1] = tot[0]; S->q = tot[1];
+#if TH_TILED
+            th_close_iteration(S, q_tolerance, hf, epoch);
+#endif
+        }
     }
 }
 
+// PCGStep3 of the untiled schedules: beta = rz_new/rz_old; p = z + beta p; closes the iteration.
 extern "C" __global__ void __launch_bounds__(TH_BLOCK)
 th_step3(const __grid_constant__ Vecs V, ThScalars* S, real q_tolerance, ThHostFlags* hf, int epoch) {
     if (S->done) return;
     const real beta = th_beta(S);
+    const real* __restrict__ vz = V.z;
+    real* __restrict__ vp = V.p;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < TH_NUNK; i += (long long)gridDim.x * blockDim.x)
-        V.p[i] = V.z[i] + beta * V.p[i];
-    // the last block to finish closes the iteration: numerator hand-over, LM zeta test
+        vp[i] = vz[i] + beta * vp[i];
     __shared__ bool last;
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -398,28 +508,244 @@ th_step3(const __grid_constant__ Vecs V, ThScalars* S, real q_tolerance, ThHostF
     __syncthreads();
     if (last && threadIdx.x == 0) {
         S->ticket[3] = 0u;
-        const int it = S->it;
-        S->it = it + 1;
-        S->lin_done = it + 1;
-#if TH_LM
-        const real Q1 = (real)S->q, Q0 = (real)S->Q0;
-        if (!th_finite(Q1)) S->done = 1;
-        else {
-            const real zeta = (real)(it + 1) * (Q1 - Q0) / Q1;
-            if (!th_finite(zeta) || zeta < q_tolerance) S->done = 1;
-            else S->Q0 = (double)Q1;
-        }
-#endif
-        // progress report to the host through mapped pinned memory: lets the host stop
-        // issuing iterations after an LM early exit without ever synchronising
-        // (the reference blocks on a 4-byte cudaMemcpy every iteration, gauss_newton.t:1667)
-        if (hf) {
-            *(volatile long long*)&hf->progress = ((long long)epoch << 32) | (long long)(it + 1);
-            if (S->done) *(volatile int*)&hf->done_epoch = epoch;
-            __threadfence_system();
-        }
+        th_close_iteration(S, q_tolerance, hf, epoch);
     }
 }
+
+// ================================================================== hoisted invariants
+#if TH_AT_OUTPUT && TH_NCOEF > 0
+// Evaluated once per nonlinear iteration (J is constant across the PCG iterations of a step).
+extern "C" __global__ void __launch_bounds__(TH_BLOCK)
+th_precompute_coef(const __grid_constant__ Params P) {
+    ThIdx<th::dom_uw> idx;
+    if (th_uw_index(idx)) {
+        GAcc<th::dom_uw> a(idx, nullptr);
+        real c[TH_NCOEF];
+        th::coef_uw(a, P, c);
+        real* __restrict__ out = (real*)P.ptr[TH_COEF_SLOT];
+#pragma unroll
+        for (int i = 0; i < TH_NCOEF; ++i) out[idx.lin * TH_NCOEF + i] = c[i];
+    }
+}
+#endif
+
+// ================================================================== tiled operator kernel (2-D / 3-D image domains)
+#if TH_TILED
+#ifndef TH_PCG_A_MINB
+#define TH_PCG_A_MINB 3
+#endif
+__device__ __forceinline__ unsigned th_smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void th_mbar_init(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(th_smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void th_mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(th_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void th_mbar_wait(unsigned long long* bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}" ::"r"(th_smem_u32(bar)), "r"(parity) : "memory");
+}
+// TMA: one bulk tensor copy of a whole (tile + halo) box into shared memory; coordinates may be
+// negative or run past the image, the hardware fills out-of-bounds elements with zeros -- exactly
+// the reference's out-of-bounds load semantics (thallo.t:876-882).
+__device__ __forceinline__ void th_tma_load(void* dst, const ThTensorMap* map, unsigned long long* bar, int c0, int c1, int c2) {
+#if TH_UW_NDIM == 2
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(th_smem_u32(dst)), "l"((unsigned long long)map), "r"(th_smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+#else
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                 ::"r"(th_smem_u32(dst)), "l"((unsigned long long)map), "r"(th_smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+#endif
+}
+
+// Fallback loader (rows not 16-byte aligned, so no tensor map can describe the image): the block
+// fills the same box cooperatively with bounds-checked loads.
+template <class T>
+__device__ __forceinline__ void th_tile_load(T* __restrict__ dst, const T* __restrict__ src, int channels, int roww,
+                                             int x0, int y0, int z0, int tid) {
+    const int rowlen = TH_EXT_X * channels;
+    const int total = roww * TH_EXT_Y * TH_EXT_Z;
+    const long long W = th::dom_uw::D0 * channels, H = th::dom_uw::D1, D = th::dom_uw::D2;
+    for (int e = tid; e < total; e += TH_TILE_THREADS) {
+        const int c = e % roww, yy = (e / roww) % TH_EXT_Y, zz = e / (roww * TH_EXT_Y);
+        const long long gx = (long long)(x0 - TH_HX) * channels + c, gy = y0 - TH_HY + yy, gz = z0 - TH_HZ + zz;
+        const bool ok = c < rowlen && gx >= 0 && gx < W && gy >= 0 && gy < H && gz >= 0 && gz < D;
+        dst[e] = ok ? src[gx + W * (gy + H * gz)] : (T)0;
+    }
+}
+__device__ __forceinline__ void th_tile_load_es(void* dst, const void* src, int es, int channels, int roww, int x0, int y0, int z0, int tid) {
+    if (es == 1) th_tile_load((unsigned char*)dst, (const unsigned char*)src, channels, roww, x0, y0, z0, tid);
+    else if (es == 4) th_tile_load((unsigned int*)dst, (const unsigned int*)src, channels, roww, x0, y0, z0, tid);
+    else th_tile_load((unsigned long long*)dst, (const unsigned long long*)src, channels, roww, x0, y0, z0, tid);
+}
+
+// Accessor over the staged tiles: stencil taps of the vector argument and of every image that
+// is read at a non-zero offset come from shared memory (zero outside the image, courtesy of the
+// loader); images read only at the element itself are loaded straight from global memory.
+template <class Dom> struct TAcc {
+    ThIdx<Dom> i;
+    const unsigned char* sm;
+    int tx, ty, tz;
+    __device__ __forceinline__ TAcc(const ThIdx<Dom>& idx, const unsigned char* s, int x, int y, int z) : i(idx), sm(s), tx(x), ty(y), tz(z) {}
+    template <int D> __device__ __forceinline__ int coord() const { return i.c[D]; }
+    template <int L0, int H0, int L1, int H1, int L2, int H2> __device__ __forceinline__ bool inb() const {
+        bool ok = true;
+        if (L0 < 0) ok = ok && (i.c[0] + L0 >= 0);
+        if (H0 > 0) ok = ok && (i.c[0] + H0 < Dom::D0);
+        if (Dom::ND > 1) {
+            if (L1 < 0) ok = ok && (i.c[1] + L1 >= 0);
+            if (H1 > 0) ok = ok && (i.c[1] + H1 < Dom::D1);
+        }
+        if (Dom::ND > 2) {
+            if (L2 < 0) ok = ok && (i.c[2] + L2 >= 0);
+            if (H2 > 0) ok = ok && (i.c[2] + H2 < Dom::D2);
+        }
+        return ok;
+    }
+    template <int O0, int O1, int O2> __device__ __forceinline__ int tile_elem(int roww, int channels) const {
+        return ((tz + TH_HZ + O2) * TH_EXT_Y + (ty + TH_HY + O1)) * roww + (tx + TH_HX + O0) * channels;
+    }
+    template <int SLOT, class CT, int C, int CH, int O0, int O1, int O2>
+    __device__ __forceinline__ real img(const Params& P) const {
+        constexpr int s = TH_SLOT_STAGE[SLOT];
+        if constexpr (s >= 0) {
+            const CT* t = (const CT*)(sm + TH_STAGE[s >= 0 ? s : 0].off);
+            return (real)t[tile_elem<O0, O1, O2>(TH_STAGE[s >= 0 ? s : 0].roww, C) + CH];
+        } else {
+            static_assert((O0 | O1 | O2) == 0, "image read at an offset must be staged");
+            return ThLoad<CT, C, CH>::ld(P.ptr[SLOT], i.lin);
+        }
+    }
+    template <int K, int CH, int O0, int O1, int O2> __device__ __forceinline__ real vec() const {
+        const real* t = (const real*)(sm + TH_VTILE[K].poff);
+        return t[tile_elem<O0, O1, O2>(TH_VTILE[K].roww, TH_UIMG[K].channels) + CH];
+    }
+    template <int SLOT> __device__ __forceinline__ real samp(const Params& P, real x, real y) const {
+        GAcc<Dom> g(i, nullptr);
+        return g.template samp<SLOT>(P, x, y);
+    }
+};
+
+// mode 0: p_new = z + beta p_old (beta = 0 on the first iteration), Ap = (JtJ [+CtC]) p_new,
+//         alphaDenominator = <p_new, Ap>; p_old is read from buffer it&1, p_new written to (it+1)&1
+//         (neighbouring blocks still read p_old in their halos).
+// mode 1: Adelta = (JtJ [+CtC]) delta   (LM residual reset, gauss_newton.t:755-762)
+template <bool TMA>
+__device__ __forceinline__ void th_pcg_a_impl(const Params& P, const Vecs& V, const ThMaps& M, ThScalars* S, double* partials, int mode) {
+    extern __shared__ __align__(128) unsigned char th_sm[];
+    __shared__ __align__(8) unsigned long long bar;
+    if (S->done) return;
+    const int it = S->it;
+    const int tx = threadIdx.x, ty = threadIdx.y, tz = threadIdx.z;
+    const int tid = tx + TH_TW * (ty + TH_TH * tz);
+    const int x0 = blockIdx.x * TH_TW, y0 = blockIdx.y * TH_TH, z0 = blockIdx.z * TH_TD;
+    const bool upd = mode == 0 && it > 0;
+    const int psrc = mode ? 2 : (it & 1);
+    if (TMA) {
+        if (tid == 0) th_mbar_init(&bar, 1);
+        __syncthreads();
+        if (tid == 0) {
+            unsigned bytes = 0;
+#pragma unroll
+            for (int k = 0; k < TH_NUM_UIMG; ++k) bytes += (unsigned)TH_VTILE[k].bytes * (upd ? 2u : 1u);
+#pragma unroll
+            for (int s = 0; s < TH_NSTAGE; ++s) bytes += (unsigned)(TH_STAGE[s].roww * TH_STAGE[s].es * TH_EXT_Y * TH_EXT_Z);
+            th_mbar_expect_tx(&bar, bytes);
+#pragma unroll
+            for (int k = 0; k < TH_NUM_UIMG; ++k) {
+                const int c0 = (x0 - TH_HX) * TH_UIMG[k].channels;
+                if (mode == 0 && it == 0) th_tma_load(th_sm + TH_VTILE[k].poff, &M.z[k], &bar, c0, y0 - TH_HY, z0 - TH_HZ);
+                else {
+                    if (upd) th_tma_load(th_sm + TH_VTILE[k].zoff, &M.z[k], &bar, c0, y0 - TH_HY, z0 - TH_HZ);
+                    th_tma_load(th_sm + TH_VTILE[k].poff, &M.p[psrc][k], &bar, c0, y0 - TH_HY, z0 - TH_HZ);
+                }
+            }
+#pragma unroll
+            for (int s = 0; s < TH_NSTAGE; ++s)
+                th_tma_load(th_sm + TH_STAGE[s].off, &M.st[s], &bar, (x0 - TH_HX) * TH_STAGE[s].channels, y0 - TH_HY, z0 - TH_HZ);
+        }
+        th_mbar_wait(&bar, 0);
+    } else {
+        const real* psrcv = mode ? V.delta : ((it & 1) ? V.p2 : V.p);
+#pragma unroll
+        for (int k = 0; k < TH_NUM_UIMG; ++k) {
+            const int ch = TH_UIMG[k].channels;
+            if (mode == 0 && it == 0) th_tile_load((real*)(th_sm + TH_VTILE[k].poff), V.z + TH_UIMG[k].offset, ch, TH_VTILE[k].roww, x0, y0, z0, tid);
+            else {
+                if (upd) th_tile_load((real*)(th_sm + TH_VTILE[k].zoff), V.z + TH_UIMG[k].offset, ch, TH_VTILE[k].roww, x0, y0, z0, tid);
+                th_tile_load((real*)(th_sm + TH_VTILE[k].poff), psrcv + TH_UIMG[k].offset, ch, TH_VTILE[k].roww, x0, y0, z0, tid);
+            }
+        }
+#pragma unroll
+        for (int s = 0; s < TH_NSTAGE; ++s)
+            th_tile_load_es(th_sm + TH_STAGE[s].off, P.ptr[TH_STAGE[s].slot], TH_STAGE[s].es, TH_STAGE[s].channels, TH_STAGE[s].roww, x0, y0, z0, tid);
+        __syncthreads();
+    }
+    if (upd) {
+        const real beta = th_beta_prev(S);
+#pragma unroll
+        for (int k = 0; k < TH_NUM_UIMG; ++k) {
+            real* __restrict__ pt = (real*)(th_sm + TH_VTILE[k].poff);
+            const real* __restrict__ zt = (const real*)(th_sm + TH_VTILE[k].zoff);
+            const int n = TH_VTILE[k].bytes / (int)sizeof(real);
+            for (int e = tid; e < n; e += TH_TILE_THREADS) pt[e] = zt[e] + beta * pt[e];
+        }
+        __syncthreads();
+    }
+    real* __restrict__ out = mode ? V.Adelta : V.Ap;
+    real* __restrict__ pnew = ((it + 1) & 1) ? V.p2 : V.p;
+    ThIdx<th::dom_uw> idx;
+    double acc[1] = {0.0};
+    if (idx.from_coords(x0 + tx, y0 + ty, z0 + tz)) {
+        TAcc<th::dom_uw> a(idx, th_sm, tx, ty, tz);
+        if (!th::exclude_u0(a, P)) {
+            real o[TH_U];
+            th::applyJTJ_uw(a, P, o);
+            real dot = (real)0;
+            int j = 0;
+#pragma unroll
+            for (int k = 0; k < TH_NUM_UIMG; ++k) {
+                const real* pt = (const real*)(th_sm + TH_VTILE[k].poff);
+                const int te = a.template tile_elem<0, 0, 0>(TH_VTILE[k].roww, TH_UIMG[k].channels);
+#pragma unroll
+                for (int ch = 0; ch < TH_UIMG[k].channels; ++ch, ++j) {
+                    const long long off = TH_UIMG[k].offset + idx.lin * TH_UIMG[k].channels + ch;
+                    const real pv = pt[te + ch];
+                    real val = o[j];
+#if TH_LM
+                    val += V.CtC[off] * pv;
+#endif
+                    out[off] = val;
+                    if (mode == 0) pnew[off] = pv;
+                    dot += pv * val;
+                }
+            }
+            acc[0] = (double)dot;
+        }
+    }
+    if (mode) return;
+    double tot[1];
+    if (th_grid_reduce<1>(acc, tot, partials, &S->ticket[1])) {
+        if (tid == 0) S->aD = tot[0];
+    }
+}
+extern "C" __global__ void __launch_bounds__(TH_TILE_THREADS, TH_PCG_A_MINB)
+th_pcg_a(const __grid_constant__ Params P, const __grid_constant__ Vecs V, const __grid_constant__ ThMaps M, ThScalars* S, double* partials, int mode) {
+    th_pcg_a_impl<true>(P, V, M, S, partials, mode);
+}
+extern "C" __global__ void __launch_bounds__(TH_TILE_THREADS, TH_PCG_A_MINB)
+th_pcg_a_ld(const __grid_constant__ Params P, const __grid_constant__ Vecs V, const __grid_constant__ ThMaps M, ThScalars* S, double* partials, int mode) {
+    th_pcg_a_impl<false>(P, V, M, S, partials, mode);
+}
+#endif  // TH_TILED
 
 // ------------------------------------------------------------------ per-unknown-image dispatch for flat kernels
 template <int K> struct ThExclude;

@@ -38,6 +38,7 @@ struct Params {
 struct Vecs {
     real* delta; real* r; real* b; real* Adelta; real* z; real* p; real* Ap;
     real* CtC; real* pre; real* SSq;
+    real* p2;      // second search-direction buffer: the tiled operator kernel ping-pongs p (see th_pcg_a)
 };
 
 // Device-resident scalars.  rz[] double-buffers the CG numerator so that no
@@ -66,6 +67,29 @@ struct ThGroup { int ndim; int dim[TH_MAXD]; int nterms; int nnz; };
 __device__ constexpr ThUImg TH_UIMG[TH_NUM_UIMG] = TH_UIMG_TABLE;
 __device__ constexpr ThGroup TH_GROUPS[TH_NGROUPS] = TH_GROUP_TABLE;
 __device__ constexpr long long TH_DIMS[TH_NDIMS] = TH_DIM_SIZES;
+
+#if TH_TILED
+// Shared-memory tile layout of the tiled operator kernel (computed by the front end):
+// every staged array is a box of (TH_TW+2*TH_HX) x (TH_TH+2*TH_HY) x (TH_TD+2*TH_HZ) elements,
+// rows padded to 16 bytes (the TMA box granularity), bases 128-byte aligned.
+struct ThStage { int slot; int es; int channels; int roww; int off; };
+struct ThVTile { int roww; int zoff; int poff; int bytes; };
+__device__ constexpr ThStage TH_STAGE[TH_NSTAGE > 0 ? TH_NSTAGE : 1] = TH_STAGE_TABLE;
+__device__ constexpr int TH_SLOT_STAGE[TH_NPTR] = TH_SLOT_STAGE_TABLE;
+__device__ constexpr ThVTile TH_VTILE[TH_NUM_UIMG] = TH_VTILE_TABLE;
+#define TH_EXT_X (TH_TW + 2 * TH_HX)
+#define TH_EXT_Y (TH_TH + 2 * TH_HY)
+#define TH_EXT_Z (TH_TD + 2 * TH_HZ)
+#define TH_TILE_THREADS (TH_TW * TH_TH * TH_TD)
+// opaque 128-byte CUtensorMap (cuda.h is not available under NVRTC)
+struct alignas(64) ThTensorMap { unsigned long long q[16]; };
+// z: preconditioned residual; p[0], p[1]: the two search-direction buffers; p[2]: delta (for A*delta in LM)
+struct ThMaps {
+    ThTensorMap z[TH_NUM_UIMG];
+    ThTensorMap p[3][TH_NUM_UIMG];
+    ThTensorMap st[TH_NSTAGE > 0 ? TH_NSTAGE : 1];
+};
+#endif
 
 // ---- math (IEEE-accurate device functions; no fast-math)
 __device__ __forceinline__ float th_sqrt(float x) { return sqrtf(x); }

@@ -65,6 +65,12 @@ bool parse_descriptor(const std::string& text, PlanDesc& d, std::string& err) {
             d.groups.push_back(g);
         } else if (key == "U") ls >> d.U;
         else if (key == "uw_dims") { int n; ls >> n; d.uw_dims.resize(n); for (auto& x : d.uw_dims) ls >> x; }
+        else if (key == "ncoef") ls >> d.ncoef;
+        else if (key == "tile") {
+            ls >> d.tile[0] >> d.tile[1] >> d.tile[2] >> d.halo[0] >> d.halo[1] >> d.halo[2] >> d.smem_bytes;
+            d.tiled = true;
+        } else if (key == "vtile") { VTileDesc v; ls >> v.roww >> v.zoff >> v.poff >> v.bytes; d.vtiles.push_back(v); }
+        else if (key == "stage") { StageDesc t; ls >> t.slot >> t.ctype >> t.es >> t.channels >> t.roww >> t.off >> t.bytes; d.stages.push_back(t); }
         if (ls.fail() && !ls.eof()) { err = "malformed descriptor line: " + line; return false; }
     }
     if (d.nunk <= 0 || d.unknowns.empty() || d.groups.empty()) { err = "descriptor lacks unknowns or residual groups"; return false; }
@@ -73,8 +79,9 @@ bool parse_descriptor(const std::string& text, PlanDesc& d, std::string& err) {
 }
 
 // ------------------------------------------------------------------ plan
-static const char* kVecNames[12] = {"delta", "r", "b", "Adelta", "z", "p", "Ap_X", "CtC", "preconditioner", "SSq", "prevX", "initX"};
-enum { V_DELTA, V_R, V_B, V_ADELTA, V_Z, V_P, V_AP, V_CTC, V_PRE, V_SSQ, V_PREVX, V_INITX };
+static const int kNumVecs = 13;
+static const char* kVecNames[kNumVecs] = {"delta", "r", "b", "Adelta", "z", "p", "Ap_X", "CtC", "preconditioner", "SSq", "prevX", "initX", "p2"};
+enum { V_DELTA, V_R, V_B, V_ADELTA, V_Z, V_P, V_AP, V_CTC, V_PRE, V_SSQ, V_PREVX, V_INITX, V_P2 };
 
 void Plan::log(const char* fmt, ...) const {
     if (opts_->init.verbosityLevel <= 0) return;
@@ -97,9 +104,14 @@ Plan::Plan(const StateOptions* opts, const PlanDesc& desc, const std::string& so
 
     // solver vectors: one allocation, 12 unknown-sized vectors (gauss_newton.t:1963-2071)
     vec_stride_ = ((size_t)d_.nunk * real_size_ + 255) / 256 * 256;
-    CD(cudaMalloc((void**)&vec_block_, vec_stride_ * 12));
-    CD(cudaMemsetAsync(vec_block_, 0, vec_stride_ * 12, stream()));
-    for (int i = 0; i < 12; ++i) vecs_[i] = vec_block_ + vec_stride_ * i;
+    CD(cudaMalloc((void**)&vec_block_, vec_stride_ * kNumVecs));
+    CD(cudaMemsetAsync(vec_block_, 0, vec_stride_ * kNumVecs, stream()));
+    for (int i = 0; i < kNumVecs; ++i) vecs_[i] = vec_block_ + vec_stride_ * i;
+    if (d_.ncoef > 0) {
+        const size_t n = (size_t)d_.unknowns[0].elements * d_.ncoef * real_size_;
+        CD(cudaMalloc(&coef_, n));
+        CD(cudaMemsetAsync(coef_, 0, n, stream()));
+    }
     CD(cudaMalloc(&d_scalars_, sizeof(HScalars)));
     CD(cudaMemsetAsync(d_scalars_, 0, sizeof(HScalars), stream()));
     CD(cudaHostAlloc((void**)&h_scalars_, sizeof(HScalars), cudaHostAllocDefault));
@@ -121,6 +133,11 @@ Plan::Plan(const StateOptions* opts, const PlanDesc& desc, const std::string& so
         else if (d_.uw_dims.size() == 2) b = ((d_.uw_dims[0] + 31) / 32) * ((d_.uw_dims[1] + 7) / 8);
         else b = ((d_.uw_dims[0] + 7) / 8) * ((d_.uw_dims[1] + 7) / 8) * ((d_.uw_dims[2] + 3) / 4);
         maxblocks = std::max(maxblocks, b);
+        if (d_.tiled) {
+            long long t = 1;
+            for (size_t i = 0; i < d_.uw_dims.size(); ++i) t *= (d_.uw_dims[i] + d_.tile[i] - 1) / d_.tile[i];
+            maxblocks = std::max(maxblocks, t);
+        }
     }
     for (auto& g : d_.groups) maxblocks = std::max(maxblocks, (g.count + 255) / 256);
     CD(cudaMalloc((void**)&d_partials_, sizeof(double) * 2 * (size_t)maxblocks));
@@ -130,14 +147,71 @@ Plan::Plan(const StateOptions* opts, const PlanDesc& desc, const std::string& so
     size_t psz = nptr * 8 + (nsc + 4) * real_size_;
     psz = (psz + 7) / 8 * 8;
     params_buf_.assign(psz, 0);
-    vecs_buf_.assign(10 * sizeof(void*), 0);
+    vecs_buf_.assign(11 * sizeof(void*), 0);
     memcpy(vecs_buf_.data(), vecs_, 10 * sizeof(void*));
+    memcpy(vecs_buf_.data() + 10 * sizeof(void*), &vecs_[V_P2], sizeof(void*));
+    if (d_.tiled) {
+        maps_buf_.assign(128 * (4 * d_.unknowns.size() + std::max<size_t>(1, d_.stages.size())) + 64, 0);
+        build_vector_maps();
+        for (const char* kn : {"th_pcg_a", "th_pcg_a_ld"}) {
+            CUfunction f = fn(kn);
+            if (d_.smem_bytes > 48 * 1024 && api.FuncSetAttribute)
+                CU(api.FuncSetAttribute(f, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, d_.smem_bytes));
+        }
+    }
     sp_ = SolverParameters();
     ok_ = true;
 }
 
+// ------------------------------------------------------------------ TMA descriptors of the staged tiles
+// One tensor map per staged array: the image as a rank-ND tensor of scalars (innermost extent
+// W*channels), box = tile + halo with rows padded to 16 bytes, zero fill outside the image.
+static char* maps_base(std::vector<char>& b) {
+    return reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(b.data()) + 63) & ~uintptr_t(63));
+}
+bool Plan::encode_map(void* dst, const void* base, int es, const std::string& ctype, int channels, int roww) {
+    const DriverApi& api = DriverApi::get();
+    if (!api.TensorMapEncodeTiled) return false;
+    const int nd = (int)d_.uw_dims.size();
+    cuuint64_t gdim[3] = {1, 1, 1};
+    cuuint64_t gstride[2] = {0, 0};
+    cuuint32_t box[3] = {1, 1, 1}, estr[3] = {1, 1, 1};
+    gdim[0] = (cuuint64_t)d_.uw_dims[0] * channels;
+    for (int i = 1; i < nd; ++i) gdim[i] = (cuuint64_t)d_.uw_dims[i];
+    gstride[0] = gdim[0] * es;
+    gstride[1] = gstride[0] * gdim[1];
+    box[0] = (cuuint32_t)roww;
+    for (int i = 1; i < nd; ++i) box[i] = (cuuint32_t)(d_.tile[i] + 2 * d_.halo[i]);
+    if ((reinterpret_cast<uintptr_t>(base) & 15) || (gstride[0] & 15) || box[0] > 256) return false;
+    CUtensorMapDataType dt = CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+    if (ctype == "uchar") dt = CU_TENSOR_MAP_DATA_TYPE_UINT8;
+    else if (ctype == "int") dt = CU_TENSOR_MAP_DATA_TYPE_INT32;
+    else if (es == 8) dt = CU_TENSOR_MAP_DATA_TYPE_FLOAT64;
+    CUtensorMap m;
+    CUresult r = api.TensorMapEncodeTiled(&m, dt, (cuuint32_t)nd, const_cast<void*>(base), gdim, gstride, box, estr,
+                                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                          CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return false;
+    static_assert(sizeof(CUtensorMap) == 128, "CUtensorMap is 128 bytes");
+    memcpy(dst, &m, 128);
+    return true;
+}
+void Plan::build_vector_maps() {
+    char* mb = maps_base(maps_buf_);
+    const size_t nu = d_.unknowns.size();
+    const int src[4] = {V_Z, V_P, V_P2, V_DELTA};      // ThMaps: z[nu], p[3][nu]
+    vector_maps_ok_ = true;
+    for (int v = 0; v < 4; ++v)
+        for (size_t k = 0; k < nu; ++k) {
+            const char* base = (const char*)vecs_[src[v]] + (size_t)d_.unknowns[k].offset * real_size_;
+            if (!encode_map(mb + 128 * (v * nu + k), base, (int)real_size_, "real", d_.unknowns[k].channels, d_.vtiles[k].roww))
+                vector_maps_ok_ = false;
+        }
+}
+
 Plan::~Plan() {
     if (vec_block_) cudaFree(vec_block_);
+    if (coef_) cudaFree(coef_);
     if (d_scalars_) cudaFree(d_scalars_);
     if (d_partials_) cudaFree(d_partials_);
     if (h_scalars_) cudaFreeHost(h_scalars_);
@@ -165,7 +239,7 @@ CUfunction Plan::fn(const std::string& name) {
     return f;
 }
 
-void Plan::launch(CUfunction f, dim3 grid, dim3 block, void** args) {
+void Plan::launch(CUfunction f, dim3 grid, dim3 block, void** args, unsigned smem) {
     const bool timed = opts_->init.timingLevel >= 2;   // per-kernel events, util.t:774-790
     Span s;
     if (timed) {
@@ -173,7 +247,7 @@ void Plan::launch(CUfunction f, dim3 grid, dim3 block, void** args) {
         else { CD(cudaEventCreate(&s.a)); CD(cudaEventCreate(&s.b)); }
         CD(cudaEventRecord(s.a, stream()));
     }
-    CU(DriverApi::get().LaunchKernel(f, grid.x, grid.y, grid.z, block.x, block.y, block.z, 0, (CUstream)stream(), args, nullptr));
+    CU(DriverApi::get().LaunchKernel(f, grid.x, grid.y, grid.z, block.x, block.y, block.z, smem, (CUstream)stream(), args, nullptr));
     ++launches;
     if (timed) {
         CD(cudaEventRecord(s.b, stream()));
@@ -216,7 +290,25 @@ void Plan::clear(void* p) { CD(cudaMemsetAsync(p, 0, (size_t)d_.nunk * real_size
 void Plan::bind(void** params) {
     char* buf = params_buf_.data();
     const size_t nptr = std::max<size_t>(1, d_.ptr_pidx.size()), nsc = std::max<size_t>(1, d_.scalars.size());
-    for (size_t i = 0; i < d_.ptr_pidx.size(); ++i) memcpy(buf + 8 * i, &params[d_.ptr_pidx[i]], 8);
+    for (size_t i = 0; i < d_.ptr_pidx.size(); ++i) {
+        if (d_.ptr_pidx[i] < 0) memcpy(buf + 8 * i, &coef_, 8);          // plan-owned coefficient image
+        else memcpy(buf + 8 * i, &params[d_.ptr_pidx[i]], 8);
+    }
+    if (d_.tiled) {
+        // tensor maps of the caller-owned staged images are re-encoded on every bind (the caller may
+        // pass different buffers at every step, util.t:609-643); any image TMA cannot describe
+        // (unaligned base or row pitch) switches the plan to the cooperative-load variant.
+        char* mb = maps_base(maps_buf_);
+        bool ok = vector_maps_ok_ && !getenv("THALLO_B200_NO_TMA");
+        for (size_t s = 0; s < d_.stages.size() && ok; ++s) {
+            const StageDesc& t = d_.stages[s];
+            void* base = nullptr;
+            memcpy(&base, buf + 8 * t.slot, 8);
+            ok = encode_map(mb + 128 * (4 * d_.unknowns.size() + s), base, t.es, t.ctype, t.channels, t.roww);
+        }
+        use_tma_ = ok;
+        pcg_a_ = fn(ok ? "th_pcg_a" : "th_pcg_a_ld");
+    }
     char* sc = buf + 8 * nptr;
     for (size_t i = 0; i < d_.scalars.size(); ++i) {
         const void* hp = params[d_.scalars[i].pidx];
@@ -314,6 +406,7 @@ void Plan::init(void** params) {
     bind(params);
     // solver vectors start from zero so that excluded unknowns stay zero everywhere
     CD(cudaMemsetAsync(vec_block_, 0, vec_stride_ * 10, stream()));
+    CD(cudaMemsetAsync(vecs_[V_P2], 0, vec_stride_, stream()));
     prev_cost_ = compute_cost();
     {   // initX = X (copyUnknownwise)
         int dir = 0;
@@ -339,11 +432,26 @@ double Plan::cost() {   // gauss_newton.t:1787-1793
     return prev_cost_;
 }
 
+void Plan::launch_tiled(int mode) {
+    void* a[] = {params_buf_.data(), vecs_buf_.data(), maps_base(maps_buf_), &d_scalars_, &d_partials_, &mode};
+    dim3 grid(1, 1, 1), block((unsigned)d_.tile[0], (unsigned)d_.tile[1], (unsigned)d_.tile[2]);
+    unsigned* g[3] = {&grid.x, &grid.y, &grid.z};
+    for (size_t i = 0; i < d_.uw_dims.size(); ++i) *g[i] = (unsigned)((d_.uw_dims[i] + d_.tile[i] - 1) / d_.tile[i]);
+    launch(pcg_a_, grid, block, a, (unsigned)d_.smem_bytes);
+}
+
 void Plan::linear_iteration(int l) {
     void* P = params_buf_.data();
     void* V = vecs_buf_.data();
     int zero = 0, one = 1;
-    if (d_.at_output) {
+    float qf = sp_.q_tolerance;
+    double qd = sp_.q_tolerance;
+    void* qtol = d_.is_double ? (void*)&qd : (void*)&qf;
+    const bool reset = d_.lm && ((l + 1) % sp_.residual_reset_period) == 0;   // gauss_newton.t:1653-1660
+    // ---- operator: Ap = (JtJ [+CtC]) p and alphaDenominator
+    if (d_.tiled) {
+        launch_tiled(0);          // also forms p = z + beta p (PCGStep3 of the previous iteration)
+    } else if (d_.at_output) {
         void* a[] = {P, V, &d_scalars_, &d_partials_, &zero};
         launch_uw(fn("th_step1_uw"), a);
     } else {
@@ -356,13 +464,16 @@ void Plan::linear_iteration(int l) {
         void* a[] = {P, V, &d_scalars_, &d_partials_, &zero};
         launch_flat(fn("th_step1_finish"), a);
     }
-    if (d_.lm && ((l + 1) % sp_.residual_reset_period) == 0) {   // gauss_newton.t:1653-1660
+    // ---- update of delta, r, z and the two dot products
+    if (reset) {
         {
             void* a[] = {V, &d_scalars_};
             launch_flat(fn("th_step2_first"), a);
         }
         int add_ctc = 0;
-        if (d_.at_output) {
+        if (d_.tiled) {
+            launch_tiled(1);
+        } else if (d_.at_output) {
             void* a[] = {P, V, &d_scalars_, &d_partials_, &one};
             launch_uw(fn("th_step1_uw"), a);
         } else {
@@ -376,16 +487,15 @@ void Plan::linear_iteration(int l) {
             launch_flat(fn("th_step1_finish"), a);
             add_ctc = 1;
         }
-        void* a[] = {V, &d_scalars_, &d_partials_, &add_ctc};
+        void* a[] = {V, &d_scalars_, &d_partials_, &add_ctc, qtol, &d_flags_, &epoch_};
         launch_flat(fn("th_step2_second"), a);
     } else {
-        void* a[] = {V, &d_scalars_, &d_partials_};
-        launch_flat(fn("th_step2"), a);
+        void* a[] = {V, &d_scalars_, &d_partials_, qtol, &d_flags_, &epoch_};
+        launch_flat(fn("th_pcg_b"), a);
     }
-    {
-        float qf = sp_.q_tolerance;
-        double qd = sp_.q_tolerance;
-        void* a[] = {V, &d_scalars_, d_.is_double ? (void*)&qd : (void*)&qf, &d_flags_, &epoch_};
+    // ---- p = z + beta p (fused into the next th_pcg_a in the tiled schedule)
+    if (!d_.tiled) {
+        void* a[] = {V, &d_scalars_, qtol, &d_flags_, &epoch_};
         launch_flat(fn("th_step3"), a);
     }
 }
@@ -400,6 +510,10 @@ int Plan::step(void** params) {
     span_begin(cur_phase_);
     ++epoch_;
     int first = sp_.nIter == 0;
+    if (d_.ncoef > 0) {   // PCG-invariant parts of J, once per nonlinear iteration
+        void* a[] = {P};
+        launch_uw(fn("th_precompute_coef"), a);
+    }
     if (d_.at_output) {
         void* a[] = {P, V, &d_scalars_, &d_partials_, &first};
         launch_uw(fn("th_init_uw"), a);
@@ -533,7 +647,7 @@ void Plan::get_parameter(const char* name, void* value) {
 }
 
 long long Plan::read_vector(const char* name, void* dst, long long count) {
-    for (int i = 0; i < 12; ++i) {
+    for (int i = 0; i < kNumVecs; ++i) {
         if (strcmp(name, kVecNames[i]) == 0) {
             const long long n = std::min<long long>(count, d_.nunk);
             CD(cudaMemcpyAsync(dst, vecs_[i], (size_t)n * real_size_, cudaMemcpyDeviceToHost, stream()));

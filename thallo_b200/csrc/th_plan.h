@@ -17,6 +17,8 @@ namespace thallo {
 struct UnknownDesc { std::string name; int channels = 0; long long offset = 0; int pidx = 0; long long elements = 0; std::vector<int> dims; };
 struct GroupDesc { std::string name; long long count = 0; int nterms = 0; int materialize = 0; int nnz = 0; std::vector<int> domain; std::vector<int> row_nnz; };
 struct ScalarDesc { int pidx; std::string ctype; };
+struct VTileDesc { int roww = 0, zoff = 0, poff = 0, bytes = 0; };
+struct StageDesc { int slot = 0; std::string ctype; int es = 4, channels = 1, roww = 0, off = 0, bytes = 0; };
 
 struct PlanDesc {
     std::string name, kind, schedule;
@@ -29,6 +31,13 @@ struct PlanDesc {
     std::vector<GroupDesc> groups;
     int U = 0;
     std::vector<long long> uw_dims;
+    // tiled operator kernel (front end "tile"/"vtile"/"stage" lines) and hoisted-invariant image
+    int ncoef = 0;
+    bool tiled = false;
+    int tile[3] = {1, 1, 1}, halo[3] = {0, 0, 0};
+    int smem_bytes = 0;
+    std::vector<VTileDesc> vtiles;
+    std::vector<StageDesc> stages;
 };
 bool parse_descriptor(const std::string& text, PlanDesc& d, std::string& err);
 
@@ -88,7 +97,10 @@ public:
 private:
     struct Fn { CUfunction f = nullptr; };
     CUfunction fn(const std::string& name);
-    void launch(CUfunction f, dim3 grid, dim3 block, void** args);
+    void launch(CUfunction f, dim3 grid, dim3 block, void** args, unsigned smem = 0);
+    void launch_tiled(int mode);
+    bool encode_map(void* dst, const void* base, int es, const std::string& ctype, int channels, int roww);
+    void build_vector_maps();
     void launch_flat(CUfunction f, void** args);
     void launch_uw(CUfunction f, void** args);
     void launch_group(CUfunction f, int g, void** args);
@@ -114,7 +126,12 @@ private:
     // device state
     char* vec_block_ = nullptr;
     size_t vec_stride_ = 0;
-    void* vecs_[12] = {};          // delta r b Adelta z p Ap CtC pre SSq prevX initX
+    void* vecs_[13] = {};          // delta r b Adelta z p Ap CtC pre SSq prevX initX p2
+    void* coef_ = nullptr;         // hoisted PCG-invariant coefficients, ncoef reals per element
+    std::vector<char> maps_buf_;   // host image of the device struct ThMaps (128-byte CUtensorMap each)
+    bool use_tma_ = false;
+    bool vector_maps_ok_ = false;
+    CUfunction pcg_a_ = nullptr;
     void* d_scalars_ = nullptr;
     double* d_partials_ = nullptr;
     HScalars* h_scalars_ = nullptr;    // pinned

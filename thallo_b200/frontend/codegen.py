@@ -158,8 +158,10 @@ class Emitter:
 
 
 class Generator:
-    def __init__(self, L, name, kind, double=False, schedule="auto", lm_as_committed=False):
+    def __init__(self, L, name, kind, double=False, schedule="auto", lm_as_committed=False, hoist=True, tile=None):
         self.L, self.name = L, name
+        self.hoist_enabled = bool(hoist)
+        self.tile_request = tile
         self.double = bool(double)
         self.lm = (kind == "levenberg_marquardt") and not lm_as_committed
         self.kind = kind
@@ -200,6 +202,10 @@ class Generator:
             assert can_at_output, "compute_at_output needs every residual domain to equal the unknown domain"
         self.schedule = schedule
         self.udomain = next(iter(udoms)) if len(udoms) == 1 else None
+        # tiled form of the unknownwise operator (shared-memory stencil tiles, TMA-staged): 2-D / 3-D image domains
+        self.tiled = self.schedule == "at_output" and len(self.udomain) in (2, 3)
+        self.coef_exprs = []          # hoisted PCG-invariant per-element expressions (channels of the __coef image)
+        self._coef_index = {}
 
     # ---- small helpers
     def image(self, name):
@@ -287,10 +293,138 @@ class Generator:
                 out.append((t, dict(s), lst))
         return out
 
+    # ---- hoisting of PCG-invariant per-element subexpressions (at-output schedule)
+    # J does not change during the PCG iterations of one nonlinear step, but the reference's
+    # applyJTJ re-evaluates it (including sin/cos of the angles at the centre and every stencil
+    # neighbour) on every CG iteration.  Sub-expressions rooted at an
+    # expensive operator whose inputs are all read at the residual's own element (zero offsets)
+    # are evaluated once per nonlinear iteration into a plan-owned multi-channel image
+    # ("__coef"), and the operator reads that image (through the staged tile) instead.  The
+    # values are bit-identical: the same device function is applied to the same inputs.
+    _EXPENSIVE = ("sin", "cos", "tan", "exp", "log", "sqrt", "asin", "acos", "atan", "sinh", "cosh", "tanh", "pow", "sample")
+
+    def _pure0(self, e, memo):
+        """(pure, reads_image): every variable under e is a zero-offset dense access on the unknown
+        domain, a scalar Param or the element's own coordinate."""
+        r = memo.get(e.id)
+        if r is not None:
+            return r
+        if e.kind == "const":
+            r = (True, False)
+        elif e.kind == "var":
+            k = e.key
+            if isinstance(k, ImageAccess):
+                ok = (all(c[0] == "d" and c[2] == 0 for c in k.index)
+                      and tuple(c[1] for c in k.index) == tuple(self.udomain))
+                r = (ok, ok)
+            elif isinstance(k, Param):
+                r = (True, False)
+            elif isinstance(k, IndexValue):
+                r = (k.off == 0, False)
+            else:
+                r = (False, False)
+        else:
+            ok, img = True, False
+            for a in e.args:
+                o, i = self._pure0(a, memo)
+                ok, img = ok and o, img or i
+            if e.op == "sample":
+                img = True
+            r = (ok, img)
+        memo[e.id] = r
+        return r
+
+    def _hoist(self, e, memo, pmemo):
+        if e.id in memo:
+            return memo[e.id]
+        if e.kind != "apply":
+            r = e
+        else:
+            pure, img = self._pure0(e, pmemo)
+            if pure and img and e.op in self._EXPENSIVE and e.type == ad.REAL:
+                ch = self._coef_index.get(e.id)
+                if ch is None:
+                    ch = len(self.coef_exprs)
+                    self._coef_index[e.id] = ch
+                    self.coef_exprs.append(e)
+                index = tuple(("d", d, 0) for d in self.udomain)
+                r = ad.var(ImageAccess("__coef", index, ch))
+            else:
+                r = ad.rebuild(e, [self._hoist(a, memo, pmemo) for a in e.args])
+        memo[e.id] = r
+        return r
+
+    def _prepare_unknownwise(self):
+        """Hoist invariants out of the partial derivatives used by applyJTJ and register the
+        plan-owned coefficient image; must run before the header is emitted."""
+        self.inst = self._instances()
+        self.inst_h = self.inst
+        if self.hoist_enabled:
+            memo, pmemo = {}, {}
+            self.inst_h = [(t, s, [(j, self._hoist(p, memo, pmemo)) for j, p in lst]) for t, s, lst in self.inst]
+            # Jp of a whole term also needs the hoisted partials of *all* its unknowns
+            self.jp_h = {}
+            for t, s, lst in self.inst:
+                if id(t) in self.jp_h:
+                    continue
+                r = ad.const(0.0)
+                for u, p in zip(t.unknowns, t.partials):
+                    k = u.key
+                    r = r + self._hoist(p, memo, pmemo) * ad.var(VecArg("P", k.image, k.index, k.channel))
+                self.jp_h[id(t)] = r
+        if self.coef_exprs:
+            from .dsl import Image
+            im = Image("__coef", "real", len(self.coef_exprs), [self.L.dims[d] for d in self.udomain], -1, "plan")
+            self.images["__coef"] = im
+            self.ptr_slot["__coef"] = len(self.ptr_pidx)
+            self.ptr_pidx.append(-1)
+
+    def _tile_layout(self, roots):
+        """Shared-memory layout of the staged tiles of the tiled operator kernel."""
+        nd = len(self.udomain)
+        halo = self._halos(roots)
+        H = [0] * MAXD
+        for tbl in (halo["img"], halo["vec"]):
+            for v in tbl.values():
+                H = [max(a, b) for a, b in zip(H, v)]
+        tile = list(self.tile_request) if self.tile_request else ([32, 8, 1] if nd == 2 else [8, 8, 4])
+        tile = tile + [1] * (MAXD - len(tile))
+        es_real = 8 if self.double else 4
+        esz = dict(real=es_real, float=4, uchar=1, int=4, double=8)
+        ext = [tile[d] + 2 * H[d] for d in range(MAXD)]
+        off = 0
+        stages = []
+
+        def place(channels, es):
+            nonlocal off
+            row_bytes = -(-(ext[0] * channels * es) // 16) * 16
+            roww = row_bytes // es
+            nbytes = row_bytes * ext[1] * ext[2]
+            o = off
+            off = -(-(off + nbytes) // 128) * 128
+            return o, roww, nbytes
+        vt = []
+        for im in self.unknowns:                     # vector tiles: z and p per unknown image
+            zo, roww, nb = place(im.channels, es_real)
+            po, _, _ = place(im.channels, es_real)
+            vt.append(dict(name=im.name, channels=im.channels, roww=roww, zoff=zo, poff=po, bytes=nb))
+        slot_stage = [-1] * len(self.ptr_pidx)
+        for name, h in halo["img"].items():
+            if not any(h):
+                continue
+            im = self.images[name]
+            es = esz[im.ctype]
+            o, roww, nb = place(im.channels, es)
+            slot_stage[self.ptr_slot[name]] = len(stages)
+            stages.append(dict(name=name, slot=self.ptr_slot[name], ctype=im.ctype, es=es, channels=im.channels,
+                               roww=roww, off=o, bytes=nb))
+        self.tl = dict(tile=tile, halo=H, ext=ext, vt=vt, stages=stages, slot_stage=slot_stage, smem=off)
+        return self.tl
+
     def gen_unknownwise(self):
         dom = self.udomain
         src = []
-        inst = self._instances()
+        inst = self.inst
         U = self.U
         zero = ad.const(0.0)
         # evalJTF: g_j = sum partial*F, d_j = sum partial^2  (createjtfcentered)
@@ -311,10 +445,10 @@ class Generator:
             dom))
         # applyJTJ: out_j = sum partial * Jp   (createjtjcentered, residual-centric)
         out = [zero] * U
-        for t, s, lst in inst:
+        for t, s, lst in self.inst_h:
             memo = {}
             cond = _inb(s)
-            jp = shift(t.jp("P"), s, memo)
+            jp = shift(self.jp_h[id(t)] if self.hoist_enabled else t.jp("P"), s, memo)
             for j, p in lst:
                 ps = shift(p, s, memo)
                 out[j] = out[j] + ad.select(cond, ps * jp, 0.0)
@@ -324,6 +458,13 @@ class Generator:
         self.uw_roots = dict(g=g, d=d, out=out)        # kept for the NumPy interpreter (frontend/interp.py)
         # halo radius per image / vector argument for the tile-staged variant
         self.halo = self._halos(out)
+        if self.coef_exprs:
+            nc = len(self.coef_exprs)
+            src.append(self._fn(
+                "template <class A> __device__ __forceinline__ void coef_uw(const A& a, const Params& P, real* __restrict__ out)",
+                list(self.coef_exprs), lambda r: ["out[%d] = %s;" % (i, r[i]) for i in range(nc)], dom))
+        if self.tiled:
+            self._tile_layout(out)
         return "\n".join(src)
 
     def _halos(self, roots):
@@ -431,6 +572,8 @@ class Generator:
     def generate(self):
         L = self.L
         out = Lowered()
+        if self.schedule == "at_output":
+            self._prepare_unknownwise()
         hdr = []
         hdr.append("// generated by thallo_b200.frontend.codegen for energy '%s' (%s)" % (self.name, self.kind))
         hdr.append("#define TH_DOUBLE %d" % int(self.double))
@@ -459,10 +602,28 @@ class Generator:
             hdr.append("#define TH_UW_DIMS {%s}" % ", ".join(str(L.dims[d].size) for d in dom))
             body.append(self.gen_unknownwise())
             hdr.append("#define TH_U %d" % self.U)
+            hdr.append("#define TH_NCOEF %d" % len(self.coef_exprs))
+            if self.coef_exprs:
+                hdr.append("#define TH_COEF_SLOT %d" % self.ptr_slot["__coef"])
+            hdr.append("#define TH_TILED %d" % int(self.tiled))
+            if self.tiled:
+                tl = self.tl
+                hdr.append("#define TH_TW %d\n#define TH_TH %d\n#define TH_TD %d" % tuple(tl["tile"]))
+                hdr.append("#define TH_HX %d\n#define TH_HY %d\n#define TH_HZ %d" % tuple(tl["halo"]))
+                hdr.append("#define TH_SMEM_BYTES %d" % max(16, tl["smem"]))
+                hdr.append("#define TH_NSTAGE %d" % len(tl["stages"]))
+                hdr.append("#define TH_STAGE_TABLE {%s}" % (", ".join(
+                    "{%d, %d, %d, %d, %d}" % (st["slot"], st["es"], st["channels"], st["roww"], st["off"])
+                    for st in tl["stages"]) or "{0, 0, 0, 0, 0}"))
+                hdr.append("#define TH_SLOT_STAGE_TABLE {%s}" % ", ".join(map(str, tl["slot_stage"])))
+                hdr.append("#define TH_VTILE_TABLE {%s}" % ", ".join(
+                    "{%d, %d, %d, %d}" % (v["roww"], v["zoff"], v["poff"], v["bytes"]) for v in tl["vt"]))
         gl = []
         for gi, g in enumerate(self.groups):
             body.append(self.gen_group(gi, g))
             gl.append("X(%d)" % gi)
+        if self.schedule != "at_output":
+            hdr.append("#define TH_TILED 0\n#define TH_NCOEF 0")
         hdr.append("#define TH_GROUP_LIST(X) %s" % " ".join(gl))
         # group domain table
         rows = []
@@ -502,6 +663,10 @@ class Generator:
             d["uw_dims"] = [L.dims[x].size for x in self.udomain]
             d["halo_img"] = {k: v for k, v in self.halo["img"].items()}
             d["halo_vec"] = {k: v for k, v in self.halo["vec"].items()}
+            d["ncoef"] = len(self.coef_exprs)
+            d["tiled"] = int(self.tiled)
+            if self.tiled:
+                d["tile"] = self.tl
         out.desc = d
         return out
 
@@ -536,14 +701,22 @@ def descriptor_text(d):
     if d["schedule"] == "at_output":
         ln.append("U %d" % d["U"])
         ln.append("uw_dims %d %s" % (len(d["uw_dims"]), " ".join(map(str, d["uw_dims"]))))
+        ln.append("ncoef %d" % d.get("ncoef", 0))
+        if d.get("tiled"):
+            tl = d["tile"]
+            ln.append("tile %s %s %d" % (" ".join(map(str, tl["tile"])), " ".join(map(str, tl["halo"])), tl["smem"]))
+            for v in tl["vt"]:
+                ln.append("vtile %d %d %d %d" % (v["roww"], v["zoff"], v["poff"], v["bytes"]))
+            for st in tl["stages"]:
+                ln.append("stage %d %s %d %d %d %d %d" % (st["slot"], st["ctype"], st["es"], st["channels"], st["roww"], st["off"], st["bytes"]))
     return "\n".join(ln) + "\n"
 
 
 def lower(define, dims, kind="gauss_newton", name="energy", double=False, schedule="auto",
-          lm_as_committed=False, **define_kwargs):
+          lm_as_committed=False, hoist=True, tile=None, **define_kwargs):
     from .dsl import build_spec
     L = build_spec(define, dims, **define_kwargs)
-    gen = Generator(L, name, kind, double, schedule, lm_as_committed)
+    gen = Generator(L, name, kind, double, schedule, lm_as_committed, hoist, tile)
     out = gen.generate()
     out.generator = gen
     return out

@@ -43,6 +43,11 @@ class Interp:
         return o
 
     def _image(self, name):
+        if name == "__coef":      # plan-owned image of hoisted invariants: evaluate its defining expressions in place
+            if "__coef" not in self.cache:
+                self.cache["__coef"] = np.stack([np.broadcast_to(v, self.shape).astype(self.dt)
+                                                 for v in self.eval(self.gen.coef_exprs)], axis=-1)
+            return self.cache["__coef"]
         im = self.gen.images[name]
         a = np.asarray(self.params[im.pidx]).astype(self.dt).reshape(self.shape + (im.channels,))
         return a

@@ -92,3 +92,63 @@ def image_warping_inputs(W, H, seed=1, w_fit=100.0, w_reg=0.01):
 def image_warping_params(d):
     return [d["Offset"], d["Angle"], d["UrShape"], d["Constraints"], d["Mask"],
             np.array([d["w_fitSqrt"]], np.float32), np.array([d["w_regSqrt"]], np.float32)]
+
+
+def optical_flow_inputs(W, H, seed=1, w_fit=10.0, w_reg=0.1):
+    """Config 3a synthetic shape: I = band-limited texture (16 seeded sinusoids),
+    I_hat = I translated by (0.6, -0.4) px, I_hat_dx/dy = Prewitt/8 with a zero border
+    (examples/optical_flow/src/CombinedSolver.h:149-175), X0 = 0."""
+    rng = np.random.RandomState(seed)
+    ys, xs = np.mgrid[0:H, 0:W].astype(np.float64)
+
+    def tex(x, y):
+        r = np.random.RandomState(seed + 7)
+        out = np.zeros_like(x)
+        for _ in range(16):
+            fx, fy = r.uniform(-0.35, 0.35, 2)
+            ph, am = r.uniform(0, 2 * np.pi), r.uniform(0.2, 1.0)
+            out += am * np.sin(fx * x + fy * y + ph)
+        return out / 8.0 + 0.5
+    I = tex(xs, ys)
+    Ih = tex(xs + 0.6, ys - 0.4)
+    dx = np.zeros_like(Ih)
+    dy = np.zeros_like(Ih)
+    dx[1:-1, 1:-1] = (-Ih[:-2, :-2] - Ih[1:-1, :-2] - Ih[2:, :-2] + Ih[:-2, 2:] + Ih[1:-1, 2:] + Ih[2:, 2:]) / 8.0
+    dy[1:-1, 1:-1] = (-Ih[:-2, :-2] - Ih[:-2, 1:-1] - Ih[:-2, 2:] + Ih[2:, :-2] + Ih[2:, 1:-1] + Ih[2:, 2:]) / 8.0
+    del rng
+    f = lambda a: np.ascontiguousarray(a.reshape(-1), np.float32)
+    return dict(w_fitSqrt=np.float32(np.sqrt(w_fit)), w_regSqrt=np.float32(np.sqrt(w_reg)),
+                X=np.zeros((W * H, 2), np.float32), I=f(I), I_hat_im=f(Ih), I_hat_dx=f(dx), I_hat_dy=f(dy))
+
+
+def optical_flow_params(d):
+    return [np.array([d["w_fitSqrt"]], np.float32), np.array([d["w_regSqrt"]], np.float32),
+            d["X"], d["I"], d["I_hat_im"], d["I_hat_dx"], d["I_hat_dy"]]
+
+
+def volumetric_inputs(W, H, D, seed=1, w_fit=1.0, w_reg=0.05):
+    """Config 4a synthetic shape: UrShape = lattice, top face (z = D-1) rotated by
+    30 degrees about the z axis through the lattice centre, bottom face fixed, every other node
+    unconstrained (sentinel below -999999.9, volumetric_mesh_deformation.t:18)."""
+    zz, yy, xx = np.mgrid[0:D, 0:H, 0:W]
+    ur = np.stack([xx, yy, zz], -1).reshape(-1, 3).astype(np.float32)
+    n = W * H * D
+    cons = np.full((n, 3), -1e7, np.float32)
+    bottom = (zz == 0).reshape(-1)
+    top = (zz == D - 1).reshape(-1)
+    cons[bottom] = ur[bottom]
+    th = np.deg2rad(30.0)
+    cx, cy = (W - 1) / 2.0, (H - 1) / 2.0
+    x, y = ur[top, 0] - cx, ur[top, 1] - cy
+    cons[top, 0] = np.cos(th) * x - np.sin(th) * y + cx
+    cons[top, 1] = np.sin(th) * x + np.cos(th) * y + cy
+    cons[top, 2] = ur[top, 2]
+    rng = np.random.RandomState(seed)
+    ang = (0.01 * rng.randn(n, 3)).astype(np.float32)
+    return dict(Offset=ur.copy(), Angle=ang, UrShape=ur, Constraints=cons,
+                w_fitSqrt=np.float32(np.sqrt(w_fit)), w_regSqrt=np.float32(np.sqrt(w_reg)))
+
+
+def volumetric_params(d):
+    return [d["Offset"], d["Angle"], d["UrShape"], d["Constraints"],
+            np.array([d["w_fitSqrt"]], np.float32), np.array([d["w_regSqrt"]], np.float32)]
