@@ -35,13 +35,15 @@ NIT, LIT = 8, 100
 # Algorithmic bytes per pixel and launch of each kernel for image_warping/LM/at-output (DESIGN.md
 # "Kernels and their algorithmic bytes"): U = 3 unknown scalars per pixel, A = 6 auxiliary scalars
 # (Angle 1, UrShape 2, Mask 1, Constraints 2), 4 B each, every array counted once per launch.
-U, A = 3, 6
+U, A = 3, 7      # A: Mask 1, UrShape 2, Constraints 2, hoisted (sin, cos) 2
 KERNEL_BYTES_PER_PX = {
-    "th_step1_uw": 4 * (2 * U + A + U),       # read p, CtC, aux; write Ap
-    "th_step2": 4 * (6 * U + 3 * U),          # read delta, p, r, Ap, pre, b; write delta, r, z
-    "th_step3": 4 * (2 * U + U),              # read z, p; write p
-    "th_pcg_fused": 4 * (9 * U + A + 4 * U),  # fused iteration kernel
+    "th_pcg_a": 4 * (3 * U + A + 2 * U),      # read z, p_old, CtC, aux; write p_new, Ap
+    "th_pcg_a_ld": 4 * (3 * U + A + 2 * U),
+    "th_pcg_b": 4 * (6 * U + 3 * U),          # read delta, p, r, Ap, pre, b; write delta, r, z
+    "th_step1_uw": 4 * (2 * U + 6 + U),       # untiled schedule: read p, CtC, aux (Angle instead of sin/cos); write Ap
+    "th_step3": 4 * (2 * U + U),              # untiled schedule: read z, p; write p
 }
+PCG_ITERATION_BYTES_PER_PX = KERNEL_BYTES_PER_PX["th_pcg_a"] + KERNEL_BYTES_PER_PX["th_pcg_b"]
 
 
 def parse():
@@ -265,8 +267,8 @@ def main():
                 "launches_timed": kern[dom][0], "share_of_kernel_time": kern[dom][1] / ktotal,
                 "kernels": {n: {"launches": v[0], "ms": round(v[1], 4), "share": round(v[1] / ktotal, 4)} for n, v in sorted(kern.items())},
                 "profiled_pass_ms_per_step": prof_ms / a.steps,
-                "pcg_iteration_bytes": 4 * ((12 + 1 + 2) * U + A) * px,
-                "pcg_iteration_gbs": (4 * ((12 + 1 + 2) * U + A) * px) * res["iters"] / world / (res["ms"] * 1e-3) / 1e9}
+                "pcg_iteration_bytes": PCG_ITERATION_BYTES_PER_PX * px,
+                "pcg_iteration_gbs": PCG_ITERATION_BYTES_PER_PX * px * res["iters"] / world / (res["ms"] * 1e-3) / 1e9}
 
     line = {"metric": METRIC, "value": res["iters"] / (res["ms"] * 1e-3), "unit": UNIT, "n_gpus": world, "steps": a.steps,
             "warmup": a.warmup, "ms_per_step": res["ms"] / a.steps, "higher_is_better": True, "scaling": "weak",

@@ -141,4 +141,4 @@ def test_solver_parameter_roundtrip_and_summary():
     sm = s.summary()
     assert sm.total.count == 1 and sm.nonlinearIteration.count == 3 and sm.linearSolve.count == 3
     assert sm.total.meanMS > 0
-    assert s.launches() >= 3 * (1 + 5 * 3)
+    assert s.launches() >= 3 * (1 + 5 * 2)      # per nonlinear iteration: init + lIterations x (th_pcg_a, th_pcg_b)

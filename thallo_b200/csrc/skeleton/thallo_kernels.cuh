@@ -569,22 +569,21 @@ __device__ __forceinline__ void th_tma_load(void* dst, const ThTensorMap* map, u
 // Fallback loader (rows not 16-byte aligned, so no tensor map can describe the image): the block
 // fills the same box cooperatively with bounds-checked loads.
 template <class T>
-__device__ __forceinline__ void th_tile_load(T* __restrict__ dst, const T* __restrict__ src, int channels, int roww,
+__device__ __forceinline__ void th_tile_load(T* __restrict__ dst, const T* __restrict__ src, int channels, int roww, int padl,
                                              int x0, int y0, int z0, int tid) {
-    const int rowlen = TH_EXT_X * channels;
     const int total = roww * TH_EXT_Y * TH_EXT_Z;
     const long long W = th::dom_uw::D0 * channels, H = th::dom_uw::D1, D = th::dom_uw::D2;
     for (int e = tid; e < total; e += TH_TILE_THREADS) {
         const int c = e % roww, yy = (e / roww) % TH_EXT_Y, zz = e / (roww * TH_EXT_Y);
-        const long long gx = (long long)(x0 - TH_HX) * channels + c, gy = y0 - TH_HY + yy, gz = z0 - TH_HZ + zz;
-        const bool ok = c < rowlen && gx >= 0 && gx < W && gy >= 0 && gy < H && gz >= 0 && gz < D;
+        const long long gx = (long long)x0 * channels - padl + c, gy = y0 - TH_HY + yy, gz = z0 - TH_HZ + zz;
+        const bool ok = gx >= 0 && gx < W && gy >= 0 && gy < H && gz >= 0 && gz < D;
         dst[e] = ok ? src[gx + W * (gy + H * gz)] : (T)0;
     }
 }
-__device__ __forceinline__ void th_tile_load_es(void* dst, const void* src, int es, int channels, int roww, int x0, int y0, int z0, int tid) {
-    if (es == 1) th_tile_load((unsigned char*)dst, (const unsigned char*)src, channels, roww, x0, y0, z0, tid);
-    else if (es == 4) th_tile_load((unsigned int*)dst, (const unsigned int*)src, channels, roww, x0, y0, z0, tid);
-    else th_tile_load((unsigned long long*)dst, (const unsigned long long*)src, channels, roww, x0, y0, z0, tid);
+__device__ __forceinline__ void th_tile_load_es(void* dst, const void* src, int es, int channels, int roww, int padl, int x0, int y0, int z0, int tid) {
+    if (es == 1) th_tile_load((unsigned char*)dst, (const unsigned char*)src, channels, roww, padl, x0, y0, z0, tid);
+    else if (es == 4) th_tile_load((unsigned int*)dst, (const unsigned int*)src, channels, roww, padl, x0, y0, z0, tid);
+    else th_tile_load((unsigned long long*)dst, (const unsigned long long*)src, channels, roww, padl, x0, y0, z0, tid);
 }
 
 // Accessor over the staged tiles: stencil taps of the vector argument and of every image that
@@ -610,15 +609,15 @@ template <class Dom> struct TAcc {
         }
         return ok;
     }
-    template <int O0, int O1, int O2> __device__ __forceinline__ int tile_elem(int roww, int channels) const {
-        return ((tz + TH_HZ + O2) * TH_EXT_Y + (ty + TH_HY + O1)) * roww + (tx + TH_HX + O0) * channels;
+    template <int O0, int O1, int O2> __device__ __forceinline__ int tile_elem(int roww, int padl, int channels) const {
+        return ((tz + TH_HZ + O2) * TH_EXT_Y + (ty + TH_HY + O1)) * roww + padl + (tx + O0) * channels;
     }
     template <int SLOT, class CT, int C, int CH, int O0, int O1, int O2>
     __device__ __forceinline__ real img(const Params& P) const {
         constexpr int s = TH_SLOT_STAGE[SLOT];
         if constexpr (s >= 0) {
             const CT* t = (const CT*)(sm + TH_STAGE[s >= 0 ? s : 0].off);
-            return (real)t[tile_elem<O0, O1, O2>(TH_STAGE[s >= 0 ? s : 0].roww, C) + CH];
+            return (real)t[tile_elem<O0, O1, O2>(TH_STAGE[s >= 0 ? s : 0].roww, TH_STAGE[s >= 0 ? s : 0].padl, C) + CH];
         } else {
             static_assert((O0 | O1 | O2) == 0, "image read at an offset must be staged");
             return ThLoad<CT, C, CH>::ld(P.ptr[SLOT], i.lin);
@@ -626,7 +625,7 @@ template <class Dom> struct TAcc {
     }
     template <int K, int CH, int O0, int O1, int O2> __device__ __forceinline__ real vec() const {
         const real* t = (const real*)(sm + TH_VTILE[K].poff);
-        return t[tile_elem<O0, O1, O2>(TH_VTILE[K].roww, TH_UIMG[K].channels) + CH];
+        return t[tile_elem<O0, O1, O2>(TH_VTILE[K].roww, TH_VTILE[K].padl, TH_UIMG[K].channels) + CH];
     }
     template <int SLOT> __device__ __forceinline__ real samp(const Params& P, real x, real y) const {
         GAcc<Dom> g(i, nullptr);
@@ -661,7 +660,7 @@ __device__ __forceinline__ void th_pcg_a_impl(const Params& P, const Vecs& V, co
             th_mbar_expect_tx(&bar, bytes);
 #pragma unroll
             for (int k = 0; k < TH_NUM_UIMG; ++k) {
-                const int c0 = (x0 - TH_HX) * TH_UIMG[k].channels;
+                const int c0 = x0 * TH_UIMG[k].channels - TH_VTILE[k].padl;
                 if (mode == 0 && it == 0) th_tma_load(th_sm + TH_VTILE[k].poff, &M.z[k], &bar, c0, y0 - TH_HY, z0 - TH_HZ);
                 else {
                     if (upd) th_tma_load(th_sm + TH_VTILE[k].zoff, &M.z[k], &bar, c0, y0 - TH_HY, z0 - TH_HZ);
@@ -670,7 +669,7 @@ __device__ __forceinline__ void th_pcg_a_impl(const Params& P, const Vecs& V, co
             }
 #pragma unroll
             for (int s = 0; s < TH_NSTAGE; ++s)
-                th_tma_load(th_sm + TH_STAGE[s].off, &M.st[s], &bar, (x0 - TH_HX) * TH_STAGE[s].channels, y0 - TH_HY, z0 - TH_HZ);
+                th_tma_load(th_sm + TH_STAGE[s].off, &M.st[s], &bar, x0 * TH_STAGE[s].channels - TH_STAGE[s].padl, y0 - TH_HY, z0 - TH_HZ);
         }
         th_mbar_wait(&bar, 0);
     } else {
@@ -678,15 +677,15 @@ __device__ __forceinline__ void th_pcg_a_impl(const Params& P, const Vecs& V, co
 #pragma unroll
         for (int k = 0; k < TH_NUM_UIMG; ++k) {
             const int ch = TH_UIMG[k].channels;
-            if (mode == 0 && it == 0) th_tile_load((real*)(th_sm + TH_VTILE[k].poff), V.z + TH_UIMG[k].offset, ch, TH_VTILE[k].roww, x0, y0, z0, tid);
+            if (mode == 0 && it == 0) th_tile_load((real*)(th_sm + TH_VTILE[k].poff), V.z + TH_UIMG[k].offset, ch, TH_VTILE[k].roww, TH_VTILE[k].padl, x0, y0, z0, tid);
             else {
-                if (upd) th_tile_load((real*)(th_sm + TH_VTILE[k].zoff), V.z + TH_UIMG[k].offset, ch, TH_VTILE[k].roww, x0, y0, z0, tid);
-                th_tile_load((real*)(th_sm + TH_VTILE[k].poff), psrcv + TH_UIMG[k].offset, ch, TH_VTILE[k].roww, x0, y0, z0, tid);
+                if (upd) th_tile_load((real*)(th_sm + TH_VTILE[k].zoff), V.z + TH_UIMG[k].offset, ch, TH_VTILE[k].roww, TH_VTILE[k].padl, x0, y0, z0, tid);
+                th_tile_load((real*)(th_sm + TH_VTILE[k].poff), psrcv + TH_UIMG[k].offset, ch, TH_VTILE[k].roww, TH_VTILE[k].padl, x0, y0, z0, tid);
             }
         }
 #pragma unroll
         for (int s = 0; s < TH_NSTAGE; ++s)
-            th_tile_load_es(th_sm + TH_STAGE[s].off, P.ptr[TH_STAGE[s].slot], TH_STAGE[s].es, TH_STAGE[s].channels, TH_STAGE[s].roww, x0, y0, z0, tid);
+            th_tile_load_es(th_sm + TH_STAGE[s].off, P.ptr[TH_STAGE[s].slot], TH_STAGE[s].es, TH_STAGE[s].channels, TH_STAGE[s].roww, TH_STAGE[s].padl, x0, y0, z0, tid);
         __syncthreads();
     }
     if (upd) {
@@ -714,7 +713,7 @@ __device__ __forceinline__ void th_pcg_a_impl(const Params& P, const Vecs& V, co
 #pragma unroll
             for (int k = 0; k < TH_NUM_UIMG; ++k) {
                 const real* pt = (const real*)(th_sm + TH_VTILE[k].poff);
-                const int te = a.template tile_elem<0, 0, 0>(TH_VTILE[k].roww, TH_UIMG[k].channels);
+                const int te = a.template tile_elem<0, 0, 0>(TH_VTILE[k].roww, TH_VTILE[k].padl, TH_UIMG[k].channels);
 #pragma unroll
                 for (int ch = 0; ch < TH_UIMG[k].channels; ++ch, ++j) {
                     const long long off = TH_UIMG[k].offset + idx.lin * TH_UIMG[k].channels + ch;

@@ -70,10 +70,11 @@ __device__ constexpr long long TH_DIMS[TH_NDIMS] = TH_DIM_SIZES;
 
 #if TH_TILED
 // Shared-memory tile layout of the tiled operator kernel (computed by the front end):
-// every staged array is a box of (TH_TW+2*TH_HX) x (TH_TH+2*TH_HY) x (TH_TD+2*TH_HZ) elements,
-// rows padded to 16 bytes (the TMA box granularity), bases 128-byte aligned.
-struct ThStage { int slot; int es; int channels; int roww; int off; };
-struct ThVTile { int roww; int zoff; int poff; int bytes; };
+// every staged array is a box of roww scalars x (TH_TH+2*TH_HY) x (TH_TD+2*TH_HZ); a row holds
+// [padl | TH_TW elements | TH_HX elements] where padl >= TH_HX elements is the left halo padded to
+// 16 bytes (TMA needs a 16-byte aligned innermost start coordinate); bases are 128-byte aligned.
+struct ThStage { int slot; int es; int channels; int roww; int off; int padl; };
+struct ThVTile { int roww; int zoff; int poff; int bytes; int padl; };
 __device__ constexpr ThStage TH_STAGE[TH_NSTAGE > 0 ? TH_NSTAGE : 1] = TH_STAGE_TABLE;
 __device__ constexpr int TH_SLOT_STAGE[TH_NPTR] = TH_SLOT_STAGE_TABLE;
 __device__ constexpr ThVTile TH_VTILE[TH_NUM_UIMG] = TH_VTILE_TABLE;

@@ -69,8 +69,8 @@ bool parse_descriptor(const std::string& text, PlanDesc& d, std::string& err) {
         else if (key == "tile") {
             ls >> d.tile[0] >> d.tile[1] >> d.tile[2] >> d.halo[0] >> d.halo[1] >> d.halo[2] >> d.smem_bytes;
             d.tiled = true;
-        } else if (key == "vtile") { VTileDesc v; ls >> v.roww >> v.zoff >> v.poff >> v.bytes; d.vtiles.push_back(v); }
-        else if (key == "stage") { StageDesc t; ls >> t.slot >> t.ctype >> t.es >> t.channels >> t.roww >> t.off >> t.bytes; d.stages.push_back(t); }
+        } else if (key == "vtile") { VTileDesc v; ls >> v.roww >> v.zoff >> v.poff >> v.bytes >> v.padl; d.vtiles.push_back(v); }
+        else if (key == "stage") { StageDesc t; ls >> t.slot >> t.ctype >> t.es >> t.channels >> t.roww >> t.off >> t.bytes >> t.padl; d.stages.push_back(t); }
         if (ls.fail() && !ls.eof()) { err = "malformed descriptor line: " + line; return false; }
     }
     if (d.nunk <= 0 || d.unknowns.empty() || d.groups.empty()) { err = "descriptor lacks unknowns or residual groups"; return false; }
@@ -182,7 +182,8 @@ bool Plan::encode_map(void* dst, const void* base, int es, const std::string& ct
     gstride[1] = gstride[0] * gdim[1];
     box[0] = (cuuint32_t)roww;
     for (int i = 1; i < nd; ++i) box[i] = (cuuint32_t)(d_.tile[i] + 2 * d_.halo[i]);
-    if ((reinterpret_cast<uintptr_t>(base) & 15) || (gstride[0] & 15) || box[0] > 256) return false;
+    // the innermost start coordinate of every box (tile origin * channels - padl) must be 16-byte aligned
+    if ((reinterpret_cast<uintptr_t>(base) & 15) || (gstride[0] & 15) || box[0] > 256 || (((size_t)d_.tile[0] * channels * es) & 15)) return false;
     CUtensorMapDataType dt = CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
     if (ctype == "uchar") dt = CU_TENSOR_MAP_DATA_TYPE_UINT8;
     else if (ctype == "int") dt = CU_TENSOR_MAP_DATA_TYPE_INT32;
@@ -533,11 +534,15 @@ int Plan::step(void** params) {
     for (int l = 0; l < sp_.lIterations; ++l) {
         if (d_.lm) {
             bool stop = false;
-            for (;;) {
+            for (unsigned spins = 0;; ++spins) {
                 if (h_flags_->done_epoch == epoch_) { stop = true; break; }
                 const long long pr = h_flags_->progress;
                 const int done_iters = (int)(pr >> 32) == epoch_ ? (int)(pr & 0xffffffff) : 0;
                 if (l - done_iters < depth) break;
+                if ((spins & 1023) == 1023) {          // a faulted kernel never reports progress: surface the error
+                    const cudaError_t e = cudaStreamQuery(stream());
+                    if (e != cudaSuccess && e != cudaErrorNotReady) fatal_cuda(e, "PCG iteration (asynchronous kernel failure)");
+                }
                 sched_yield();
             }
             if (stop) break;

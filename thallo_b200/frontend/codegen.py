@@ -396,28 +396,32 @@ class Generator:
         stages = []
 
         def place(channels, es):
+            # TMA requires the innermost start coordinate of a box to be 16-byte aligned (measured on
+            # B200: an unaligned start raises "illegal instruction"), so the left halo is padded to
+            # 16 bytes: a row is [padl | tile | right halo] scalars, rounded up to 16 bytes.
             nonlocal off
-            row_bytes = -(-(ext[0] * channels * es) // 16) * 16
+            padl = -(-(H[0] * channels * es) // 16) * 16 // es
+            row_bytes = -(-((padl + (tile[0] + H[0]) * channels) * es) // 16) * 16
             roww = row_bytes // es
             nbytes = row_bytes * ext[1] * ext[2]
             o = off
             off = -(-(off + nbytes) // 128) * 128
-            return o, roww, nbytes
+            return o, roww, nbytes, padl
         vt = []
         for im in self.unknowns:                     # vector tiles: z and p per unknown image
-            zo, roww, nb = place(im.channels, es_real)
-            po, _, _ = place(im.channels, es_real)
-            vt.append(dict(name=im.name, channels=im.channels, roww=roww, zoff=zo, poff=po, bytes=nb))
+            zo, roww, nb, padl = place(im.channels, es_real)
+            po, _, _, _ = place(im.channels, es_real)
+            vt.append(dict(name=im.name, channels=im.channels, roww=roww, zoff=zo, poff=po, bytes=nb, padl=padl))
         slot_stage = [-1] * len(self.ptr_pidx)
         for name, h in halo["img"].items():
             if not any(h):
                 continue
             im = self.images[name]
             es = esz[im.ctype]
-            o, roww, nb = place(im.channels, es)
+            o, roww, nb, padl = place(im.channels, es)
             slot_stage[self.ptr_slot[name]] = len(stages)
             stages.append(dict(name=name, slot=self.ptr_slot[name], ctype=im.ctype, es=es, channels=im.channels,
-                               roww=roww, off=o, bytes=nb))
+                               roww=roww, off=o, bytes=nb, padl=padl))
         self.tl = dict(tile=tile, halo=H, ext=ext, vt=vt, stages=stages, slot_stage=slot_stage, smem=off)
         return self.tl
 
@@ -613,11 +617,11 @@ class Generator:
                 hdr.append("#define TH_SMEM_BYTES %d" % max(16, tl["smem"]))
                 hdr.append("#define TH_NSTAGE %d" % len(tl["stages"]))
                 hdr.append("#define TH_STAGE_TABLE {%s}" % (", ".join(
-                    "{%d, %d, %d, %d, %d}" % (st["slot"], st["es"], st["channels"], st["roww"], st["off"])
-                    for st in tl["stages"]) or "{0, 0, 0, 0, 0}"))
+                    "{%d, %d, %d, %d, %d, %d}" % (st["slot"], st["es"], st["channels"], st["roww"], st["off"], st["padl"])
+                    for st in tl["stages"]) or "{0, 0, 0, 0, 0, 0}"))
                 hdr.append("#define TH_SLOT_STAGE_TABLE {%s}" % ", ".join(map(str, tl["slot_stage"])))
                 hdr.append("#define TH_VTILE_TABLE {%s}" % ", ".join(
-                    "{%d, %d, %d, %d}" % (v["roww"], v["zoff"], v["poff"], v["bytes"]) for v in tl["vt"]))
+                    "{%d, %d, %d, %d, %d}" % (v["roww"], v["zoff"], v["poff"], v["bytes"], v["padl"]) for v in tl["vt"]))
         gl = []
         for gi, g in enumerate(self.groups):
             body.append(self.gen_group(gi, g))
@@ -706,9 +710,9 @@ def descriptor_text(d):
             tl = d["tile"]
             ln.append("tile %s %s %d" % (" ".join(map(str, tl["tile"])), " ".join(map(str, tl["halo"])), tl["smem"]))
             for v in tl["vt"]:
-                ln.append("vtile %d %d %d %d" % (v["roww"], v["zoff"], v["poff"], v["bytes"]))
+                ln.append("vtile %d %d %d %d %d" % (v["roww"], v["zoff"], v["poff"], v["bytes"], v["padl"]))
             for st in tl["stages"]:
-                ln.append("stage %d %s %d %d %d %d %d" % (st["slot"], st["ctype"], st["es"], st["channels"], st["roww"], st["off"], st["bytes"]))
+                ln.append("stage %d %s %d %d %d %d %d %d" % (st["slot"], st["ctype"], st["es"], st["channels"], st["roww"], st["off"], st["bytes"], st["padl"]))
     return "\n".join(ln) + "\n"
 
 

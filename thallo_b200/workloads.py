@@ -152,3 +152,41 @@ def volumetric_inputs(W, H, D, seed=1, w_fit=1.0, w_reg=0.05):
 def volumetric_params(d):
     return [d["Offset"], d["Angle"], d["UrShape"], d["Constraints"],
             np.array([d["w_fitSqrt"]], np.float32), np.array([d["w_regSqrt"]], np.float32)]
+
+
+def arap_mesh_inputs(nx, ny, seed=1, w_fit=4.0, w_reg=1.0, handle_fraction=0.01):
+    """Config 4b synthetic shape: a triangulated nx x ny grid (interior valence 6),
+    directed edges listed per vertex as examples/shared/ThalloGraph.h:67-79
+    (createGraphFromNeighborLists) does, Original = grid + seeded z-noise, ~1% handle vertices
+    displaced, every other vertex unconstrained (sentinel below -999999.9,
+    arap_mesh_deformation.t:20)."""
+    rng = np.random.RandomState(seed)
+    n = nx * ny
+    ys, xs = np.mgrid[0:ny, 0:nx]
+    vid = (xs + nx * ys)
+    heads, tails = [], []
+    # neighbour offsets of a grid triangulated along one diagonal: 6-neighbourhood
+    for dx, dy in [(-1, -1), (0, -1), (-1, 0), (1, 0), (0, 1), (1, 1)]:
+        x2, y2 = xs + dx, ys + dy
+        ok = (x2 >= 0) & (x2 < nx) & (y2 >= 0) & (y2 < ny)
+        heads.append(np.where(ok, vid, -1))
+        tails.append(np.where(ok, x2 + nx * y2, -1))
+    heads = np.stack(heads, -1).reshape(-1)       # per vertex, then per neighbour: the reference's order
+    tails = np.stack(tails, -1).reshape(-1)
+    keep = heads >= 0
+    v0 = heads[keep].astype(np.int32)
+    v1 = tails[keep].astype(np.int32)
+    orig = np.stack([xs, ys, 0.05 * rng.randn(ny, nx)], -1).reshape(n, 3).astype(np.float32)
+    cons = np.full((n, 3), -1e7, np.float32)
+    nh = max(2, int(handle_fraction * n))
+    hidx = rng.choice(n, nh, replace=False)
+    cons[hidx] = orig[hidx] + np.stack([0.3 * np.sin(orig[hidx, 1] * 0.1), 0.2 * np.cos(orig[hidx, 0] * 0.1),
+                                        0.5 + 0 * orig[hidx, 0]], -1).astype(np.float32)
+    ang = np.zeros((n, 3), np.float32)
+    return dict(w_fitSqrt=np.float32(np.sqrt(w_fit)), w_regSqrt=np.float32(np.sqrt(w_reg)),
+                Position=orig.copy(), Angle=ang, Original=orig, Constraints=cons, V0=v0, V1=v1)
+
+
+def arap_mesh_params(d):
+    return [np.array([d["w_fitSqrt"]], np.float32), np.array([d["w_regSqrt"]], np.float32),
+            d["Position"], d["Angle"], d["Original"], d["Constraints"], d["V0"], d["V1"]]
