@@ -635,100 +635,148 @@ template <class Dom> struct TAcc {
 
 // mode 0: p_new = z + beta p_old (beta = 0 on the first iteration), Ap = (JtJ [+CtC]) p_new,
 //         alphaDenominator = <p_new, Ap>; p_old is read from buffer it&1, p_new written to (it+1)&1
-//         (neighbouring blocks still read p_old in their halos).
+//         (neighbouring tiles still read p_old in their halos).
 // mode 1: Adelta = (JtJ [+CtC]) delta   (LM residual reset, gauss_newton.t:755-762)
+//
+// Persistent CTAs (the host launches SMs x resident-CTAs-per-SM of them) walk the tile list with a
+// two-stage shared-memory pipeline: while tile i is processed, the TMA unit already fills the other
+// stage with tile i+1, so the HBM latency of a tile is hidden behind the arithmetic of the previous
+// one and there is a single grid reduction per CTA at the very end.
+#define TH_NTX ((int)((th::dom_uw::D0 + TH_TW - 1) / TH_TW))
+#define TH_NTY ((int)((th::dom_uw::D1 + TH_TH - 1) / TH_TH))
+#define TH_NTZ ((int)((th::dom_uw::D2 + TH_TD - 1) / TH_TD))
+#define TH_NTILES (TH_NTX * TH_NTY * TH_NTZ)
+
+__device__ __forceinline__ void th_tile_origin(int t, int& x0, int& y0, int& z0) {
+    x0 = (t % TH_NTX) * TH_TW;
+    y0 = ((t / TH_NTX) % TH_NTY) * TH_TH;
+    z0 = (t / (TH_NTX * TH_NTY)) * TH_TD;
+}
+
+// all bulk copies of one tile, issued by one thread
+__device__ __forceinline__ void th_tile_issue(unsigned char* sm, unsigned long long* bar, const ThMaps& M, int t, int mode, int it) {
+    int x0, y0, z0;
+    th_tile_origin(t, x0, y0, z0);
+    const bool upd = mode == 0 && it > 0;
+    const int psrc = mode ? 2 : (it & 1);
+    unsigned bytes = 0;
+#pragma unroll
+    for (int k = 0; k < TH_NUM_UIMG; ++k) bytes += (unsigned)TH_VTILE[k].bytes * (upd ? 2u : 1u);
+#pragma unroll
+    for (int s = 0; s < TH_NSTAGE; ++s) bytes += (unsigned)(TH_STAGE[s].roww * TH_STAGE[s].es * TH_EXT_Y * TH_EXT_Z);
+    th_mbar_expect_tx(bar, bytes);
+#pragma unroll
+    for (int k = 0; k < TH_NUM_UIMG; ++k) {
+        const int c0 = x0 * TH_UIMG[k].channels - TH_VTILE[k].padl;
+        if (mode == 0 && it == 0) th_tma_load(sm + TH_VTILE[k].poff, &M.z[k], bar, c0, y0 - TH_HY, z0 - TH_HZ);
+        else {
+            if (upd) th_tma_load(sm + TH_VTILE[k].zoff, &M.z[k], bar, c0, y0 - TH_HY, z0 - TH_HZ);
+            th_tma_load(sm + TH_VTILE[k].poff, &M.p[psrc][k], bar, c0, y0 - TH_HY, z0 - TH_HZ);
+        }
+    }
+#pragma unroll
+    for (int s = 0; s < TH_NSTAGE; ++s)
+        th_tma_load(sm + TH_STAGE[s].off, &M.st[s], bar, x0 * TH_STAGE[s].channels - TH_STAGE[s].padl, y0 - TH_HY, z0 - TH_HZ);
+}
+
+// the same fill with cooperative bounds-checked loads (synchronous; all threads)
+__device__ __forceinline__ void th_tile_fill(unsigned char* sm, const Params& P, const Vecs& V, int t, int mode, int it, int tid) {
+    int x0, y0, z0;
+    th_tile_origin(t, x0, y0, z0);
+    const bool upd = mode == 0 && it > 0;
+    const real* psrcv = mode ? V.delta : ((it & 1) ? V.p2 : V.p);
+#pragma unroll
+    for (int k = 0; k < TH_NUM_UIMG; ++k) {
+        const int ch = TH_UIMG[k].channels;
+        if (mode == 0 && it == 0) th_tile_load((real*)(sm + TH_VTILE[k].poff), V.z + TH_UIMG[k].offset, ch, TH_VTILE[k].roww, TH_VTILE[k].padl, x0, y0, z0, tid);
+        else {
+            if (upd) th_tile_load((real*)(sm + TH_VTILE[k].zoff), V.z + TH_UIMG[k].offset, ch, TH_VTILE[k].roww, TH_VTILE[k].padl, x0, y0, z0, tid);
+            th_tile_load((real*)(sm + TH_VTILE[k].poff), psrcv + TH_UIMG[k].offset, ch, TH_VTILE[k].roww, TH_VTILE[k].padl, x0, y0, z0, tid);
+        }
+    }
+#pragma unroll
+    for (int s = 0; s < TH_NSTAGE; ++s)
+        th_tile_load_es(sm + TH_STAGE[s].off, P.ptr[TH_STAGE[s].slot], TH_STAGE[s].es, TH_STAGE[s].channels, TH_STAGE[s].roww, TH_STAGE[s].padl, x0, y0, z0, tid);
+}
+
 template <bool TMA>
 __device__ __forceinline__ void th_pcg_a_impl(const Params& P, const Vecs& V, const ThMaps& M, ThScalars* S, double* partials, int mode) {
-    extern __shared__ __align__(128) unsigned char th_sm[];
-    __shared__ __align__(8) unsigned long long bar;
+    extern __shared__ __align__(128) unsigned char th_sm[];      // TMA: two stages of TH_SMEM_BYTES; otherwise one
+    __shared__ __align__(8) unsigned long long bar[2];
     if (S->done) return;
     const int it = S->it;
     const int tx = threadIdx.x, ty = threadIdx.y, tz = threadIdx.z;
     const int tid = tx + TH_TW * (ty + TH_TH * tz);
-    const int x0 = blockIdx.x * TH_TW, y0 = blockIdx.y * TH_TH, z0 = blockIdx.z * TH_TD;
     const bool upd = mode == 0 && it > 0;
-    const int psrc = mode ? 2 : (it & 1);
-    if (TMA) {
-        if (tid == 0) th_mbar_init(&bar, 1);
-        __syncthreads();
-        if (tid == 0) {
-            unsigned bytes = 0;
-#pragma unroll
-            for (int k = 0; k < TH_NUM_UIMG; ++k) bytes += (unsigned)TH_VTILE[k].bytes * (upd ? 2u : 1u);
-#pragma unroll
-            for (int s = 0; s < TH_NSTAGE; ++s) bytes += (unsigned)(TH_STAGE[s].roww * TH_STAGE[s].es * TH_EXT_Y * TH_EXT_Z);
-            th_mbar_expect_tx(&bar, bytes);
-#pragma unroll
-            for (int k = 0; k < TH_NUM_UIMG; ++k) {
-                const int c0 = x0 * TH_UIMG[k].channels - TH_VTILE[k].padl;
-                if (mode == 0 && it == 0) th_tma_load(th_sm + TH_VTILE[k].poff, &M.z[k], &bar, c0, y0 - TH_HY, z0 - TH_HZ);
-                else {
-                    if (upd) th_tma_load(th_sm + TH_VTILE[k].zoff, &M.z[k], &bar, c0, y0 - TH_HY, z0 - TH_HZ);
-                    th_tma_load(th_sm + TH_VTILE[k].poff, &M.p[psrc][k], &bar, c0, y0 - TH_HY, z0 - TH_HZ);
-                }
-            }
-#pragma unroll
-            for (int s = 0; s < TH_NSTAGE; ++s)
-                th_tma_load(th_sm + TH_STAGE[s].off, &M.st[s], &bar, x0 * TH_STAGE[s].channels - TH_STAGE[s].padl, y0 - TH_HY, z0 - TH_HZ);
-        }
-        th_mbar_wait(&bar, 0);
-    } else {
-        const real* psrcv = mode ? V.delta : ((it & 1) ? V.p2 : V.p);
-#pragma unroll
-        for (int k = 0; k < TH_NUM_UIMG; ++k) {
-            const int ch = TH_UIMG[k].channels;
-            if (mode == 0 && it == 0) th_tile_load((real*)(th_sm + TH_VTILE[k].poff), V.z + TH_UIMG[k].offset, ch, TH_VTILE[k].roww, TH_VTILE[k].padl, x0, y0, z0, tid);
-            else {
-                if (upd) th_tile_load((real*)(th_sm + TH_VTILE[k].zoff), V.z + TH_UIMG[k].offset, ch, TH_VTILE[k].roww, TH_VTILE[k].padl, x0, y0, z0, tid);
-                th_tile_load((real*)(th_sm + TH_VTILE[k].poff), psrcv + TH_UIMG[k].offset, ch, TH_VTILE[k].roww, TH_VTILE[k].padl, x0, y0, z0, tid);
-            }
-        }
-#pragma unroll
-        for (int s = 0; s < TH_NSTAGE; ++s)
-            th_tile_load_es(th_sm + TH_STAGE[s].off, P.ptr[TH_STAGE[s].slot], TH_STAGE[s].es, TH_STAGE[s].channels, TH_STAGE[s].roww, TH_STAGE[s].padl, x0, y0, z0, tid);
-        __syncthreads();
-    }
-    if (upd) {
-        const real beta = th_beta_prev(S);
-#pragma unroll
-        for (int k = 0; k < TH_NUM_UIMG; ++k) {
-            real* __restrict__ pt = (real*)(th_sm + TH_VTILE[k].poff);
-            const real* __restrict__ zt = (const real*)(th_sm + TH_VTILE[k].zoff);
-            const int n = TH_VTILE[k].bytes / (int)sizeof(real);
-            for (int e = tid; e < n; e += TH_TILE_THREADS) pt[e] = zt[e] + beta * pt[e];
-        }
-        __syncthreads();
-    }
+    const real beta = upd ? th_beta_prev(S) : (real)0;
     real* __restrict__ out = mode ? V.Adelta : V.Ap;
     real* __restrict__ pnew = ((it + 1) & 1) ? V.p2 : V.p;
-    ThIdx<th::dom_uw> idx;
+    if (TMA) {
+        if (tid == 0) { th_mbar_init(&bar[0], 1); th_mbar_init(&bar[1], 1); }
+        __syncthreads();
+        if (tid == 0 && (int)blockIdx.x < TH_NTILES) th_tile_issue(th_sm, &bar[0], M, blockIdx.x, mode, it);
+    }
     double acc[1] = {0.0};
-    if (idx.from_coords(x0 + tx, y0 + ty, z0 + tz)) {
-        TAcc<th::dom_uw> a(idx, th_sm, tx, ty, tz);
-        if (!th::exclude_u0(a, P)) {
-            real o[TH_U];
-            th::applyJTJ_uw(a, P, o);
-            real dot = (real)0;
-            int j = 0;
-#pragma unroll
-            for (int k = 0; k < TH_NUM_UIMG; ++k) {
-                const real* pt = (const real*)(th_sm + TH_VTILE[k].poff);
-                const int te = a.template tile_elem<0, 0, 0>(TH_VTILE[k].roww, TH_VTILE[k].padl, TH_UIMG[k].channels);
-#pragma unroll
-                for (int ch = 0; ch < TH_UIMG[k].channels; ++ch, ++j) {
-                    const long long off = TH_UIMG[k].offset + idx.lin * TH_UIMG[k].channels + ch;
-                    const real pv = pt[te + ch];
-                    real val = o[j];
-#if TH_LM
-                    val += V.CtC[off] * pv;
-#endif
-                    out[off] = val;
-                    if (mode == 0) pnew[off] = pv;
-                    dot += pv * val;
-                }
+    unsigned phase = 0;          // bit s: parity of the next completion of stage s
+    int stage = 0;
+    for (int t = blockIdx.x; t < TH_NTILES; t += gridDim.x) {
+        unsigned char* sm = th_sm + (TMA ? stage * TH_SMEM_BYTES : 0);
+        if (TMA) {
+            const int tn = t + gridDim.x;
+            if (tid == 0 && tn < TH_NTILES) {
+                // the other stage was last touched by generic-proxy accesses of the previous tile
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                th_tile_issue(th_sm + (stage ^ 1) * TH_SMEM_BYTES, &bar[stage ^ 1], M, tn, mode, it);
             }
-            acc[0] = (double)dot;
+            th_mbar_wait(&bar[stage], (phase >> stage) & 1u);
+            phase ^= 1u << stage;
+        } else {
+            th_tile_fill(sm, P, V, t, mode, it, tid);
+            __syncthreads();
         }
+        if (upd) {               // p = z + beta p over the whole p region (tile + halo of every unknown image)
+            real4* __restrict__ p4 = (real4*)(sm + TH_VTILE[0].poff);
+            const real4* __restrict__ z4 = (const real4*)(sm + TH_VTILE[0].zoff);
+            for (int e = tid; e < TH_VREGION_BYTES / (int)sizeof(real4); e += TH_TILE_THREADS) {
+                const real4 z = z4[e];
+                real4 p = p4[e];
+                p.x = z.x + beta * p.x; p.y = z.y + beta * p.y; p.z = z.z + beta * p.z; p.w = z.w + beta * p.w;
+                p4[e] = p;
+            }
+            __syncthreads();
+        }
+        int x0, y0, z0;
+        th_tile_origin(t, x0, y0, z0);
+        ThIdx<th::dom_uw> idx;
+        if (idx.from_coords(x0 + tx, y0 + ty, z0 + tz)) {
+            TAcc<th::dom_uw> a(idx, sm, tx, ty, tz);
+            if (!th::exclude_u0(a, P)) {
+                real o[TH_U];
+                th::applyJTJ_uw(a, P, o);
+                real dot = (real)0;
+                int j = 0;
+#pragma unroll
+                for (int k = 0; k < TH_NUM_UIMG; ++k) {
+                    const real* pt = (const real*)(sm + TH_VTILE[k].poff);
+                    const int te = a.template tile_elem<0, 0, 0>(TH_VTILE[k].roww, TH_VTILE[k].padl, TH_UIMG[k].channels);
+#pragma unroll
+                    for (int ch = 0; ch < TH_UIMG[k].channels; ++ch, ++j) {
+                        const long long off = TH_UIMG[k].offset + idx.lin * TH_UIMG[k].channels + ch;
+                        const real pv = pt[te + ch];
+                        real val = o[j];
+#if TH_LM
+                        val += V.CtC[off] * pv;
+#endif
+                        out[off] = val;
+                        if (mode == 0) pnew[off] = pv;
+                        dot += pv * val;
+                    }
+                }
+                acc[0] += (double)dot;
+            }
+        }
+        __syncthreads();         // every thread is done with this stage before it is refilled
+        stage ^= 1;
     }
     if (mode) return;
     double tot[1];

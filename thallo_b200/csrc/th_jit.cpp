@@ -39,6 +39,7 @@ const DriverApi& DriverApi::get() {
         TH_ENTRY(LaunchKernel, "cuLaunchKernel");
         TH_ENTRY(FuncSetAttribute, "cuFuncSetAttribute");
         TH_ENTRY(GetErrorString, "cuGetErrorString");
+        TH_ENTRY(OccupancyMaxActiveBlocks, "cuOccupancyMaxActiveBlocksPerMultiprocessor");
         TH_ENTRY(TensorMapEncodeTiled, "cuTensorMapEncodeTiled");
 #undef TH_ENTRY
         api.ok = api.ModuleLoadData && api.ModuleGetFunction && api.LaunchKernel && api.ModuleUnload;

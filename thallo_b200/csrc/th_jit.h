@@ -19,6 +19,7 @@ struct DriverApi {
                              void**, void**) = nullptr;
     CUresult (*FuncSetAttribute)(CUfunction, CUfunction_attribute, int) = nullptr;
     CUresult (*GetErrorString)(CUresult, const char**) = nullptr;
+    CUresult (*OccupancyMaxActiveBlocks)(int*, CUfunction, int, size_t) = nullptr;
     CUresult (*TensorMapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                      const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                      CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill) = nullptr;

@@ -123,6 +123,7 @@ Plan::Plan(const StateOptions* opts, const PlanDesc& desc, const std::string& so
     int dev = 0;
     CD(cudaGetDevice(&dev));
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    sms_ = sms;
     const long long want = (d_.nunk + 255) / 256;
     flat_grid_ = (unsigned)std::max(1LL, std::min<long long>(want, (long long)sms * 8));
     // partial sums: up to 2 values per block of the largest grid
@@ -133,11 +134,7 @@ Plan::Plan(const StateOptions* opts, const PlanDesc& desc, const std::string& so
         else if (d_.uw_dims.size() == 2) b = ((d_.uw_dims[0] + 31) / 32) * ((d_.uw_dims[1] + 7) / 8);
         else b = ((d_.uw_dims[0] + 7) / 8) * ((d_.uw_dims[1] + 7) / 8) * ((d_.uw_dims[2] + 3) / 4);
         maxblocks = std::max(maxblocks, b);
-        if (d_.tiled) {
-            long long t = 1;
-            for (size_t i = 0; i < d_.uw_dims.size(); ++i) t *= (d_.uw_dims[i] + d_.tile[i] - 1) / d_.tile[i];
-            maxblocks = std::max(maxblocks, t);
-        }
+        if (d_.tiled) maxblocks = std::max<long long>(maxblocks, (long long)sms * 32);   // persistent grid <= SMs x resident CTAs
     }
     for (auto& g : d_.groups) maxblocks = std::max(maxblocks, (g.count + 255) / 256);
     CD(cudaMalloc((void**)&d_partials_, sizeof(double) * 2 * (size_t)maxblocks));
@@ -153,10 +150,21 @@ Plan::Plan(const StateOptions* opts, const PlanDesc& desc, const std::string& so
     if (d_.tiled) {
         maps_buf_.assign(128 * (4 * d_.unknowns.size() + std::max<size_t>(1, d_.stages.size())) + 64, 0);
         build_vector_maps();
-        for (const char* kn : {"th_pcg_a", "th_pcg_a_ld"}) {
-            CUfunction f = fn(kn);
-            if (d_.smem_bytes > 48 * 1024 && api.FuncSetAttribute)
-                CU(api.FuncSetAttribute(f, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, d_.smem_bytes));
+        // persistent grids: SMs x CTAs resident per SM (two pipeline stages of shared memory with TMA, one without)
+        long long ntiles = 1;
+        for (size_t i = 0; i < d_.uw_dims.size(); ++i) ntiles *= (d_.uw_dims[i] + d_.tile[i] - 1) / d_.tile[i];
+        const char* names[2] = {"th_pcg_a_ld", "th_pcg_a"};
+        for (int v = 0; v < 2; ++v) {
+            CUfunction f = fn(names[v]);
+            tiled_smem_[v] = (unsigned)d_.smem_bytes * (v ? 2u : 1u);
+            if (tiled_smem_[v] > 48 * 1024 && api.FuncSetAttribute)
+                CU(api.FuncSetAttribute(f, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)tiled_smem_[v]));
+            int per_sm = 2;
+            const int threads = d_.tile[0] * d_.tile[1] * d_.tile[2];
+            if (api.OccupancyMaxActiveBlocks && api.OccupancyMaxActiveBlocks(&per_sm, f, threads, tiled_smem_[v]) != CUDA_SUCCESS) per_sm = 2;
+            per_sm = std::max(1, std::min(per_sm, 32));
+            if (const char* e = getenv("THALLO_B200_CTAS_PER_SM")) per_sm = std::max(1, atoi(e));
+            tiled_grid_[v] = (unsigned)std::min<long long>(ntiles, (long long)sms * per_sm);
         }
     }
     sp_ = SolverParameters();
@@ -435,10 +443,9 @@ double Plan::cost() {   // gauss_newton.t:1787-1793
 
 void Plan::launch_tiled(int mode) {
     void* a[] = {params_buf_.data(), vecs_buf_.data(), maps_base(maps_buf_), &d_scalars_, &d_partials_, &mode};
-    dim3 grid(1, 1, 1), block((unsigned)d_.tile[0], (unsigned)d_.tile[1], (unsigned)d_.tile[2]);
-    unsigned* g[3] = {&grid.x, &grid.y, &grid.z};
-    for (size_t i = 0; i < d_.uw_dims.size(); ++i) *g[i] = (unsigned)((d_.uw_dims[i] + d_.tile[i] - 1) / d_.tile[i]);
-    launch(pcg_a_, grid, block, a, (unsigned)d_.smem_bytes);
+    const int v = use_tma_ ? 1 : 0;
+    dim3 grid(tiled_grid_[v], 1, 1), block((unsigned)d_.tile[0], (unsigned)d_.tile[1], (unsigned)d_.tile[2]);
+    launch(pcg_a_, grid, block, a, tiled_smem_[v]);
 }
 
 void Plan::linear_iteration(int l) {

@@ -132,6 +132,9 @@ private:
     bool use_tma_ = false;
     bool vector_maps_ok_ = false;
     CUfunction pcg_a_ = nullptr;
+    unsigned tiled_grid_[2] = {1, 1};   // persistent grid of th_pcg_a_ld / th_pcg_a
+    unsigned tiled_smem_[2] = {0, 0};
+    int sms_ = 148;
     void* d_scalars_ = nullptr;
     double* d_partials_ = nullptr;
     HScalars* h_scalars_ = nullptr;    // pinned

@@ -408,10 +408,16 @@ class Generator:
             off = -(-(off + nbytes) // 128) * 128
             return o, roww, nbytes, padl
         vt = []
-        for im in self.unknowns:                     # vector tiles: z and p per unknown image
+        # vector tiles: all z tiles first, then all p tiles at the same relative offsets, so that the
+        # direction update p = z + beta p is one flat vectorised loop over the p region
+        for im in self.unknowns:
             zo, roww, nb, padl = place(im.channels, es_real)
+            vt.append(dict(name=im.name, channels=im.channels, roww=roww, zoff=zo, poff=0, bytes=nb, padl=padl))
+        vregion = off
+        for v, im in zip(vt, self.unknowns):
             po, _, _, _ = place(im.channels, es_real)
-            vt.append(dict(name=im.name, channels=im.channels, roww=roww, zoff=zo, poff=po, bytes=nb, padl=padl))
+            v["poff"] = po
+            assert po - v["zoff"] == vregion
         slot_stage = [-1] * len(self.ptr_pidx)
         for name, h in halo["img"].items():
             if not any(h):
@@ -422,7 +428,7 @@ class Generator:
             slot_stage[self.ptr_slot[name]] = len(stages)
             stages.append(dict(name=name, slot=self.ptr_slot[name], ctype=im.ctype, es=es, channels=im.channels,
                                roww=roww, off=o, bytes=nb, padl=padl))
-        self.tl = dict(tile=tile, halo=H, ext=ext, vt=vt, stages=stages, slot_stage=slot_stage, smem=off)
+        self.tl = dict(tile=tile, halo=H, ext=ext, vt=vt, stages=stages, slot_stage=slot_stage, smem=off, vregion=vregion)
         return self.tl
 
     def gen_unknownwise(self):
@@ -614,7 +620,8 @@ class Generator:
                 tl = self.tl
                 hdr.append("#define TH_TW %d\n#define TH_TH %d\n#define TH_TD %d" % tuple(tl["tile"]))
                 hdr.append("#define TH_HX %d\n#define TH_HY %d\n#define TH_HZ %d" % tuple(tl["halo"]))
-                hdr.append("#define TH_SMEM_BYTES %d" % max(16, tl["smem"]))
+                hdr.append("#define TH_SMEM_BYTES %d" % max(128, tl["smem"]))
+                hdr.append("#define TH_VREGION_BYTES %d" % tl["vregion"])
                 hdr.append("#define TH_NSTAGE %d" % len(tl["stages"]))
                 hdr.append("#define TH_STAGE_TABLE {%s}" % (", ".join(
                     "{%d, %d, %d, %d, %d, %d}" % (st["slot"], st["es"], st["channels"], st["roww"], st["off"], st["padl"])
@@ -708,7 +715,7 @@ def descriptor_text(d):
         ln.append("ncoef %d" % d.get("ncoef", 0))
         if d.get("tiled"):
             tl = d["tile"]
-            ln.append("tile %s %s %d" % (" ".join(map(str, tl["tile"])), " ".join(map(str, tl["halo"])), tl["smem"]))
+            ln.append("tile %s %s %d" % (" ".join(map(str, tl["tile"])), " ".join(map(str, tl["halo"])), max(128, tl["smem"])))
             for v in tl["vt"]:
                 ln.append("vtile %d %d %d %d %d" % (v["roww"], v["zoff"], v["poff"], v["bytes"], v["padl"]))
             for st in tl["stages"]:
