@@ -566,34 +566,45 @@ __device__ __forceinline__ void th_tma_load(void* dst, const ThTensorMap* map, u
 #endif
 }
 
+__device__ __forceinline__ void th_mbar_arrive(unsigned long long* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(th_smem_u32(bar)) : "memory");
+}
+
 // Fallback loader (rows not 16-byte aligned, so no tensor map can describe the image): the block
-// fills the same box cooperatively with bounds-checked loads.
+// fills the same box cooperatively with bounds-checked loads.  center: tile-only box, no halo.
 template <class T>
 __device__ __forceinline__ void th_tile_load(T* __restrict__ dst, const T* __restrict__ src, int channels, int roww, int padl,
-                                             int x0, int y0, int z0, int tid) {
-    const int total = roww * TH_EXT_Y * TH_EXT_Z;
+                                             int center, int x0, int y0, int z0, int tid) {
+    const int ey = center ? TH_TH : TH_EXT_Y, ez = center ? TH_TD : TH_EXT_Z;
+    const int hy = center ? 0 : TH_HY, hz = center ? 0 : TH_HZ;
+    const int total = roww * ey * ez;
     const long long W = th::dom_uw::D0 * channels, H = th::dom_uw::D1, D = th::dom_uw::D2;
     for (int e = tid; e < total; e += TH_TILE_THREADS) {
-        const int c = e % roww, yy = (e / roww) % TH_EXT_Y, zz = e / (roww * TH_EXT_Y);
-        const long long gx = (long long)x0 * channels - padl + c, gy = y0 - TH_HY + yy, gz = z0 - TH_HZ + zz;
+        const int c = e % roww, yy = (e / roww) % ey, zz = e / (roww * ey);
+        const long long gx = (long long)x0 * channels - padl + c, gy = y0 - hy + yy, gz = z0 - hz + zz;
         const bool ok = gx >= 0 && gx < W && gy >= 0 && gy < H && gz >= 0 && gz < D;
         dst[e] = ok ? src[gx + W * (gy + H * gz)] : (T)0;
     }
 }
-__device__ __forceinline__ void th_tile_load_es(void* dst, const void* src, int es, int channels, int roww, int padl, int x0, int y0, int z0, int tid) {
-    if (es == 1) th_tile_load((unsigned char*)dst, (const unsigned char*)src, channels, roww, padl, x0, y0, z0, tid);
-    else if (es == 4) th_tile_load((unsigned int*)dst, (const unsigned int*)src, channels, roww, padl, x0, y0, z0, tid);
-    else th_tile_load((unsigned long long*)dst, (const unsigned long long*)src, channels, roww, padl, x0, y0, z0, tid);
+__device__ __forceinline__ void th_tile_load_es(void* dst, const void* src, int es, int channels, int roww, int padl, int center,
+                                                int x0, int y0, int z0, int tid) {
+    if (es == 1) th_tile_load((unsigned char*)dst, (const unsigned char*)src, channels, roww, padl, center, x0, y0, z0, tid);
+    else if (es == 4) th_tile_load((unsigned int*)dst, (const unsigned int*)src, channels, roww, padl, center, x0, y0, z0, tid);
+    else th_tile_load((unsigned long long*)dst, (const unsigned long long*)src, channels, roww, padl, center, x0, y0, z0, tid);
 }
 
-// Accessor over the staged tiles: stencil taps of the vector argument and of every image that
-// is read at a non-zero offset come from shared memory (zero outside the image, courtesy of the
-// loader); images read only at the element itself are loaded straight from global memory.
-template <class Dom> struct TAcc {
+// Accessor over the staged tiles: stencil taps of the vector argument and of every staged image
+// come from shared memory (zero outside the image, courtesy of the loader); anything not staged
+// is read at the element itself straight from global memory.  With UPD the vector argument is the
+// new search direction p = z + beta p_old, formed on the fly from the z and p_old tiles
+// (PCGStep3 fused into the operator; fma() so that every tap and the stored p_new agree bit for bit).
+template <class Dom, bool UPD> struct TAcc {
     ThIdx<Dom> i;
     const unsigned char* sm;
     int tx, ty, tz;
-    __device__ __forceinline__ TAcc(const ThIdx<Dom>& idx, const unsigned char* s, int x, int y, int z) : i(idx), sm(s), tx(x), ty(y), tz(z) {}
+    real beta;
+    __device__ __forceinline__ TAcc(const ThIdx<Dom>& idx, const unsigned char* s, int x, int y, int z, real b)
+        : i(idx), sm(s), tx(x), ty(y), tz(z), beta(b) {}
     template <int D> __device__ __forceinline__ int coord() const { return i.c[D]; }
     template <int L0, int H0, int L1, int H1, int L2, int H2> __device__ __forceinline__ bool inb() const {
         bool ok = true;
@@ -612,20 +623,31 @@ template <class Dom> struct TAcc {
     template <int O0, int O1, int O2> __device__ __forceinline__ int tile_elem(int roww, int padl, int channels) const {
         return ((tz + TH_HZ + O2) * TH_EXT_Y + (ty + TH_HY + O1)) * roww + padl + (tx + O0) * channels;
     }
+    __device__ __forceinline__ int center_elem(int roww, int channels) const { return (tz * TH_TH + ty) * roww + tx * channels; }
     template <int SLOT, class CT, int C, int CH, int O0, int O1, int O2>
     __device__ __forceinline__ real img(const Params& P) const {
         constexpr int s = TH_SLOT_STAGE[SLOT];
         if constexpr (s >= 0) {
-            const CT* t = (const CT*)(sm + TH_STAGE[s >= 0 ? s : 0].off);
-            return (real)t[tile_elem<O0, O1, O2>(TH_STAGE[s >= 0 ? s : 0].roww, TH_STAGE[s >= 0 ? s : 0].padl, C) + CH];
+            constexpr ThStage st = TH_STAGE[s >= 0 ? s : 0];
+            const CT* t = (const CT*)(sm + st.off);
+            if constexpr (st.center != 0) {
+                static_assert((O0 | O1 | O2) == 0, "image staged without halo is read at an offset");
+                return (real)t[center_elem(st.roww, C) + CH];
+            } else {
+                return (real)t[tile_elem<O0, O1, O2>(st.roww, st.padl, C) + CH];
+            }
         } else {
             static_assert((O0 | O1 | O2) == 0, "image read at an offset must be staged");
             return ThLoad<CT, C, CH>::ld(P.ptr[SLOT], i.lin);
         }
     }
+    __device__ __forceinline__ real vec_at(int k, int e) const {
+        const real pv = ((const real*)(sm + TH_VTILE[k].poff))[e];
+        if (UPD) return fma(beta, pv, ((const real*)(sm + TH_VTILE[k].zoff))[e]);
+        return pv;
+    }
     template <int K, int CH, int O0, int O1, int O2> __device__ __forceinline__ real vec() const {
-        const real* t = (const real*)(sm + TH_VTILE[K].poff);
-        return t[tile_elem<O0, O1, O2>(TH_VTILE[K].roww, TH_VTILE[K].padl, TH_UIMG[K].channels) + CH];
+        return vec_at(K, tile_elem<O0, O1, O2>(TH_VTILE[K].roww, TH_VTILE[K].padl, TH_UIMG[K].channels) + CH);
     }
     template <int SLOT> __device__ __forceinline__ real samp(const Params& P, real x, real y) const {
         GAcc<Dom> g(i, nullptr);
@@ -640,12 +662,14 @@ template <class Dom> struct TAcc {
 //
 // Persistent CTAs (the host launches SMs x resident-CTAs-per-SM of them) walk the tile list with a
 // two-stage shared-memory pipeline: while tile i is processed, the TMA unit already fills the other
-// stage with tile i+1, so the HBM latency of a tile is hidden behind the arithmetic of the previous
-// one and there is a single grid reduction per CTA at the very end.
+// stage with tile i+1 (every array the operator reads, so no thread issues a global load), the
+// stage is handed back through an mbarrier the warps arrive on, and there is a single grid
+// reduction per CTA at the very end.
 #define TH_NTX ((int)((th::dom_uw::D0 + TH_TW - 1) / TH_TW))
 #define TH_NTY ((int)((th::dom_uw::D1 + TH_TH - 1) / TH_TH))
 #define TH_NTZ ((int)((th::dom_uw::D2 + TH_TD - 1) / TH_TD))
 #define TH_NTILES (TH_NTX * TH_NTY * TH_NTZ)
+#define TH_CTC_STAGED (TH_LM && TH_STAGE_CTC)
 
 __device__ __forceinline__ void th_tile_origin(int t, int& x0, int& y0, int& z0) {
     x0 = (t % TH_NTX) * TH_TW;
@@ -661,9 +685,9 @@ __device__ __forceinline__ void th_tile_issue(unsigned char* sm, unsigned long l
     const int psrc = mode ? 2 : (it & 1);
     unsigned bytes = 0;
 #pragma unroll
-    for (int k = 0; k < TH_NUM_UIMG; ++k) bytes += (unsigned)TH_VTILE[k].bytes * (upd ? 2u : 1u);
+    for (int k = 0; k < TH_NUM_UIMG; ++k) bytes += (unsigned)TH_VTILE[k].bytes * (upd ? 2u : 1u) + (TH_CTC_STAGED ? (unsigned)TH_VTILE[k].cbytes : 0u);
 #pragma unroll
-    for (int s = 0; s < TH_NSTAGE; ++s) bytes += (unsigned)(TH_STAGE[s].roww * TH_STAGE[s].es * TH_EXT_Y * TH_EXT_Z);
+    for (int s = 0; s < TH_NSTAGE; ++s) bytes += (unsigned)TH_STAGE[s].bytes;
     th_mbar_expect_tx(bar, bytes);
 #pragma unroll
     for (int k = 0; k < TH_NUM_UIMG; ++k) {
@@ -673,10 +697,13 @@ __device__ __forceinline__ void th_tile_issue(unsigned char* sm, unsigned long l
             if (upd) th_tma_load(sm + TH_VTILE[k].zoff, &M.z[k], bar, c0, y0 - TH_HY, z0 - TH_HZ);
             th_tma_load(sm + TH_VTILE[k].poff, &M.p[psrc][k], bar, c0, y0 - TH_HY, z0 - TH_HZ);
         }
+        if (TH_CTC_STAGED) th_tma_load(sm + TH_VTILE[k].coff, &M.c[k], bar, x0 * TH_UIMG[k].channels, y0, z0);
     }
 #pragma unroll
-    for (int s = 0; s < TH_NSTAGE; ++s)
-        th_tma_load(sm + TH_STAGE[s].off, &M.st[s], bar, x0 * TH_STAGE[s].channels - TH_STAGE[s].padl, y0 - TH_HY, z0 - TH_HZ);
+    for (int s = 0; s < TH_NSTAGE; ++s) {
+        if (TH_STAGE[s].center) th_tma_load(sm + TH_STAGE[s].off, &M.st[s], bar, x0 * TH_STAGE[s].channels, y0, z0);
+        else th_tma_load(sm + TH_STAGE[s].off, &M.st[s], bar, x0 * TH_STAGE[s].channels - TH_STAGE[s].padl, y0 - TH_HY, z0 - TH_HZ);
+    }
 }
 
 // the same fill with cooperative bounds-checked loads (synchronous; all threads)
@@ -688,21 +715,62 @@ __device__ __forceinline__ void th_tile_fill(unsigned char* sm, const Params& P,
 #pragma unroll
     for (int k = 0; k < TH_NUM_UIMG; ++k) {
         const int ch = TH_UIMG[k].channels;
-        if (mode == 0 && it == 0) th_tile_load((real*)(sm + TH_VTILE[k].poff), V.z + TH_UIMG[k].offset, ch, TH_VTILE[k].roww, TH_VTILE[k].padl, x0, y0, z0, tid);
+        if (mode == 0 && it == 0) th_tile_load((real*)(sm + TH_VTILE[k].poff), V.z + TH_UIMG[k].offset, ch, TH_VTILE[k].roww, TH_VTILE[k].padl, 0, x0, y0, z0, tid);
         else {
-            if (upd) th_tile_load((real*)(sm + TH_VTILE[k].zoff), V.z + TH_UIMG[k].offset, ch, TH_VTILE[k].roww, TH_VTILE[k].padl, x0, y0, z0, tid);
-            th_tile_load((real*)(sm + TH_VTILE[k].poff), psrcv + TH_UIMG[k].offset, ch, TH_VTILE[k].roww, TH_VTILE[k].padl, x0, y0, z0, tid);
+            if (upd) th_tile_load((real*)(sm + TH_VTILE[k].zoff), V.z + TH_UIMG[k].offset, ch, TH_VTILE[k].roww, TH_VTILE[k].padl, 0, x0, y0, z0, tid);
+            th_tile_load((real*)(sm + TH_VTILE[k].poff), psrcv + TH_UIMG[k].offset, ch, TH_VTILE[k].roww, TH_VTILE[k].padl, 0, x0, y0, z0, tid);
         }
+        if (TH_CTC_STAGED) th_tile_load((real*)(sm + TH_VTILE[k].coff), V.CtC + TH_UIMG[k].offset, ch, TH_VTILE[k].croww, 0, 1, x0, y0, z0, tid);
     }
 #pragma unroll
     for (int s = 0; s < TH_NSTAGE; ++s)
-        th_tile_load_es(sm + TH_STAGE[s].off, P.ptr[TH_STAGE[s].slot], TH_STAGE[s].es, TH_STAGE[s].channels, TH_STAGE[s].roww, TH_STAGE[s].padl, x0, y0, z0, tid);
+        th_tile_load_es(sm + TH_STAGE[s].off, P.ptr[TH_STAGE[s].slot], TH_STAGE[s].es, TH_STAGE[s].channels, TH_STAGE[s].roww,
+                        TH_STAGE[s].padl, TH_STAGE[s].center, x0, y0, z0, tid);
+}
+
+// operator applied to one tile from shared-memory stage `sm`; returns this thread's <p, Ap> contribution
+template <bool UPD>
+__device__ __forceinline__ real th_tile_apply(const unsigned char* sm, const Params& P, const Vecs& V, int t, int mode, real beta,
+                                              real* __restrict__ out, real* __restrict__ pnew, int tx, int ty, int tz) {
+    int x0, y0, z0;
+    th_tile_origin(t, x0, y0, z0);
+    ThIdx<th::dom_uw> idx;
+    real dot = (real)0;
+    if (idx.from_coords(x0 + tx, y0 + ty, z0 + tz)) {
+        TAcc<th::dom_uw, UPD> a(idx, sm, tx, ty, tz, beta);
+        if (!th::exclude_u0(a, P)) {
+            real o[TH_U];
+            th::applyJTJ_uw(a, P, o);
+            int j = 0;
+#pragma unroll
+            for (int k = 0; k < TH_NUM_UIMG; ++k) {
+                const int te = a.template tile_elem<0, 0, 0>(TH_VTILE[k].roww, TH_VTILE[k].padl, TH_UIMG[k].channels);
+#pragma unroll
+                for (int ch = 0; ch < TH_UIMG[k].channels; ++ch, ++j) {
+                    const long long off = TH_UIMG[k].offset + idx.lin * TH_UIMG[k].channels + ch;
+                    const real pv = a.vec_at(k, te + ch);
+                    real val = o[j];
+#if TH_LM
+#if TH_STAGE_CTC
+                    val += ((const real*)(sm + TH_VTILE[k].coff))[a.center_elem(TH_VTILE[k].croww, TH_UIMG[k].channels) + ch] * pv;
+#else
+                    val += V.CtC[off] * pv;
+#endif
+#endif
+                    out[off] = val;
+                    if (mode == 0) pnew[off] = pv;
+                    dot += pv * val;
+                }
+            }
+        }
+    }
+    return dot;
 }
 
 template <bool TMA>
 __device__ __forceinline__ void th_pcg_a_impl(const Params& P, const Vecs& V, const ThMaps& M, ThScalars* S, double* partials, int mode) {
     extern __shared__ __align__(128) unsigned char th_sm[];      // TMA: two stages of TH_SMEM_BYTES; otherwise one
-    __shared__ __align__(8) unsigned long long bar[2];
+    __shared__ __align__(8) unsigned long long full[2], empty[2];
     if (S->done) return;
     const int it = S->it;
     const int tx = threadIdx.x, ty = threadIdx.y, tz = threadIdx.z;
@@ -712,70 +780,41 @@ __device__ __forceinline__ void th_pcg_a_impl(const Params& P, const Vecs& V, co
     real* __restrict__ out = mode ? V.Adelta : V.Ap;
     real* __restrict__ pnew = ((it + 1) & 1) ? V.p2 : V.p;
     if (TMA) {
-        if (tid == 0) { th_mbar_init(&bar[0], 1); th_mbar_init(&bar[1], 1); }
+        if (tid == 0) {
+            th_mbar_init(&full[0], 1); th_mbar_init(&full[1], 1);
+            th_mbar_init(&empty[0], TH_TILE_THREADS / 32); th_mbar_init(&empty[1], TH_TILE_THREADS / 32);
+        }
         __syncthreads();
-        if (tid == 0 && (int)blockIdx.x < TH_NTILES) th_tile_issue(th_sm, &bar[0], M, blockIdx.x, mode, it);
+        if (tid == 0 && (int)blockIdx.x < TH_NTILES) th_tile_issue(th_sm, &full[0], M, blockIdx.x, mode, it);
     }
     double acc[1] = {0.0};
-    unsigned phase = 0;          // bit s: parity of the next completion of stage s
+    unsigned fphase = 0, ephase = 0;      // bit s: parity of the next completion of full[s] / empty[s]
     int stage = 0;
     for (int t = blockIdx.x; t < TH_NTILES; t += gridDim.x) {
         unsigned char* sm = th_sm + (TMA ? stage * TH_SMEM_BYTES : 0);
         if (TMA) {
             const int tn = t + gridDim.x;
             if (tid == 0 && tn < TH_NTILES) {
-                // the other stage was last touched by generic-proxy accesses of the previous tile
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                th_tile_issue(th_sm + (stage ^ 1) * TH_SMEM_BYTES, &bar[stage ^ 1], M, tn, mode, it);
+                if (t != (int)blockIdx.x) {          // the other stage held the previous tile: wait until every warp released it
+                    th_mbar_wait(&empty[stage ^ 1], (ephase >> (stage ^ 1)) & 1u);
+                    ephase ^= 1u << (stage ^ 1);
+                }
+                th_tile_issue(th_sm + (stage ^ 1) * TH_SMEM_BYTES, &full[stage ^ 1], M, tn, mode, it);
             }
-            th_mbar_wait(&bar[stage], (phase >> stage) & 1u);
-            phase ^= 1u << stage;
+            th_mbar_wait(&full[stage], (fphase >> stage) & 1u);
+            fphase ^= 1u << stage;
         } else {
+            __syncthreads();                         // previous tile fully consumed
             th_tile_fill(sm, P, V, t, mode, it, tid);
             __syncthreads();
         }
-        if (upd) {               // p = z + beta p over the whole p region (tile + halo of every unknown image)
-            real4* __restrict__ p4 = (real4*)(sm + TH_VTILE[0].poff);
-            const real4* __restrict__ z4 = (const real4*)(sm + TH_VTILE[0].zoff);
-            for (int e = tid; e < TH_VREGION_BYTES / (int)sizeof(real4); e += TH_TILE_THREADS) {
-                const real4 z = z4[e];
-                real4 p = p4[e];
-                p.x = z.x + beta * p.x; p.y = z.y + beta * p.y; p.z = z.z + beta * p.z; p.w = z.w + beta * p.w;
-                p4[e] = p;
-            }
-            __syncthreads();
+        const real dot = upd ? th_tile_apply<true>(sm, P, V, t, mode, beta, out, pnew, tx, ty, tz)
+                             : th_tile_apply<false>(sm, P, V, t, mode, beta, out, pnew, tx, ty, tz);
+        acc[0] += (double)dot;
+        if (TMA) {
+            __syncwarp();
+            if ((tid & 31) == 0) th_mbar_arrive(&empty[stage]);
         }
-        int x0, y0, z0;
-        th_tile_origin(t, x0, y0, z0);
-        ThIdx<th::dom_uw> idx;
-        if (idx.from_coords(x0 + tx, y0 + ty, z0 + tz)) {
-            TAcc<th::dom_uw> a(idx, sm, tx, ty, tz);
-            if (!th::exclude_u0(a, P)) {
-                real o[TH_U];
-                th::applyJTJ_uw(a, P, o);
-                real dot = (real)0;
-                int j = 0;
-#pragma unroll
-                for (int k = 0; k < TH_NUM_UIMG; ++k) {
-                    const real* pt = (const real*)(sm + TH_VTILE[k].poff);
-                    const int te = a.template tile_elem<0, 0, 0>(TH_VTILE[k].roww, TH_VTILE[k].padl, TH_UIMG[k].channels);
-#pragma unroll
-                    for (int ch = 0; ch < TH_UIMG[k].channels; ++ch, ++j) {
-                        const long long off = TH_UIMG[k].offset + idx.lin * TH_UIMG[k].channels + ch;
-                        const real pv = pt[te + ch];
-                        real val = o[j];
-#if TH_LM
-                        val += V.CtC[off] * pv;
-#endif
-                        out[off] = val;
-                        if (mode == 0) pnew[off] = pv;
-                        dot += pv * val;
-                    }
-                }
-                acc[0] += (double)dot;
-            }
-        }
-        __syncthreads();         // every thread is done with this stage before it is refilled
         stage ^= 1;
     }
     if (mode) return;

@@ -73,8 +73,10 @@ __device__ constexpr long long TH_DIMS[TH_NDIMS] = TH_DIM_SIZES;
 // every staged array is a box of roww scalars x (TH_TH+2*TH_HY) x (TH_TD+2*TH_HZ); a row holds
 // [padl | TH_TW elements | TH_HX elements] where padl >= TH_HX elements is the left halo padded to
 // 16 bytes (TMA needs a 16-byte aligned innermost start coordinate); bases are 128-byte aligned.
-struct ThStage { int slot; int es; int channels; int roww; int off; int padl; };
-struct ThVTile { int roww; int zoff; int poff; int bytes; int padl; };
+// Arrays read only at the element itself are staged as a plain TH_TW x TH_TH x TH_TD box (center = 1);
+// coff/croww/cbytes describe the CtC tile (LM diagonal) of an unknown image in that form.
+struct ThStage { int slot; int es; int channels; int roww; int off; int padl; int center; int bytes; };
+struct ThVTile { int roww; int zoff; int poff; int bytes; int padl; int coff; int croww; int cbytes; };
 __device__ constexpr ThStage TH_STAGE[TH_NSTAGE > 0 ? TH_NSTAGE : 1] = TH_STAGE_TABLE;
 __device__ constexpr int TH_SLOT_STAGE[TH_NPTR] = TH_SLOT_STAGE_TABLE;
 __device__ constexpr ThVTile TH_VTILE[TH_NUM_UIMG] = TH_VTILE_TABLE;
@@ -84,10 +86,12 @@ __device__ constexpr ThVTile TH_VTILE[TH_NUM_UIMG] = TH_VTILE_TABLE;
 #define TH_TILE_THREADS (TH_TW * TH_TH * TH_TD)
 // opaque 128-byte CUtensorMap (cuda.h is not available under NVRTC)
 struct alignas(64) ThTensorMap { unsigned long long q[16]; };
-// z: preconditioned residual; p[0], p[1]: the two search-direction buffers; p[2]: delta (for A*delta in LM)
+// z: preconditioned residual; p[0], p[1]: the two search-direction buffers; p[2]: delta (for A*delta in LM);
+// c: CtC (tile-only boxes); st: the staged problem images
 struct ThMaps {
     ThTensorMap z[TH_NUM_UIMG];
     ThTensorMap p[3][TH_NUM_UIMG];
+    ThTensorMap c[TH_NUM_UIMG];
     ThTensorMap st[TH_NSTAGE > 0 ? TH_NSTAGE : 1];
 };
 #endif

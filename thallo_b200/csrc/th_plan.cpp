@@ -69,8 +69,8 @@ bool parse_descriptor(const std::string& text, PlanDesc& d, std::string& err) {
         else if (key == "tile") {
             ls >> d.tile[0] >> d.tile[1] >> d.tile[2] >> d.halo[0] >> d.halo[1] >> d.halo[2] >> d.smem_bytes;
             d.tiled = true;
-        } else if (key == "vtile") { VTileDesc v; ls >> v.roww >> v.zoff >> v.poff >> v.bytes >> v.padl; d.vtiles.push_back(v); }
-        else if (key == "stage") { StageDesc t; ls >> t.slot >> t.ctype >> t.es >> t.channels >> t.roww >> t.off >> t.bytes >> t.padl; d.stages.push_back(t); }
+        } else if (key == "vtile") { VTileDesc v; ls >> v.roww >> v.zoff >> v.poff >> v.bytes >> v.padl >> v.coff >> v.croww >> v.cbytes; d.vtiles.push_back(v); }
+        else if (key == "stage") { StageDesc t; ls >> t.slot >> t.ctype >> t.es >> t.channels >> t.roww >> t.off >> t.bytes >> t.padl >> t.center; d.stages.push_back(t); }
         if (ls.fail() && !ls.eof()) { err = "malformed descriptor line: " + line; return false; }
     }
     if (d.nunk <= 0 || d.unknowns.empty() || d.groups.empty()) { err = "descriptor lacks unknowns or residual groups"; return false; }
@@ -148,7 +148,7 @@ Plan::Plan(const StateOptions* opts, const PlanDesc& desc, const std::string& so
     memcpy(vecs_buf_.data(), vecs_, 10 * sizeof(void*));
     memcpy(vecs_buf_.data() + 10 * sizeof(void*), &vecs_[V_P2], sizeof(void*));
     if (d_.tiled) {
-        maps_buf_.assign(128 * (4 * d_.unknowns.size() + std::max<size_t>(1, d_.stages.size())) + 64, 0);
+        maps_buf_.assign(128 * (5 * d_.unknowns.size() + std::max<size_t>(1, d_.stages.size())) + 64, 0);
         build_vector_maps();
         // persistent grids: SMs x CTAs resident per SM (two pipeline stages of shared memory with TMA, one without)
         long long ntiles = 1;
@@ -177,7 +177,7 @@ Plan::Plan(const StateOptions* opts, const PlanDesc& desc, const std::string& so
 static char* maps_base(std::vector<char>& b) {
     return reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(b.data()) + 63) & ~uintptr_t(63));
 }
-bool Plan::encode_map(void* dst, const void* base, int es, const std::string& ctype, int channels, int roww) {
+bool Plan::encode_map(void* dst, const void* base, int es, const std::string& ctype, int channels, int roww, bool center) {
     const DriverApi& api = DriverApi::get();
     if (!api.TensorMapEncodeTiled) return false;
     const int nd = (int)d_.uw_dims.size();
@@ -189,7 +189,7 @@ bool Plan::encode_map(void* dst, const void* base, int es, const std::string& ct
     gstride[0] = gdim[0] * es;
     gstride[1] = gstride[0] * gdim[1];
     box[0] = (cuuint32_t)roww;
-    for (int i = 1; i < nd; ++i) box[i] = (cuuint32_t)(d_.tile[i] + 2 * d_.halo[i]);
+    for (int i = 1; i < nd; ++i) box[i] = (cuuint32_t)(d_.tile[i] + (center ? 0 : 2 * d_.halo[i]));
     // the innermost start coordinate of every box (tile origin * channels - padl) must be 16-byte aligned
     if ((reinterpret_cast<uintptr_t>(base) & 15) || (gstride[0] & 15) || box[0] > 256 || (((size_t)d_.tile[0] * channels * es) & 15)) return false;
     CUtensorMapDataType dt = CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
@@ -208,12 +208,15 @@ bool Plan::encode_map(void* dst, const void* base, int es, const std::string& ct
 void Plan::build_vector_maps() {
     char* mb = maps_base(maps_buf_);
     const size_t nu = d_.unknowns.size();
-    const int src[4] = {V_Z, V_P, V_P2, V_DELTA};      // ThMaps: z[nu], p[3][nu]
+    const int src[5] = {V_Z, V_P, V_P2, V_DELTA, V_CTC};      // ThMaps: z[nu], p[3][nu], c[nu]
     vector_maps_ok_ = true;
-    for (int v = 0; v < 4; ++v)
+    for (int v = 0; v < 5; ++v)
         for (size_t k = 0; k < nu; ++k) {
             const char* base = (const char*)vecs_[src[v]] + (size_t)d_.unknowns[k].offset * real_size_;
-            if (!encode_map(mb + 128 * (v * nu + k), base, (int)real_size_, "real", d_.unknowns[k].channels, d_.vtiles[k].roww))
+            const bool center = v == 4;
+            if (center && d_.vtiles[k].coff < 0) continue;      // CtC not staged
+            if (!encode_map(mb + 128 * (v * nu + k), base, (int)real_size_, "real", d_.unknowns[k].channels,
+                            center ? d_.vtiles[k].croww : d_.vtiles[k].roww, center))
                 vector_maps_ok_ = false;
         }
 }
@@ -313,7 +316,7 @@ void Plan::bind(void** params) {
             const StageDesc& t = d_.stages[s];
             void* base = nullptr;
             memcpy(&base, buf + 8 * t.slot, 8);
-            ok = encode_map(mb + 128 * (4 * d_.unknowns.size() + s), base, t.es, t.ctype, t.channels, t.roww);
+            ok = encode_map(mb + 128 * (5 * d_.unknowns.size() + s), base, t.es, t.ctype, t.channels, t.roww, t.center != 0);
         }
         use_tma_ = ok;
         pcg_a_ = fn(ok ? "th_pcg_a" : "th_pcg_a_ld");

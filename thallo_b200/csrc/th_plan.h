@@ -17,8 +17,8 @@ namespace thallo {
 struct UnknownDesc { std::string name; int channels = 0; long long offset = 0; int pidx = 0; long long elements = 0; std::vector<int> dims; };
 struct GroupDesc { std::string name; long long count = 0; int nterms = 0; int materialize = 0; int nnz = 0; std::vector<int> domain; std::vector<int> row_nnz; };
 struct ScalarDesc { int pidx; std::string ctype; };
-struct VTileDesc { int roww = 0, zoff = 0, poff = 0, bytes = 0, padl = 0; };
-struct StageDesc { int slot = 0; std::string ctype; int es = 4, channels = 1, roww = 0, off = 0, bytes = 0, padl = 0; };
+struct VTileDesc { int roww = 0, zoff = 0, poff = 0, bytes = 0, padl = 0, coff = -1, croww = 0, cbytes = 0; };
+struct StageDesc { int slot = 0; std::string ctype; int es = 4, channels = 1, roww = 0, off = 0, bytes = 0, padl = 0, center = 0; };
 
 struct PlanDesc {
     std::string name, kind, schedule;
@@ -99,7 +99,7 @@ private:
     CUfunction fn(const std::string& name);
     void launch(CUfunction f, dim3 grid, dim3 block, void** args, unsigned smem = 0);
     void launch_tiled(int mode);
-    bool encode_map(void* dst, const void* base, int es, const std::string& ctype, int channels, int roww);
+    bool encode_map(void* dst, const void* base, int es, const std::string& ctype, int channels, int roww, bool center);
     void build_vector_maps();
     void launch_flat(CUfunction f, void** args);
     void launch_uw(CUfunction f, void** args);

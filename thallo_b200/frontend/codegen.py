@@ -204,6 +204,7 @@ class Generator:
         self.udomain = next(iter(udoms)) if len(udoms) == 1 else None
         # tiled form of the unknownwise operator (shared-memory stencil tiles, TMA-staged): 2-D / 3-D image domains
         self.tiled = self.schedule == "at_output" and len(self.udomain) in (2, 3)
+        self.stage_center = self.tiled and len(self.udomain) == 2    # also stage centre-only arrays (2-D: shared memory to spare)
         self.coef_exprs = []          # hoisted PCG-invariant per-element expressions (channels of the __coef image)
         self._coef_index = {}
 
@@ -407,28 +408,46 @@ class Generator:
             o = off
             off = -(-(off + nbytes) // 128) * 128
             return o, roww, nbytes, padl
+        def place_center(channels, es):
+            # tile-only box (no halo) for arrays that are read at the element itself
+            nonlocal off
+            row_bytes = tile[0] * channels * es
+            if row_bytes % 16:
+                return None
+            nbytes = row_bytes * tile[1] * tile[2]
+            o = off
+            off = -(-(off + nbytes) // 128) * 128
+            return o, row_bytes // es, nbytes
         vt = []
-        # vector tiles: all z tiles first, then all p tiles at the same relative offsets, so that the
-        # direction update p = z + beta p is one flat vectorised loop over the p region
-        for im in self.unknowns:
+        for im in self.unknowns:                     # z and p_old tiles (with halo) per unknown image
             zo, roww, nb, padl = place(im.channels, es_real)
-            vt.append(dict(name=im.name, channels=im.channels, roww=roww, zoff=zo, poff=0, bytes=nb, padl=padl))
-        vregion = off
-        for v, im in zip(vt, self.unknowns):
             po, _, _, _ = place(im.channels, es_real)
-            v["poff"] = po
-            assert po - v["zoff"] == vregion
+            v = dict(name=im.name, channels=im.channels, roww=roww, zoff=zo, poff=po, bytes=nb, padl=padl,
+                     coff=-1, croww=0, cbytes=0)
+            if self.lm and self.stage_center:        # CtC tile (LM diagonal), read at the element only
+                c = place_center(im.channels, es_real)
+                if c is not None:
+                    v["coff"], v["croww"], v["cbytes"] = c
+            vt.append(v)
+        if any(v["coff"] < 0 for v in vt):           # all or nothing, keeps the kernel simple
+            for v in vt:
+                v["coff"], v["croww"], v["cbytes"] = -1, 0, 0
         slot_stage = [-1] * len(self.ptr_pidx)
         for name, h in halo["img"].items():
-            if not any(h):
-                continue
             im = self.images[name]
             es = esz[im.ctype]
-            o, roww, nb, padl = place(im.channels, es)
+            if any(h):
+                o, roww, nb, padl = place(im.channels, es)
+                center = 0
+            else:
+                c = place_center(im.channels, es) if self.stage_center else None
+                if c is None:
+                    continue                         # read straight from global memory
+                (o, roww, nb), padl, center = c, 0, 1
             slot_stage[self.ptr_slot[name]] = len(stages)
             stages.append(dict(name=name, slot=self.ptr_slot[name], ctype=im.ctype, es=es, channels=im.channels,
-                               roww=roww, off=o, bytes=nb, padl=padl))
-        self.tl = dict(tile=tile, halo=H, ext=ext, vt=vt, stages=stages, slot_stage=slot_stage, smem=off, vregion=vregion)
+                               roww=roww, off=o, bytes=nb, padl=padl, center=center))
+        self.tl = dict(tile=tile, halo=H, ext=ext, vt=vt, stages=stages, slot_stage=slot_stage, smem=off)
         return self.tl
 
     def gen_unknownwise(self):
@@ -474,7 +493,8 @@ class Generator:
                 "template <class A> __device__ __forceinline__ void coef_uw(const A& a, const Params& P, real* __restrict__ out)",
                 list(self.coef_exprs), lambda r: ["out[%d] = %s;" % (i, r[i]) for i in range(nc)], dom))
         if self.tiled:
-            self._tile_layout(out)
+            excl = [im.exclude for im in self.unknowns if im.exclude is not None]
+            self._tile_layout(out + excl)
         return "\n".join(src)
 
     def _halos(self, roots):
@@ -621,14 +641,16 @@ class Generator:
                 hdr.append("#define TH_TW %d\n#define TH_TH %d\n#define TH_TD %d" % tuple(tl["tile"]))
                 hdr.append("#define TH_HX %d\n#define TH_HY %d\n#define TH_HZ %d" % tuple(tl["halo"]))
                 hdr.append("#define TH_SMEM_BYTES %d" % max(128, tl["smem"]))
-                hdr.append("#define TH_VREGION_BYTES %d" % tl["vregion"])
                 hdr.append("#define TH_NSTAGE %d" % len(tl["stages"]))
                 hdr.append("#define TH_STAGE_TABLE {%s}" % (", ".join(
-                    "{%d, %d, %d, %d, %d, %d}" % (st["slot"], st["es"], st["channels"], st["roww"], st["off"], st["padl"])
-                    for st in tl["stages"]) or "{0, 0, 0, 0, 0, 0}"))
+                    "{%d, %d, %d, %d, %d, %d, %d, %d}" % (st["slot"], st["es"], st["channels"], st["roww"], st["off"], st["padl"],
+                                                          st["center"], st["bytes"])
+                    for st in tl["stages"]) or "{0, 0, 0, 0, 0, 0, 0, 0}"))
                 hdr.append("#define TH_SLOT_STAGE_TABLE {%s}" % ", ".join(map(str, tl["slot_stage"])))
                 hdr.append("#define TH_VTILE_TABLE {%s}" % ", ".join(
-                    "{%d, %d, %d, %d, %d}" % (v["roww"], v["zoff"], v["poff"], v["bytes"], v["padl"]) for v in tl["vt"]))
+                    "{%d, %d, %d, %d, %d, %d, %d, %d}" % (v["roww"], v["zoff"], v["poff"], v["bytes"], v["padl"], v["coff"],
+                                                          v["croww"], v["cbytes"]) for v in tl["vt"]))
+                hdr.append("#define TH_STAGE_CTC %d" % int(all(v["coff"] >= 0 for v in tl["vt"])))
         gl = []
         for gi, g in enumerate(self.groups):
             body.append(self.gen_group(gi, g))
@@ -717,9 +739,11 @@ def descriptor_text(d):
             tl = d["tile"]
             ln.append("tile %s %s %d" % (" ".join(map(str, tl["tile"])), " ".join(map(str, tl["halo"])), max(128, tl["smem"])))
             for v in tl["vt"]:
-                ln.append("vtile %d %d %d %d %d" % (v["roww"], v["zoff"], v["poff"], v["bytes"], v["padl"]))
+                ln.append("vtile %d %d %d %d %d %d %d %d" % (v["roww"], v["zoff"], v["poff"], v["bytes"], v["padl"], v["coff"],
+                                                             v["croww"], v["cbytes"]))
             for st in tl["stages"]:
-                ln.append("stage %d %s %d %d %d %d %d %d" % (st["slot"], st["ctype"], st["es"], st["channels"], st["roww"], st["off"], st["bytes"], st["padl"]))
+                ln.append("stage %d %s %d %d %d %d %d %d %d" % (st["slot"], st["ctype"], st["es"], st["channels"], st["roww"], st["off"],
+                                                                st["bytes"], st["padl"], st["center"]))
     return "\n".join(ln) + "\n"
 
 
