@@ -47,6 +47,23 @@ long long ThalloB200_PlanReadVector(Thallo_State* state, Thallo_Plan* plan, cons
  * util.t:774-790).  Writes "kernel_name launches total_ms\n" lines; returns bytes written. */
 long long ThalloB200_PlanKernelTimes(Thallo_State* state, Thallo_Plan* plan, char* buf, long long capacity);
 
+/* ---- multi-GPU: slab partition of an image / volume domain along its slowest axis.
+ * One process per GPU.  Every rank lowers the energy for its LOCAL extent including the ghost
+ * layers it shares with its neighbours (descriptor line "partition <ghost_lo> <ghost_hi>", see
+ * thallo_b200/distributed.py) and passes local slabs of every image (ghost layers included).  The
+ * reference has no multi-device path (SURVEY 2b "Collectives: none").
+ *   ThalloB200_NcclUniqueId       rank 0 creates the NCCL id (128 bytes); the host program distributes it
+ *   ThalloB200_PlanInitComm       collective: NCCL communicator for the PCG scalar reductions
+ *   ThalloB200_PlanIpcHandle      CUDA IPC handle (64 bytes) of this plan's solver vectors + local slow-axis extent
+ *   ThalloB200_PlanConnect        map the neighbours' solver vectors (NULL = no neighbour on that side); halo layers
+ *                                 of p / z / delta are then stored straight into the neighbours' memory over NVLink
+ * All return 0 on success. */
+int ThalloB200_NcclUniqueId(void* id, int capacity);
+int ThalloB200_PlanInitComm(Thallo_State* state, Thallo_Plan* plan, const void* nccl_id, int rank, int world);
+int ThalloB200_PlanIpcHandle(Thallo_State* state, Thallo_Plan* plan, void* handle64, long long* slow_extent);
+int ThalloB200_PlanConnect(Thallo_State* state, Thallo_Plan* plan, const void* handle_lo, long long extent_lo,
+                           const void* handle_hi, long long extent_hi);
+
 /* Last error message of this thread ("" if none). */
 const char* ThalloB200_LastError(void);
 

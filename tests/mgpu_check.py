@@ -1,0 +1,76 @@
+"""Multi-GPU parity check, run under torchrun (one rank per GPU):
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tests/mgpu_check.py
+Solves the same global image_warping problem (a) slab-partitioned over all ranks and (b) on one
+GPU, and compares every cost of the trajectory, the LM inner iteration counts and the unknowns.
+Exit code 0 = parity.  Called by tests/test_gpu_multi.py."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def run(kind, W, H, nit, lit, dist, rank, world, torch):
+    from thallo_b200 import workloads as wl
+    from thallo_b200.api import ThalloSolver
+    from thallo_b200.distributed import SlabSolver
+    d = wl.image_warping_inputs(W, H)
+    names = ("Offset", "Angle", "UrShape", "Constraints", "Mask")
+    scal = [np.array([d["w_fitSqrt"]], np.float32), np.array([d["w_regSqrt"]], np.float32)]
+    s = SlabSolver([W, H], "image_warping", kind, rank, world)
+    loc = [torch.from_numpy(s.slab(d[k])).cuda() for k in names]
+    s.set_parameters(nIterations=nit, lIterations=lit)
+    s.init(loc + scal)
+    costs, lin = [s.current_cost()], []
+    while s.step():
+        costs.append(s.current_cost())
+        lin.append(s.last_linear_iterations())
+    costs.append(s.current_cost())
+    torch.cuda.synchronize()
+    own = [s.owned(t.cpu().numpy()) for t in loc[:2]]
+    gathered = [None] * world
+    dist.all_gather_object(gathered, own)
+    ok = True
+    if rank == 0:
+        off = np.concatenate([g[0] for g in gathered])
+        ang = np.concatenate([g[1] for g in gathered])
+        d1 = wl.image_warping_inputs(W, H)
+        one = [torch.from_numpy(np.ascontiguousarray(d1[k])).cuda() for k in names]
+        r = ThalloSolver([W, H], "image_warping", kind)
+        r.set_parameters(nIterations=nit, lIterations=lit)
+        r.init(one + scal)
+        c1, l1 = [r.current_cost()], []
+        while r.step():
+            c1.append(r.current_cost())
+            l1.append(r.last_linear_iterations())
+        c1.append(r.current_cost())
+        rel = max(abs(a - b) / max(abs(b), 1e-3) for a, b in zip(costs, c1)) if len(costs) == len(c1) else float("inf")
+        du = float(np.abs(off - one[0].cpu().numpy()).max())
+        da = float(np.abs(ang - one[1].cpu().numpy()).max())
+        ok = len(costs) == len(c1) and rel <= 1e-5 and lin == l1 and du < 1e-3 and da < 1e-3
+        print("mgpu %s %dx%d world=%d: max rel cost diff %.3g, lin %s vs %s, max|dOffset| %.3g max|dAngle| %.3g -> %s"
+              % (kind, W, H, world, rel, lin, l1, du, da, "OK" if ok else "MISMATCH"), flush=True)
+        if not ok:
+            print(costs, c1, flush=True)
+    return ok
+
+
+def main():
+    import torch
+    import torch.distributed as dist
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("gloo")
+    ok = True
+    for kind, W, H, nit, lit in [("gauss_newton", 96, 64, 3, 20), ("levenberg_marquardt", 128, 90, 5, 40)]:
+        ok = run(kind, W, H, nit, lit, dist, rank, world, torch) and ok
+    flag = [ok]
+    dist.broadcast_object_list(flag, src=0)
+    dist.destroy_process_group()
+    sys.exit(0 if flag[0] else 1)
+
+
+if __name__ == "__main__":
+    main()

@@ -77,6 +77,12 @@ def lib():
     L.ThalloB200_PlanReadVector.argtypes = [vp, vp, cp, vp, C.c_longlong]
     L.ThalloB200_PlanKernelTimes.restype = C.c_longlong
     L.ThalloB200_PlanKernelTimes.argtypes = [vp, vp, C.c_char_p, C.c_longlong]
+    L.ThalloB200_NcclUniqueId.restype, L.ThalloB200_NcclUniqueId.argtypes = C.c_int, [vp, C.c_int]
+    L.ThalloB200_PlanInitComm.restype, L.ThalloB200_PlanInitComm.argtypes = C.c_int, [vp, vp, vp, C.c_int, C.c_int]
+    L.ThalloB200_PlanIpcHandle.restype = C.c_int
+    L.ThalloB200_PlanIpcHandle.argtypes = [vp, vp, vp, C.POINTER(C.c_longlong)]
+    L.ThalloB200_PlanConnect.restype = C.c_int
+    L.ThalloB200_PlanConnect.argtypes = [vp, vp, vp, C.c_longlong, vp, C.c_longlong]
     L.ThalloB200_LastError.restype, L.ThalloB200_LastError.argtypes = cp, []
     L.ThalloB200_Version.restype, L.ThalloB200_Version.argtypes = cp, []
     _lib = L
@@ -100,7 +106,7 @@ class ThalloSolver:
     ThalloB200_ProblemDefineFromSource."""
 
     def __init__(self, dims, energy, kind="gauss_newton", double=False, verbosity=0, timing=1,
-                 via_file=False, schedule="auto", define_kwargs=None, stream=None):
+                 via_file=False, schedule="auto", define_kwargs=None, stream=None, partition=None):
         L = lib()
         self.L = L
         self.dims = [int(d) for d in dims]
@@ -116,7 +122,8 @@ class ThalloSolver:
             import energies
             from .frontend import codegen
             mod = energies.resolve(energy) or energy
-            low = codegen.lower(energies.load(mod), self.dims, kind, mod, double, schedule, **(define_kwargs or {}))
+            low = codegen.lower(energies.load(mod), self.dims, kind, mod, double, schedule, partition=partition,
+                                **(define_kwargs or {}))
             self.lowered = low
             self.problem = L.ThalloB200_ProblemDefineFromSource(
                 self.state, codegen.descriptor_text(low.desc).encode(), low.source.encode(), kind.encode())

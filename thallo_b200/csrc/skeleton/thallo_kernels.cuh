@@ -283,7 +283,7 @@ extern "C" __global__ void __launch_bounds__(TH_BLOCK)
 th_init_uw(const __grid_constant__ Params P, const __grid_constant__ Vecs V, ThScalars* S, double* partials, int first_nonlinear) {
     ThIdx<th::dom_uw> idx;
     double acc[1] = {0.0};
-    if (th_uw_index(idx)) {
+    if (th_uw_index(idx) && th_owned_slow(idx.c[th::dom_uw::ND - 1])) {     // ghost layers are the neighbours' to initialise
         GAcc<th::dom_uw> a(idx, nullptr);
         const bool ex = th::exclude_u0(a, P);
         real g[TH_U], d[TH_U];
@@ -385,8 +385,15 @@ __device__ __forceinline__ void th_close_iteration(ThScalars* S, real q_toleranc
     }
 #endif
     if (hf) {
+        // the exit decision is published before the progress counter, so a host that has seen
+        // progress >= n also sees every exit taken at an iteration <= n (all ranks of a multi-GPU
+        // solve must stop issuing iterations at the same point)
+        if (S->done) {
+            *(volatile int*)&hf->done_at = it + 1;
+            *(volatile int*)&hf->done_epoch = epoch;
+            __threadfence_system();
+        }
         *(volatile long long*)&hf->progress = ((long long)epoch << 32) | (long long)(it + 1);
-        if (S->done) *(volatile int*)&hf->done_epoch = epoch;
         __threadfence_system();
     }
 }
@@ -403,6 +410,38 @@ __device__ __forceinline__ void th_close_iteration(ThScalars* S, real q_toleranc
         acc[0] += (double)(z_ * rn_);                                            \
         if (TH_LM) acc[1] += (double)((real)0.5 * (dn_ * (rn_ + bb.c)));         \
     }
+// End of step 2 in the last block: publish the two sums.  Multi-GPU plans publish this rank's
+// partial sums instead; the host all-reduces them over NCCL and th_mg_close finishes the iteration.
+__device__ __forceinline__ void th_step2_publish(ThScalars* S, const double (&tot)[2], real q_tolerance, ThHostFlags* hf, int epoch) {
+#if TH_MULTI
+    S->red[0] = tot[0]; S->red[1] = tot[1];
+#else
+    S->rz[(S->it + 1) & 1] = tot[0]; S->q = tot[1];
+#if TH_TILED
+    th_close_iteration(S, q_tolerance, hf, epoch);
+#endif
+#endif
+}
+#if TH_MULTI
+extern "C" __global__ void th_mg_close(ThScalars* S, real q_tolerance, ThHostFlags* hf, int epoch) {
+    if (S->done) return;
+    S->rz[(S->it + 1) & 1] = S->red[0]; S->q = S->red[1];
+    th_close_iteration(S, q_tolerance, hf, epoch);
+}
+// halo push: copy contiguous segments (boundary layers of every unknown image) into the
+// neighbours' ghost layers over NVLink peer mappings
+struct ThSegs { const real* src[2 * TH_NUM_UIMG]; real* dst[2 * TH_NUM_UIMG]; long long count[2 * TH_NUM_UIMG]; };
+extern "C" __global__ void __launch_bounds__(TH_BLOCK)
+th_halo_push(const __grid_constant__ ThSegs G, int nseg, const ThScalars* S, int check_done) {
+    if (check_done && S->done) return;
+    for (int s = 0; s < nseg; ++s) {
+        const real* __restrict__ src = G.src[s];
+        real* __restrict__ dst = G.dst[s];
+        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < G.count[s]; i += (long long)gridDim.x * blockDim.x) dst[i] = src[i];
+    }
+}
+#endif
+
 extern "C" __global__ void __launch_bounds__(TH_BLOCK)
 th_pcg_b(const __grid_constant__ Vecs V, ThScalars* S, double* partials, real q_tolerance, ThHostFlags* hf, int epoch) {
     if (S->done) return;
@@ -415,23 +454,9 @@ th_pcg_b(const __grid_constant__ Vecs V, ThScalars* S, double* partials, real q_
     const real* __restrict__ vpre = V.pre;
     const real* __restrict__ vb = V.b;
     double acc[2] = {0.0, 0.0};
-    const long long n4 = TH_NUNK / 4;
     const long long stride = (long long)gridDim.x * blockDim.x;
     const long long gtid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    for (long long i = gtid; i < n4; i += stride) {
-        const real4 p = ((const real4*)pp)[i];
-        real4 dl = ((const real4*)vd)[i];
-        real4 r = ((const real4*)vr)[i];
-        const real4 ap = ((const real4*)vap)[i];
-        real4 pre, bb, zz;
-        if (TH_USEPRE) pre = ((const real4*)vpre)[i];
-        if (TH_LM) bb = ((const real4*)vb)[i];
-        TH_B_LANE(x) TH_B_LANE(y) TH_B_LANE(z) TH_B_LANE(w)
-        ((real4*)vd)[i] = dl;
-        ((real4*)vr)[i] = r;
-        ((real4*)vz)[i] = zz;
-    }
-    for (long long i = n4 * 4 + gtid; i < TH_NUNK; i += stride) {
+    auto scalar = [&](long long i) {
         const real pv = pp[i];
         const real dn = vd[i] + alpha * pv;
         const real rn = vr[i] - alpha * vap[i];
@@ -439,15 +464,30 @@ th_pcg_b(const __grid_constant__ Vecs V, ThScalars* S, double* partials, real q_
         vd[i] = dn; vr[i] = rn; vz[i] = zv;
         acc[0] += (double)(zv * rn);
         if (TH_LM) acc[1] += (double)((real)0.5 * (dn * (rn + vb[i])));
+    };
+#pragma unroll
+    for (int k = 0; k < TH_NRANGES; ++k) {          // owned flat ranges (one range = everything on a single GPU)
+        const long long lo = th_range_lo(k), hi = th_range_hi(k);
+        const long long v0 = (lo + 3) / 4, v1 = hi / 4 > v0 ? hi / 4 : v0;
+        for (long long i = v0 + gtid; i < v1; i += stride) {
+            const real4 p = ((const real4*)pp)[i];
+            real4 dl = ((const real4*)vd)[i];
+            real4 r = ((const real4*)vr)[i];
+            const real4 ap = ((const real4*)vap)[i];
+            real4 pre, bb, zz;
+            if (TH_USEPRE) pre = ((const real4*)vpre)[i];
+            if (TH_LM) bb = ((const real4*)vb)[i];
+            TH_B_LANE(x) TH_B_LANE(y) TH_B_LANE(z) TH_B_LANE(w)
+            ((real4*)vd)[i] = dl;
+            ((real4*)vr)[i] = r;
+            ((real4*)vz)[i] = zz;
+        }
+        for (long long i = lo + gtid; i < (v0 * 4 < hi ? v0 * 4 : hi); i += stride) scalar(i);
+        for (long long i = v1 * 4 + gtid; i < hi; i += stride) scalar(i);
     }
     double tot[2];
     if (th_grid_reduce<2>(acc, tot, partials, &S->ticket[2])) {
-        if (threadIdx.x == 0) {
-            S->rz[(S->it + 1) & 1] = tot[0]; S->q = tot[1];
-#if TH_TILED
-            th_close_iteration(S, q_tolerance, hf, epoch);
-#endif
-        }
+        if (threadIdx.x == 0) th_step2_publish(S, tot, q_tolerance, hf, epoch);
     }
 }
 
@@ -457,8 +497,10 @@ th_step2_first(const __grid_constant__ Vecs V, ThScalars* S) {
     const real alpha = th_alpha(S);
     const real* __restrict__ pp = th_pcur(V, S);
     real* __restrict__ vd = V.delta;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < TH_NUNK; i += (long long)gridDim.x * blockDim.x)
-        vd[i] = vd[i] + alpha * pp[i];
+#pragma unroll
+    for (int k = 0; k < TH_NRANGES; ++k)
+        for (long long i = th_range_lo(k) + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < th_range_hi(k); i += (long long)gridDim.x * blockDim.x)
+            vd[i] = vd[i] + alpha * pp[i];
 }
 
 // r = b - A delta; add_ctc: A delta still lacks the CtC*delta term (residualwise / materialized schedules)
@@ -466,27 +508,31 @@ extern "C" __global__ void __launch_bounds__(TH_BLOCK)
 th_step2_second(const __grid_constant__ Vecs V, ThScalars* S, double* partials, int add_ctc, real q_tolerance, ThHostFlags* hf, int epoch) {
     if (S->done) return;
     double acc[2] = {0.0, 0.0};
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < TH_NUNK; i += (long long)gridDim.x * blockDim.x) {
-        const real delta = V.delta[i];
-        real Ax = V.Adelta[i];
-        if (add_ctc) Ax += V.CtC[i] * delta;
-        const real b = V.b[i];
-        const real pre = TH_USEPRE ? V.pre[i] : (real)1;
-        const real r = b - Ax;
-        const real z = TH_USEPRE ? pre * r : r;
-        V.r[i] = r;
-        V.z[i] = z;
-        acc[0] += (double)(z * r);
-        acc[1] += (double)((real)0.5 * (delta * (r + b)));
-    }
+    const real* __restrict__ vdl = V.delta;
+    const real* __restrict__ vad = V.Adelta;
+    const real* __restrict__ vctc = V.CtC;
+    const real* __restrict__ vb = V.b;
+    const real* __restrict__ vpre = V.pre;
+    real* __restrict__ vr = V.r;
+    real* __restrict__ vz = V.z;
+#pragma unroll
+    for (int k = 0; k < TH_NRANGES; ++k)
+        for (long long i = th_range_lo(k) + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < th_range_hi(k); i += (long long)gridDim.x * blockDim.x) {
+            const real delta = vdl[i];
+            real Ax = vad[i];
+            if (add_ctc) Ax += vctc[i] * delta;
+            const real b = vb[i];
+            const real pre = TH_USEPRE ? vpre[i] : (real)1;
+            const real r = b - Ax;
+            const real z = TH_USEPRE ? pre * r : r;
+            vr[i] = r;
+            vz[i] = z;
+            acc[0] += (double)(z * r);
+            acc[1] += (double)((real)0.5 * (delta * (r + b)));
+        }
     double tot[2];
     if (th_grid_reduce<2>(acc, tot, partials, &S->ticket[2])) {
-        if (threadIdx.x == 0) {
-            S->rz[(S->it + 1) & 1] = tot[0]; S->q = tot[1];
-#if TH_TILED
-            th_close_iteration(S, q_tolerance, hf, epoch);
-#endif
-        }
+        if (threadIdx.x == 0) th_step2_publish(S, tot, q_tolerance, hf, epoch);
     }
 }
 
@@ -738,6 +784,22 @@ __device__ __forceinline__ real th_tile_apply(const unsigned char* sm, const Par
     real dot = (real)0;
     if (idx.from_coords(x0 + tx, y0 + ty, z0 + tz)) {
         TAcc<th::dom_uw, UPD> a(idx, sm, tx, ty, tz, beta);
+#if TH_MULTI
+        if (!th_owned_slow(idx.c[th::dom_uw::ND - 1])) {
+            // ghost layer: the owner computes Ap there; this rank only keeps its copy of the search
+            // direction current (same z, same p_old, same beta -> the same bits as the owner's)
+            if (mode == 0) {
+#pragma unroll
+                for (int k = 0; k < TH_NUM_UIMG; ++k) {
+                    const int te = a.template tile_elem<0, 0, 0>(TH_VTILE[k].roww, TH_VTILE[k].padl, TH_UIMG[k].channels);
+#pragma unroll
+                    for (int ch = 0; ch < TH_UIMG[k].channels; ++ch)
+                        pnew[TH_UIMG[k].offset + idx.lin * TH_UIMG[k].channels + ch] = a.vec_at(k, te + ch);
+                }
+            }
+            return dot;
+        }
+#endif
         if (!th::exclude_u0(a, P)) {
             real o[TH_U];
             th::applyJTJ_uw(a, P, o);
@@ -930,7 +992,8 @@ th_step1_finish(const __grid_constant__ Params P, const __grid_constant__ Vecs V
     th_cost_g##G(const __grid_constant__ Params P, ThScalars* S, double* partials, int first) {                     \
         ThIdx<th::dom_g##G> idx;                                                                                    \
         double acc[1] = {0.0};                                                                                      \
-        if (idx.from_linear((long long)blockIdx.x * blockDim.x + threadIdx.x)) {                                    \
+        if (idx.from_linear((long long)blockIdx.x * blockDim.x + threadIdx.x) &&                                    \
+            th_owned_slow(idx.c[th::dom_g##G::ND - 1])) {                                                           \
             GAcc<th::dom_g##G> a(idx, nullptr);                                                                     \
             acc[0] = (double)th::cost_g##G(a, P);                                                                   \
         }                                                                                                           \
@@ -944,7 +1007,8 @@ th_step1_finish(const __grid_constant__ Params P, const __grid_constant__ Vecs V
                       double* partials, int first) {                                                                \
         ThIdx<th::dom_g##G> idx;                                                                                    \
         double acc[1] = {0.0};                                                                                      \
-        if (idx.from_linear((long long)blockIdx.x * blockDim.x + threadIdx.x)) {                                    \
+        if (idx.from_linear((long long)blockIdx.x * blockDim.x + threadIdx.x) &&                                    \
+            th_owned_slow(idx.c[th::dom_g##G::ND - 1])) {                                                           \
             GAcc<th::dom_g##G> a(idx, V.delta);                                                                     \
             acc[0] = (double)th::modelcost_g##G(a, P);                                                              \
         }                                                                                                           \

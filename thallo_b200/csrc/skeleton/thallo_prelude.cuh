@@ -52,6 +52,7 @@ struct ThScalars {
     double cost;
     double modelcost;
     double spare;
+    double red[2];        // multi-GPU: this rank's partial <z,r> and q, all-reduced before the iteration is closed
     unsigned int ticket[8];
     int it;
     int done;
@@ -60,13 +61,39 @@ struct ThScalars {
 };
 
 // Host-visible progress flags (pinned, mapped).
-struct ThHostFlags { long long progress; int done_epoch; int pad; };
+struct ThHostFlags { long long progress; int done_epoch; int done_at; };
 
 struct ThUImg { int channels; long long offset; int ptr_slot; int ndim; int dim[TH_MAXD]; long long elements; };
 struct ThGroup { int ndim; int dim[TH_MAXD]; int nterms; int nnz; };
 __device__ constexpr ThUImg TH_UIMG[TH_NUM_UIMG] = TH_UIMG_TABLE;
 __device__ constexpr ThGroup TH_GROUPS[TH_NGROUPS] = TH_GROUP_TABLE;
 __device__ constexpr long long TH_DIMS[TH_NDIMS] = TH_DIM_SIZES;
+
+// ---- multi-GPU slab partition: the plan is compiled for the rank-local extent of the
+// slowest axis INCLUDING TH_GHOST_LO / TH_GHOST_HI ghost layers that belong to the neighbouring
+// ranks.  Owned elements of every unknown image form one contiguous flat range.
+#ifndef TH_MULTI
+#define TH_MULTI 0
+#endif
+#ifndef TH_GHOST_LO
+#define TH_GHOST_LO 0
+#define TH_GHOST_HI 0
+#endif
+#if TH_MULTI
+#define TH_NRANGES TH_NUM_UIMG
+__device__ constexpr long long th_range_lo(int k) {
+    return TH_UIMG[k].offset + (long long)TH_GHOST_LO * (TH_UIMG[k].elements / TH_DSLOW) * TH_UIMG[k].channels;
+}
+__device__ constexpr long long th_range_hi(int k) {
+    return TH_UIMG[k].offset + (long long)(TH_DSLOW - TH_GHOST_HI) * (TH_UIMG[k].elements / TH_DSLOW) * TH_UIMG[k].channels;
+}
+__device__ __forceinline__ bool th_owned_slow(int c) { return c >= TH_GHOST_LO && c < TH_DSLOW - TH_GHOST_HI; }
+#else
+#define TH_NRANGES 1
+__device__ constexpr long long th_range_lo(int) { return 0; }
+__device__ constexpr long long th_range_hi(int) { return TH_NUNK; }
+__device__ __forceinline__ bool th_owned_slow(int) { return true; }
+#endif
 
 #if TH_TILED
 // Shared-memory tile layout of the tiled operator kernel (computed by the front end):

@@ -211,6 +211,20 @@ long long ThalloB200_PlanKernelTimes(Thallo_State*, Thallo_Plan* plan, char* buf
     buf[n] = 0;
     return n;
 }
+int ThalloB200_NcclUniqueId(void* id, int capacity) { return thallo::nccl_unique_id(id, capacity); }
+int ThalloB200_PlanInitComm(Thallo_State*, Thallo_Plan* plan, const void* nccl_id, int rank, int world) {
+    if (!plan || !nccl_id) return 1;
+    const int r = plan->plan->comm_init(nccl_id, rank, world);
+    if (r) set_error(plan->plan->error());
+    return r;
+}
+int ThalloB200_PlanIpcHandle(Thallo_State*, Thallo_Plan* plan, void* handle64, long long* slow_extent) {
+    return plan && handle64 ? plan->plan->ipc_handle(handle64, slow_extent) : 1;
+}
+int ThalloB200_PlanConnect(Thallo_State*, Thallo_Plan* plan, const void* handle_lo, long long extent_lo, const void* handle_hi,
+                           long long extent_hi) {
+    return plan ? plan->plan->connect(handle_lo, extent_lo, handle_hi, extent_hi) : 1;
+}
 const char* ThalloB200_LastError(void) { return g_last_error.c_str(); }
 const char* ThalloB200_Version(void) { return "thallo_b200 0.1.0 (sm_100a)"; }
 

@@ -1,7 +1,9 @@
 #include "th_plan.h"
 
+#include <dlfcn.h>
 #include <sched.h>
 
+#include <atomic>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -66,6 +68,7 @@ bool parse_descriptor(const std::string& text, PlanDesc& d, std::string& err) {
         } else if (key == "U") ls >> d.U;
         else if (key == "uw_dims") { int n; ls >> n; d.uw_dims.resize(n); for (auto& x : d.uw_dims) ls >> x; }
         else if (key == "ncoef") ls >> d.ncoef;
+        else if (key == "partition") { ls >> d.ghost_lo >> d.ghost_hi; d.multi = true; }
         else if (key == "tile") {
             ls >> d.tile[0] >> d.tile[1] >> d.tile[2] >> d.halo[0] >> d.halo[1] >> d.halo[2] >> d.smem_bytes;
             d.tiled = true;
@@ -76,6 +79,120 @@ bool parse_descriptor(const std::string& text, PlanDesc& d, std::string& err) {
     if (d.nunk <= 0 || d.unknowns.empty() || d.groups.empty()) { err = "descriptor lacks unknowns or residual groups"; return false; }
     if (d.kind != "gauss_newton" && d.kind != "levenberg_marquardt") { err = "solver kind must be gauss_newton or levenberg_marquardt"; return false; }
     return true;
+}
+
+// ------------------------------------------------------------------ NCCL (loaded at run time; only multi-GPU plans need it)
+struct NcclId { char internal[128]; };
+struct NcclApi {
+    int (*GetUniqueId)(NcclId*) = nullptr;
+    int (*CommInitRank)(void**, int, NcclId, int) = nullptr;
+    int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    int (*CommDestroy)(void*) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+    bool ok = false;
+};
+static NcclApi& nccl() {
+    static NcclApi api;
+    static bool tried = false;
+    if (tried) return api;
+    tried = true;
+    void* h = nullptr;
+    if (const char* e = getenv("THALLO_B200_NCCL")) h = dlopen(e, RTLD_NOW | RTLD_GLOBAL);
+    for (const char* name : {"libnccl.so.2", "libnccl.so"})      // already mapped when the host process imported torch
+        if (!h) h = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
+    if (!h) return api;
+    api.GetUniqueId = (decltype(api.GetUniqueId))dlsym(h, "ncclGetUniqueId");
+    api.CommInitRank = (decltype(api.CommInitRank))dlsym(h, "ncclCommInitRank");
+    api.AllReduce = (decltype(api.AllReduce))dlsym(h, "ncclAllReduce");
+    api.CommDestroy = (decltype(api.CommDestroy))dlsym(h, "ncclCommDestroy");
+    api.GetErrorString = (decltype(api.GetErrorString))dlsym(h, "ncclGetErrorString");
+    api.ok = api.GetUniqueId && api.CommInitRank && api.AllReduce && api.CommDestroy;
+    return api;
+}
+int nccl_unique_id(void* out, int capacity) {
+    if (capacity < (int)sizeof(NcclId) || !nccl().ok) return 1;
+    return nccl().GetUniqueId((NcclId*)out);
+}
+static void fatal_nccl(int r, const char* what) {
+    fprintf(stderr, "thallo_b200: NCCL error %d (%s) in %s\n", r, nccl().GetErrorString ? nccl().GetErrorString(r) : "?", what);
+    exit(1);
+}
+
+int Plan::comm_init(const void* id, int rank, int world) {
+    if (!d_.multi) { error_ = "plan was not lowered with a partition"; return 1; }
+    if (!nccl().ok) { error_ = "libnccl.so.2 not found (set THALLO_B200_NCCL)"; return 1; }
+    NcclId nid;
+    memcpy(&nid, id, sizeof nid);
+    rank_ = rank; world_ = world;
+    const int r = nccl().CommInitRank(&comm_, world, nid, rank);
+    if (r != 0) fatal_nccl(r, "ncclCommInitRank");
+    return 0;
+}
+int Plan::ipc_handle(void* handle64, long long* slow_extent) {
+    cudaIpcMemHandle_t h;
+    CD(cudaIpcGetMemHandle(&h, vec_block_));
+    static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    memcpy(handle64, &h, 64);
+    if (slow_extent) *slow_extent = d_.uw_dims.back();
+    return 0;
+}
+int Plan::connect(const void* handle_lo, long long extent_lo, const void* handle_hi, long long extent_hi) {
+    const void* hs[2] = {handle_lo, handle_hi};
+    const long long ex[2] = {extent_lo, extent_hi};
+    for (int i = 0; i < 2; ++i) {
+        if (!hs[i]) continue;
+        cudaIpcMemHandle_t h;
+        memcpy(&h, hs[i], 64);
+        CD(cudaIpcOpenMemHandle((void**)&peer_[i], h, cudaIpcMemLazyEnablePeerAccess));
+        peer_extent_[i] = ex[i];
+    }
+    return 0;
+}
+// sum a few doubles of the device scalar block over all ranks, in place, on the solver stream (NVLink / NVLS)
+void Plan::allreduce(size_t off, int count) {
+    if (!comm_) { fprintf(stderr, "thallo_b200: multi-GPU plan used before ThalloB200_PlanInitComm\n"); exit(1); }
+    const int r = nccl().AllReduce(dscalar(off), dscalar(off), (size_t)count, /*ncclFloat64*/ 8, /*ncclSum*/ 0, comm_, stream());
+    if (r != 0) fatal_nccl(r, "ncclAllReduce");
+}
+// Boundary layers of solver vector `vec` -> the neighbours' ghost layers, stored directly into their
+// memory over NVLink (CUDA IPC peer mappings).  Ordering: the push precedes this rank's next
+// all-reduce contribution in stream order, and a neighbour reads its ghost layers only after that
+// all-reduce has completed on its side.
+void Plan::halo_push(int vec, int check_done) {
+    const int nd = (int)d_.uw_dims.size();
+    const long long D = d_.uw_dims[nd - 1];
+    const int h = d_.halo[nd - 1];
+    if (h == 0 || world_ == 1) return;
+    struct Segs { const void* src[8]; void* dst[8]; long long count[8]; } g{};
+    int n = 0;
+    for (int side = 0; side < 2; ++side) {
+        if (!peer_[side]) continue;
+        const long long E = peer_extent_[side];
+        long long peer_off = 0, peer_nunk = 0;
+        for (auto& u : d_.unknowns) peer_nunk += (u.elements / D) * E * u.channels;
+        const size_t peer_stride = ((size_t)peer_nunk * real_size_ + 255) / 256 * 256;
+        for (auto& u : d_.unknowns) {
+            const long long layer = (u.elements / D) * u.channels;           // scalars per slow-axis layer
+            const long long src_row = side == 0 ? d_.ghost_lo : D - d_.ghost_hi - h;
+            const long long dst_row = side == 0 ? E - h : 0;
+            g.src[n] = (const char*)vecs_[vec] + (size_t)(u.offset + src_row * layer) * real_size_;
+            g.dst[n] = peer_[side] + peer_stride * vec + (size_t)(peer_off + dst_row * layer) * real_size_;
+            g.count[n] = (long long)h * layer;
+            peer_off += (u.elements / D) * E * u.channels;
+            ++n;
+        }
+    }
+    if (!n) return;
+    // ThSegs: src[2*NU], dst[2*NU], count[2*NU]
+    const size_t nu2 = 2 * d_.unknowns.size();
+    std::vector<char> buf(nu2 * 24, 0);
+    for (int i = 0; i < n; ++i) {
+        memcpy(buf.data() + 8 * i, &g.src[i], 8);
+        memcpy(buf.data() + 8 * (nu2 + i), &g.dst[i], 8);
+        memcpy(buf.data() + 8 * (2 * nu2 + i), &g.count[i], 8);
+    }
+    void* a[] = {buf.data(), &n, &d_scalars_, &check_done};
+    launch(fn("th_halo_push"), dim3(32), dim3(256), a);
 }
 
 // ------------------------------------------------------------------ plan
@@ -116,7 +233,7 @@ Plan::Plan(const StateOptions* opts, const PlanDesc& desc, const std::string& so
     CD(cudaMemsetAsync(d_scalars_, 0, sizeof(HScalars), stream()));
     CD(cudaHostAlloc((void**)&h_scalars_, sizeof(HScalars), cudaHostAllocDefault));
     CD(cudaHostAlloc((void**)&h_flags_, sizeof(HHostFlags), cudaHostAllocMapped));
-    h_flags_->progress = 0; h_flags_->done_epoch = -1;
+    h_flags_->progress = 0; h_flags_->done_epoch = -1; h_flags_->done_at = 0;
     CD(cudaHostGetDevicePointer(&d_flags_, (void*)h_flags_, 0));
 
     int sms = 148;
@@ -222,6 +339,8 @@ void Plan::build_vector_maps() {
 }
 
 Plan::~Plan() {
+    for (int i = 0; i < 2; ++i) if (peer_[i]) cudaIpcCloseMemHandle(peer_[i]);
+    if (comm_) nccl().CommDestroy(comm_);
     if (vec_block_) cudaFree(vec_block_);
     if (coef_) cudaFree(coef_);
     if (d_scalars_) cudaFree(d_scalars_);
@@ -359,6 +478,7 @@ double Plan::compute_cost() {
         void* args[] = {P, &d_scalars_, &d_partials_, &first};
         launch_group(fn("th_cost_g" + std::to_string(g)), (int)g, args);
     }
+    if (d_.multi) allreduce(offsetof(HScalars, cost), 1);
     read_scalars();
     return round_real(h_scalars_->cost);
 }
@@ -462,6 +582,7 @@ void Plan::linear_iteration(int l) {
     // ---- operator: Ap = (JtJ [+CtC]) p and alphaDenominator
     if (d_.tiled) {
         launch_tiled(0);          // also forms p = z + beta p (PCGStep3 of the previous iteration)
+        if (d_.multi) allreduce(offsetof(HScalars, aD), 1);
     } else if (d_.at_output) {
         void* a[] = {P, V, &d_scalars_, &d_partials_, &zero};
         launch_uw(fn("th_step1_uw"), a);
@@ -483,6 +604,10 @@ void Plan::linear_iteration(int l) {
         }
         int add_ctc = 0;
         if (d_.tiled) {
+            if (d_.multi) {       // A*delta gathers delta from the ghost layers
+                halo_push(V_DELTA, 1);
+                allreduce(offsetof(HScalars, spare), 1);
+            }
             launch_tiled(1);
         } else if (d_.at_output) {
             void* a[] = {P, V, &d_scalars_, &d_partials_, &one};
@@ -503,6 +628,12 @@ void Plan::linear_iteration(int l) {
     } else {
         void* a[] = {V, &d_scalars_, &d_partials_, qtol, &d_flags_, &epoch_};
         launch_flat(fn("th_pcg_b"), a);
+    }
+    if (d_.multi) {               // z ghost layers, global <z,r> and q, then close the iteration
+        halo_push(V_Z, 1);
+        allreduce(offsetof(HScalars, red), 2);
+        void* a[] = {&d_scalars_, qtol, &d_flags_, &epoch_};
+        launch(fn("th_mg_close"), dim3(1), dim3(1), a);
     }
     // ---- p = z + beta p (fused into the next th_pcg_a in the tiled schedule)
     if (!d_.tiled) {
@@ -528,6 +659,10 @@ int Plan::step(void** params) {
     if (d_.at_output) {
         void* a[] = {P, V, &d_scalars_, &d_partials_, &first};
         launch_uw(fn("th_init_uw"), a);
+        if (d_.multi) {                       // z (= p0) ghost layers, global <r,p>
+            halo_push(V_Z, 0);
+            allreduce(offsetof(HScalars, rz), 1);
+        }
     } else {
         clear(vecs_[V_R]);
         clear(vecs_[V_PRE]);
@@ -540,15 +675,23 @@ int Plan::step(void** params) {
     }
     span_end(cur_phase_, ev_setup_);
     span_begin(cur_phase_);
-    const int depth = 4;   // LM: how far the host may run ahead of the device's progress report
+    // LM: the device decides when the linear solve ends (zeta test) and reports it through mapped
+    // pinned memory; the host runs at most `depth` iterations ahead.  Before issuing iteration l it
+    // waits until iteration l - depth + 1 has been closed and stops iff the exit was taken at or
+    // before that iteration -- a function of device data only, so every rank of a multi-GPU solve
+    // issues exactly the same sequence of kernels and collectives.
+    const int depth = 4;
     for (int l = 0; l < sp_.lIterations; ++l) {
-        if (d_.lm) {
+        const int need = l - depth + 1;
+        if (d_.lm && need >= 1) {
             bool stop = false;
             for (unsigned spins = 0;; ++spins) {
-                if (h_flags_->done_epoch == epoch_) { stop = true; break; }
                 const long long pr = h_flags_->progress;
                 const int done_iters = (int)(pr >> 32) == epoch_ ? (int)(pr & 0xffffffff) : 0;
-                if (l - done_iters < depth) break;
+                std::atomic_thread_fence(std::memory_order_acquire);
+                const bool done = h_flags_->done_epoch == epoch_;
+                if (done && h_flags_->done_at <= need) { stop = true; break; }
+                if (done_iters >= need) break;
                 if ((spins & 1023) == 1023) {          // a faulted kernel never reports progress: surface the error
                     const cudaError_t e = cudaStreamQuery(stream());
                     if (e != cudaSuccess && e != cudaErrorNotReady) fatal_cuda(e, "PCG iteration (asynchronous kernel failure)");
@@ -562,12 +705,17 @@ int Plan::step(void** params) {
     span_end(cur_phase_, ev_linear_);
     span_begin(cur_phase_);
     int zero = 0;
+    if (d_.multi) {   // delta ghost layers (model cost and the update read them); the all-reduce orders the exchange
+        halo_push(V_DELTA, 0);
+        allreduce(offsetof(HScalars, spare), 1);
+    }
     if (d_.lm) {   // computeModelCostChange + savePreviousUnknowns, gauss_newton.t:1694-1697
         for (size_t g = 0; g < d_.groups.size(); ++g) {
             int f = g == 0;
             void* a[] = {P, V, &d_scalars_, &d_partials_, &f};
             launch_group(fn("th_modelcost_g" + std::to_string(g)), (int)g, a);
         }
+        if (d_.multi) allreduce(offsetof(HScalars, modelcost), 1);
         void* a[] = {P, &vecs_[V_PREVX], &zero};
         launch_flat(fn("th_copy_x"), a);
     }

@@ -38,8 +38,12 @@ struct PlanDesc {
     int smem_bytes = 0;
     std::vector<VTileDesc> vtiles;
     std::vector<StageDesc> stages;
+    // multi-GPU slab partition ("partition" line): ghost layers of the slowest axis included in dims
+    bool multi = false;
+    int ghost_lo = 0, ghost_hi = 0;
 };
 bool parse_descriptor(const std::string& text, PlanDesc& d, std::string& err);
+int nccl_unique_id(void* out, int capacity);
 
 struct SolverParameters {   // gauss_newton.t:200-216, defaults :41-55
     float min_relative_decrease = 1e-3f;
@@ -65,11 +69,11 @@ struct StateOptions {
 
 // mirrors the device structs in skeleton/thallo_prelude.cuh
 struct HScalars {
-    double rz[2], aD, q, Q0, cost, modelcost, spare;
+    double rz[2], aD, q, Q0, cost, modelcost, spare, red[2];
     unsigned int ticket[8];
     int it, done, lin_done, pad;
 };
-struct HHostFlags { volatile long long progress; volatile int done_epoch; int pad; };
+struct HHostFlags { volatile long long progress; volatile int done_epoch; volatile int done_at; };
 
 class Plan {
 public:
@@ -86,6 +90,10 @@ public:
     void get_parameter(const char* name, void* value);
     void summary(Thallo_PerformanceSummary* s) const { *s = perf_; }
     long long read_vector(const char* name, void* dst, long long count);
+    // multi-GPU (include/thallo_b200.h "slab partition")
+    int comm_init(const void* nccl_id, int rank, int world);
+    int ipc_handle(void* handle64, long long* slow_extent);
+    int connect(const void* handle_lo, long long extent_lo, const void* handle_hi, long long extent_hi);
     // per-kernel device times (timingLevel >= 2, like util.t:774-790): "name count total_ms\n" lines
     std::string kernel_times();
 
@@ -132,6 +140,14 @@ private:
     bool use_tma_ = false;
     bool vector_maps_ok_ = false;
     CUfunction pcg_a_ = nullptr;
+    // multi-GPU state
+    void* comm_ = nullptr;              // ncclComm_t
+    int rank_ = 0, world_ = 1;
+    char* peer_[2] = {nullptr, nullptr};            // neighbours' solver-vector blocks (CUDA IPC mappings): lo, hi
+    long long peer_extent_[2] = {0, 0};
+    void allreduce(size_t scalars_offset, int count);
+    void halo_push(int vec, int check_done);
+    void* dscalar(size_t off) const { return (char*)d_scalars_ + off; }
     unsigned tiled_grid_[2] = {1, 1};   // persistent grid of th_pcg_a_ld / th_pcg_a
     unsigned tiled_smem_[2] = {0, 0};
     int sms_ = 148;

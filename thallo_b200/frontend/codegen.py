@@ -158,8 +158,11 @@ class Emitter:
 
 
 class Generator:
-    def __init__(self, L, name, kind, double=False, schedule="auto", lm_as_committed=False, hoist=True, tile=None):
+    def __init__(self, L, name, kind, double=False, schedule="auto", lm_as_committed=False, hoist=True, tile=None,
+                 partition=None):
         self.L, self.name = L, name
+        # multi-GPU slab partition: (ghost_lo, ghost_hi) ghost layers of the slowest axis included in `dims`
+        self.partition = tuple(int(x) for x in partition) if partition is not None else None
         self.hoist_enabled = bool(hoist)
         self.tile_request = tile
         self.double = bool(double)
@@ -610,6 +613,13 @@ class Generator:
         hdr.append("#define TH_LM %d" % int(self.lm))
         hdr.append("#define TH_USEPRE %d" % int(L.usepreconditioner))
         hdr.append("#define TH_AT_OUTPUT %d" % int(self.schedule == "at_output"))
+        if self.partition is not None:
+            assert self.tiled, "multi-GPU partitioning needs the tiled at-output schedule (2-D / 3-D image domain)"
+            assert all(tuple(g["domain"]) == tuple(self.udomain) for g in self.groups), \
+                "multi-GPU partitioning needs every residual domain to equal the unknown domain"
+            hdr.append("#define TH_MULTI 1")
+            hdr.append("#define TH_GHOST_LO %d\n#define TH_GHOST_HI %d" % self.partition)
+            hdr.append("#define TH_DSLOW %d" % L.dims[self.udomain[-1]].size)
         hdr.append("#define TH_NUM_UIMG %d" % len(self.unknowns))
         hdr.append("#define TH_NUNK %dLL" % self.nunk)
         hdr.append("#define TH_NPTR %d" % max(1, len(self.ptr_pidx)))
@@ -697,6 +707,7 @@ class Generator:
             d["halo_img"] = {k: v for k, v in self.halo["img"].items()}
             d["halo_vec"] = {k: v for k, v in self.halo["vec"].items()}
             d["ncoef"] = len(self.coef_exprs)
+            d["partition"] = self.partition
             d["tiled"] = int(self.tiled)
             if self.tiled:
                 d["tile"] = self.tl
@@ -735,6 +746,8 @@ def descriptor_text(d):
         ln.append("U %d" % d["U"])
         ln.append("uw_dims %d %s" % (len(d["uw_dims"]), " ".join(map(str, d["uw_dims"]))))
         ln.append("ncoef %d" % d.get("ncoef", 0))
+        if d.get("partition") is not None:
+            ln.append("partition %d %d" % tuple(d["partition"]))
         if d.get("tiled"):
             tl = d["tile"]
             ln.append("tile %s %s %d" % (" ".join(map(str, tl["tile"])), " ".join(map(str, tl["halo"])), max(128, tl["smem"])))
@@ -748,10 +761,10 @@ def descriptor_text(d):
 
 
 def lower(define, dims, kind="gauss_newton", name="energy", double=False, schedule="auto",
-          lm_as_committed=False, hoist=True, tile=None, **define_kwargs):
+          lm_as_committed=False, hoist=True, tile=None, partition=None, **define_kwargs):
     from .dsl import build_spec
     L = build_spec(define, dims, **define_kwargs)
-    gen = Generator(L, name, kind, double, schedule, lm_as_committed, hoist, tile)
+    gen = Generator(L, name, kind, double, schedule, lm_as_committed, hoist, tile, partition)
     out = gen.generate()
     out.generator = gen
     return out
