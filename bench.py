@@ -9,8 +9,11 @@ examples/image_warping/src/main.cpp:131-134), synthetic inputs from thallo_b200.
 A "step" is one whole Thallo_ProblemSolve of that problem from its initial state.
 `value` = PCG (linear) iterations executed per second, inputs resident in HBM; `e2e` = the same
 through Thallo_ProblemSolve with HOST buffers (pinned H2D of every input, D2H of the unknowns and
-the final cost inside the timed region).  N > 1: one process per GPU (torchrun); until the
-slab-partitioned solver lands every rank solves its own 2048x2048 problem ("replicas", weak scaling).
+the final cost inside the timed region).  N > 1: one process per GPU (torchrun), ONE global problem of
+2048 x (2048 N) pixels slab-partitioned along y over the N ranks (weak scaling: 2048x2048 owned pixels
+per GPU): halo rows go over NVLink peer mappings, the PCG scalars over NCCL (thallo_b200/distributed.py).
+`value` at N > 1 counts every global PCG iteration N times (it processes N 2048x2048 slabs), i.e. it is
+the aggregate number of 2048x2048-slab PCG iterations per second.
 
 `--impl reference` times the reference's CPU path: the plain-C restatement of its cpuOnly
 simulator (oracle/iw_cpu.c; the Terra/Lua reference cannot be built in this image) on all host
@@ -147,9 +150,12 @@ def run_reference(a, rank, world):
 
 def workload_config(a, world):
     return {"workload": "examples/image_warping 2-D ARAP %dx%d, levenberg_marquardt, float32, nIterations=%d, lIterations=%d, "
-                        "one Thallo_ProblemSolve per step" % (a.size, a.size, NIT, LIT),
-            "unknowns": 3 * a.size * a.size, "schedule": "at_output",
-            "parallelism": "single GPU" if world == 1 else "replicas x%d (one independent problem per GPU)" % world,
+                        "one Thallo_ProblemSolve per step" % (a.size, a.size * world, NIT, LIT),
+            "unknowns": 3 * a.size * a.size * world, "schedule": "at_output",
+            "parallelism": "single GPU" if world == 1 else
+                           "one %dx%d problem slab-partitioned along y over %d GPUs (%dx%d owned pixels each): halo rows over NVLink "
+                           "peer stores, PCG scalars over NCCL all-reduce; value = global PCG iterations/s x %d slabs"
+                           % (a.size, a.size * world, world, a.size, a.size, world),
             "l2": "working set 12 solver vectors x %.0f MB + inputs, larger than the 126 MB L2; no flush needed" % (12.0 * a.size * a.size / 1e6)}
 
 
@@ -173,7 +179,15 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     S = a.size
-    d = wl.image_warping_inputs(S, S)
+    d = wl.image_warping_inputs(S, S * world)
+    gloo = dist.new_group(backend="gloo") if world > 1 else None
+    part = None
+    if world > 1:
+        from thallo_b200.distributed import SlabSolver, slab_partition, local_slab, stencil_halo
+        halo = stencil_halo("image_warping", [S, S * world], "levenberg_marquardt")
+        part = slab_partition(S * world, world, halo)[rank]
+        for k in ("Offset", "Angle", "UrShape", "Constraints", "Mask"):
+            d[k] = local_slab(d[k], S, part)
     host = [torch.from_numpy(np.ascontiguousarray(d[k])).pin_memory() for k in ("Offset", "Angle", "UrShape", "Constraints", "Mask")]
     pristine = [h.cuda() for h in host]
     work = [p.clone() for p in pristine]
@@ -189,7 +203,10 @@ def main():
         torch.cuda.synchronize()
 
     def make(timing):
-        s = ThalloSolver([S, S], "image_warping", "levenberg_marquardt", timing=timing)
+        if world > 1:
+            s = SlabSolver([S, S * world], "image_warping", "levenberg_marquardt", rank, world, group=gloo, timing=timing)
+        else:
+            s = ThalloSolver([S, S], "image_warping", "levenberg_marquardt", timing=timing)
         s.set_parameters(nIterations=NIT, lIterations=LIT)
         return s
 
@@ -250,7 +267,7 @@ def main():
     ktotal = sum(v[1] for v in kern.values())
     dom = max(kern, key=lambda n: kern[n][1])
     peak, peak_src = peaks()
-    px = S * S
+    px = host[1].numel()       # pixels this rank's kernels sweep (owned + ghost rows)
     bpl = KERNEL_BYTES_PER_PX.get(dom, 0) * px
     avg_ms = kern[dom][1] / kern[dom][0]
     achieved = bpl / (avg_ms * 1e-3) / 1e9 if bpl else None
