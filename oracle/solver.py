@@ -44,6 +44,10 @@ class OracleSolver:
         self.p = dict(DEFAULTS)
         self.trace = []
         self.finalized = False
+        # test hook: force_lin[i] = number of PCG iterations to run in nonlinear iteration i instead of
+        # applying the zeta test (used to compare trajectories when a borderline zeta decision falls
+        # differently in float32 on the GPU; every zeta is recorded in the trace either way)
+        self.force_lin = None
 
     # ---- helpers
     def set(self, name, value):
@@ -155,6 +159,10 @@ class OracleSolver:
             return out
 
         nlin = 0
+        forced = None
+        if self.force_lin is not None and self.nIter < len(self.force_lin):
+            forced = int(self.force_lin[self.nIter])
+        it["zeta"] = []
         for l in range(int(P["lIterations"])):
             Ap = applyA(p)
             aD = self._dot(p, Ap)
@@ -182,6 +190,12 @@ class OracleSolver:
                     break
                 with np.errstate(divide="ignore", invalid="ignore"):
                     zeta = dt(l + 1) * (Q1 - Q0) / Q1
+                it["zeta"].append(float(zeta))
+                if forced is not None:
+                    if nlin >= forced:
+                        break
+                    Q0 = Q1
+                    continue
                 if not np.isfinite(zeta):
                     break
                 if zeta < dt(P["q_tolerance"]):

@@ -50,13 +50,67 @@ def gpu_trajectory(name, dims, kind, params, device_slots, dtype, nit, lit, **kw
 NOISE_FACTOR = 8.0
 
 
-def assert_costs_close(c, cref, tol, floor, cref64=None):
+def assert_costs_close(c, cref, tol, floor, cref64=None, perturbed=()):
+    """perturbed: float32 oracle trajectories of the same problem with the unknowns' initial values
+    moved by one ulp -- a direct measurement of how far float32 rounding alone moves the trajectory
+    (truncated PCG far from convergence amplifies rounding differences, and graph-domain sums are
+    order-dependent)."""
     assert len(c) == len(cref), (c, cref)
     noise = [0.0] * len(cref)
-    if cref64 is not None:
-        assert len(cref64) == len(cref), (cref, cref64)
-        rel = [abs(a - b) / max(abs(b), floor) for a, b in zip(cref, cref64)]
-        noise = [max(rel[max(0, i - 1):i + 2]) for i in range(len(rel))]
+    for other in ([cref64] if cref64 is not None else []) + list(perturbed):
+        if len(other) != len(cref):
+            continue
+        rel = [abs(a - b) / max(abs(b), floor) for a, b in zip(cref, other)]
+        noise = [max(n, max(rel[max(0, i - 1):i + 2])) for i, n in enumerate(noise)]
     for i, (a, b) in enumerate(zip(c, cref)):
         allowed = max(tol, NOISE_FACTOR * noise[i]) * max(abs(b), floor)
         assert abs(a - b) <= allowed, (i, a, b, allowed, c, cref)
+
+
+def oracle_run(make_oracle, params, nit, lit, force_lin=None):
+    o = make_oracle()
+    o.set("nIterations", nit); o.set("lIterations", lit)
+    o.force_lin = force_lin
+    o.init(params)
+    costs = [o.current_cost()]
+    while o.step(params):
+        costs.append(o.current_cost())
+    costs.append(o.current_cost())
+    return o, costs
+
+
+ZETA_MARGIN = 0.25
+
+
+def assert_lm_parity(c, lin, make_oracle, make_params, nit, lit, tol, floor, cref64=None, q_tolerance=1e-4):
+    """Cost trajectory and PCG iteration counts of an LM solve against the oracle.  BASELINE.json asks
+    for identical iteration counts "where convergence criteria fire identically": the zeta test
+    (gauss_newton.t:1666-1686) differences two nearly equal float32 sums, so its value carries
+    percent-level noise and a borderline decision can fall one iteration apart.  Where the GPU's
+    count differs from the oracle's, the oracle's own zeta at the earlier of the two exits must lie
+    within ZETA_MARGIN of q_tolerance (i.e. the decision was borderline), and the trajectory is then
+    compared against the oracle re-run with the GPU's iteration counts forced."""
+    o, cref = oracle_run(make_oracle, make_params(), nit, lit)
+    ref_lin = [it["n_lin"] for it in o.trace]
+    if lin != ref_lin[:len(lin)] or len(c) != len(cref):
+        o, cref = oracle_run(make_oracle, make_params(), nit, lit, force_lin=list(lin))
+        for i, it in enumerate(o.trace[:len(lin)]):
+            free = ref_lin[i] if i < len(ref_lin) else None
+            if free is None or free == lin[i]:
+                continue
+            first = min(free, lin[i])
+            z = it["zeta"][first - 1] if first - 1 < len(it["zeta"]) else float("nan")
+            # float32 noise of zeta = (l+1)(Q1-Q0)/Q1 grows with l: the Q's agree to ~1e-6 relative, their difference does not
+            assert abs(z - q_tolerance) <= ZETA_MARGIN * q_tolerance + first * 2e-5, \
+                "PCG iteration count differs (gpu %s, oracle %s) and zeta=%g at iteration %d is not borderline" % (lin, ref_lin, z, first)
+            break       # later iterations legitimately follow a different trajectory in the free-running oracle
+        cref64 = None
+    assert_costs_close(c, cref, tol, floor, cref64)
+    return o
+
+
+def ulp_perturbed(a, seed):
+    """float32 array moved by one ulp up or down per element (seeded)."""
+    a = np.asarray(a, np.float32)
+    sign = np.where(np.random.RandomState(seed).rand(*a.shape) < 0.5, -1.0, 1.0).astype(np.float32)
+    return np.nextafter(a, a + sign)

@@ -75,3 +75,47 @@ def test_optical_flow_at_output_matches_oracle():
     I, Ih, Ix, Iy = (rng.rand(n) for _ in range(4))
     params = [np.array([np.sqrt(10.0)]), np.array([np.sqrt(0.1)]), X, I, Ih, Ix, Iy]
     _check("optical_flow", [W, H], params)
+
+
+# ---- gather schedule (graph domains / materialised Jacobians): endpoint functions summed per unknown
+def _check_gather(name, dims, params, kw=None):
+    low = codegen.lower(energies.load(name), dims, "gauss_newton", name, True, "gather", **(kw or {}))
+    gen = low.generator
+    L, F, J = evaluate(energies.load(name), dims, params, np.float64, **(kw or {}))
+    p = np.random.RandomState(5).randn(J.shape[1])
+    o0 = J.T.tocsr() @ (J @ p)
+    for mat in (False, True):       # matrix-free endpoint functions, then the stored-value (materialised J) functions
+        out = interp.gather_apply(gen, params, p, materialised=mat)
+        assert np.abs(out - o0).max() <= 1e-10 * max(1.0, np.abs(o0).max()), mat
+    return low
+
+
+def test_arap_mesh_gather_matches_oracle():
+    nx, ny = 9, 7
+    d = wl.arap_mesh_inputs(nx, ny)
+    rng = np.random.RandomState(6)
+    d["Position"] = d["Position"] + 0.3 * rng.randn(*d["Position"].shape).astype(np.float32)
+    d["Angle"] = d["Angle"] + 0.4 * rng.randn(*d["Angle"].shape).astype(np.float32)
+    params = [np.asarray(p, np.float64) if np.asarray(p).dtype == np.float32 else p for p in wl.arap_mesh_params(d)]
+    low = _check_gather("arap_mesh_deformation", [nx * ny, len(d["V0"])], params)
+    assert low.desc["schedule"] == "gather" and len(low.desc["gather"]["sparse_endpoints"]) == 2
+
+
+def test_graph_laplacian_gather_matches_oracle():
+    X, A, v0, v1 = wl.minimal_graph_inputs(64)
+    _check_gather("graph_laplacian", [64, 63], [X.astype(np.float64) * 1.1, A.astype(np.float64), v0, v1])
+
+
+def test_bundle_adjustment_gather_matches_oracle():
+    d = wl.bundle_adjustment_inputs(6, 40, 4)
+    params = [np.asarray(p, np.float64) if np.asarray(p).dtype == np.float32 else p for p in wl.bundle_adjustment_params(d)]
+    low = _check_gather("bundle_adjustment", [6, 40, len(d["oToC"])], params)
+    g = low.desc["gather"]
+    assert g["groups"][0]["nnzp"] == 24 and low.desc["groups"][0]["materialize"] == 1
+
+
+def test_materialised_laplacian_gather_matches_oracle():
+    X, A = wl.minimal_inputs(13, 11)
+    low = _check_gather("laplacian", [13, 11], [X.astype(np.float64) * 1.3, A.astype(np.float64)],
+                        dict(variant="committed", materialize=True))
+    assert all(g["materialize"] for g in low.desc["groups"])

@@ -1,0 +1,260 @@
+// thallo_b200 solver skeleton, part 2: index helpers, accessors, the scatter sink, deterministic
+// reductions and the scalar helpers shared by the kernels.  Included after the generated
+// per-energy device functions (namespace th) and before the generated gather functions and
+// thallo_kernels.cuh.
+#pragma once
+
+#define TH_BLOCK 256
+
+// ------------------------------------------------------------------ index helpers
+template <class Dom> struct ThIdx {
+    int c[TH_MAXD];
+    long long lin;
+    __device__ __forceinline__ bool from_linear(long long l) {
+        lin = l;
+        const long long n = Dom::D0 * Dom::D1 * Dom::D2;
+        if (l >= n) return false;
+        c[0] = (int)(l % Dom::D0);
+        c[1] = (int)((l / Dom::D0) % Dom::D1);
+        c[2] = (int)(l / (Dom::D0 * Dom::D1));
+        return true;
+    }
+    __device__ __forceinline__ bool from_coords(int x, int y, int z) {
+        c[0] = x; c[1] = y; c[2] = z;
+        lin = x + Dom::D0 * (y + Dom::D1 * (long long)z);
+        return x < Dom::D0 && y < Dom::D1 && z < Dom::D2;
+    }
+};
+
+// Unknownwise launch geometry: 1-D 256, 2-D 32x8, 3-D 8x8x4 threads per block
+// (the reference uses 256 / 16x16 / 8x8x4, util.t:715-725; 32-wide rows coalesce better).
+template <class Dom> __device__ __forceinline__ bool th_uw_index(ThIdx<Dom>& i) {
+    if (Dom::ND == 1) return i.from_linear((long long)blockIdx.x * blockDim.x + threadIdx.x);
+    return i.from_coords(blockIdx.x * blockDim.x + threadIdx.x, blockIdx.y * blockDim.y + threadIdx.y,
+                         blockIdx.z * blockDim.z + threadIdx.z);
+}
+
+// ------------------------------------------------------------------ global-memory accessor
+// Bounds-checked loads return 0 out of bounds (thallo.t:876-882); `vec` reads the
+// unknown-shaped vector argument (P / Delta).
+template <class Dom> struct GAcc {
+    ThIdx<Dom> i;
+    const real* __restrict__ v;
+    __device__ __forceinline__ GAcc(const ThIdx<Dom>& idx, const real* vec) : i(idx), v(vec) {}
+
+    template <int D> __device__ __forceinline__ int coord() const { return i.c[D]; }
+
+    template <int L0, int H0, int L1, int H1, int L2, int H2> __device__ __forceinline__ bool inb() const {
+        bool ok = true;
+        if (L0 < 0) ok = ok && (i.c[0] + L0 >= 0);
+        if (H0 > 0) ok = ok && (i.c[0] + H0 < Dom::D0);
+        if (Dom::ND > 1) {
+            if (L1 < 0) ok = ok && (i.c[1] + L1 >= 0);
+            if (H1 > 0) ok = ok && (i.c[1] + H1 < Dom::D1);
+        }
+        if (Dom::ND > 2) {
+            if (L2 < 0) ok = ok && (i.c[2] + L2 >= 0);
+            if (H2 > 0) ok = ok && (i.c[2] + H2 < Dom::D2);
+        }
+        return ok;
+    }
+    template <int O0, int O1, int O2> __device__ __forceinline__ long long elem() const {
+        return i.lin + O0 + Dom::D0 * (O1 + Dom::D1 * (long long)O2);
+    }
+    template <int SLOT, class CT, int C, int CH, int O0, int O1, int O2>
+    __device__ __forceinline__ real img(const Params& P) const {
+        if ((O0 | O1 | O2) != 0) { if (!inb<O0, O0, O1, O1, O2, O2>()) return (real)0; }
+        return ThLoad<CT, C, CH>::ld(P.ptr[SLOT], elem<O0, O1, O2>());
+    }
+    template <int K, int CH, int O0, int O1, int O2> __device__ __forceinline__ real vec() const {
+        if ((O0 | O1 | O2) != 0) { if (!inb<O0, O0, O1, O1, O2, O2>()) return (real)0; }
+        return ThLoad<real, TH_UIMG[K].channels, CH>::ld(v + TH_UIMG[K].offset, elem<O0, O1, O2>());
+    }
+    template <int K, int CH, int O0, int O1, int O2> __device__ __forceinline__ long long ucol() const {
+        if ((O0 | O1 | O2) != 0) { if (!inb<O0, O0, O1, O1, O2, O2>()) return -1; }
+        return TH_UIMG[K].offset + elem<O0, O1, O2>() * TH_UIMG[K].channels + CH;
+    }
+    // sparse (graph) accesses: the index array lives in ptr slot SP and is indexed by this element
+    template <int SP> __device__ __forceinline__ long long sidx(const Params& P) const {
+        return (long long)__ldg(((const int*)P.ptr[SP]) + i.lin);
+    }
+    template <int SLOT, class CT, int C, int CH, int SP> __device__ __forceinline__ real simg(const Params& P) const {
+        return ThLoad<CT, C, CH>::ld(P.ptr[SLOT], sidx<SP>(P));
+    }
+    template <int K, int CH, int SP> __device__ __forceinline__ real svec(const Params& P) const {
+        return ThLoad<real, TH_UIMG[K].channels, CH>::ld(v + TH_UIMG[K].offset, sidx<SP>(P));
+    }
+    template <int K, int CH, int SP> __device__ __forceinline__ long long sucol(const Params& P) const {
+        return TH_UIMG[K].offset + sidx<SP>(P) * TH_UIMG[K].channels + CH;
+    }
+    // bilinear sample, floor/ceil lerp with zero outside (thallo.t:899-907)
+    template <int SLOT> __device__ __forceinline__ real samp(const Params& P, real x, real y) const {
+        const real* im = (const real*)P.ptr[SLOT];
+        const int x0 = (int)th_floor(x), x1 = (int)th_ceil(x);
+        const int y0 = (int)th_floor(y), y1 = (int)th_ceil(y);
+        const real xn = x - (real)x0, yn = y - (real)y0;
+        auto get = [&](int xx, int yy) -> real {
+            return (xx >= 0 && xx < Dom::D0 && yy >= 0 && yy < Dom::D1) ? __ldg(im + xx + Dom::D0 * (long long)yy) : (real)0;
+        };
+        const real u = ((real)1 - xn) * get(x0, y0) + xn * get(x1, y0);
+        const real b = ((real)1 - xn) * get(x0, y1) + xn * get(x1, y1);
+        return ((real)1 - yn) * u + yn * b;
+    }
+};
+
+// ------------------------------------------------------------------ scatter sink (atomics)
+// WHICH selects the target vector (0: r / Ap / Adelta, 1: preconditioner diagonal);
+// out-of-bounds targets are dropped (thallo.t:3355-3390).
+template <class Dom> struct GScatter {
+    ThIdx<Dom> i;
+    real* t0; real* t1;
+    __device__ __forceinline__ GScatter(const ThIdx<Dom>& idx, real* a, real* b) : i(idx), t0(a), t1(b) {}
+    template <int WHICH, int K, int CH, int O0, int O1, int O2> __device__ __forceinline__ void add(real val) {
+        const int x = i.c[0] + O0, y = i.c[1] + O1, z = i.c[2] + O2;
+        bool ok = x >= 0 && x < Dom::D0;
+        if (Dom::ND > 1) ok = ok && y >= 0 && y < Dom::D1;
+        if (Dom::ND > 2) ok = ok && z >= 0 && z < Dom::D2;
+        if (!ok) return;
+        const long long e = i.lin + O0 + Dom::D0 * (O1 + Dom::D1 * (long long)O2);
+        atomicAdd((WHICH ? t1 : t0) + TH_UIMG[K].offset + e * TH_UIMG[K].channels + CH, val);
+    }
+    template <int WHICH, int K, int CH, int SP> __device__ __forceinline__ void sadd(const Params& P, real val) {
+        const long long e = (long long)__ldg(((const int*)P.ptr[SP]) + i.lin);
+        atomicAdd((WHICH ? t1 : t0) + TH_UIMG[K].offset + e * TH_UIMG[K].channels + CH, val);
+    }
+};
+
+// ------------------------------------------------------------------ deterministic block/grid reduction
+__device__ __forceinline__ double th_warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Every thread of every block calls this with K per-thread values.  partials holds
+// K * gridsize doubles.  Returns true (in all threads of exactly one block, the last to
+// arrive) with tot[k] = sum over blocks in block order.
+template <int K> __device__ __forceinline__ bool th_grid_reduce(double (&val)[K], double (&tot)[K], double* partials,
+                                                               unsigned int* ticket) {
+    __shared__ double sm[K][32];
+    __shared__ bool last;
+    const int tid = threadIdx.x + blockDim.x * (threadIdx.y + blockDim.y * threadIdx.z);
+    const int nthreads = blockDim.x * blockDim.y * blockDim.z;
+    const int lane = tid & 31, warp = tid >> 5, nwarps = (nthreads + 31) >> 5;
+    const unsigned int nblocks = gridDim.x * gridDim.y * gridDim.z;
+    const unsigned int bid = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        const double w = th_warp_sum(val[k]);
+        if (lane == 0) sm[k][warp] = w;
+    }
+    __syncthreads();
+    if (warp == 0) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            double w = lane < nwarps ? sm[k][lane] : 0.0;
+            w = th_warp_sum(w);
+            if (lane == 0) partials[(size_t)k * nblocks + bid] = w;
+        }
+    }
+    if (tid == 0) {
+        __threadfence();
+        const unsigned int t = atomicAdd(ticket, 1u);
+        last = (t == nblocks - 1);
+    }
+    __syncthreads();
+    if (!last) return false;
+    __threadfence();
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        double s = 0.0;
+        for (unsigned int b = tid; b < nblocks; b += nthreads) s += __ldcg(partials + (size_t)k * nblocks + b);
+        s = th_warp_sum(s);
+        __syncthreads();
+        if (lane == 0) sm[k][warp] = s;
+        __syncthreads();
+        double w = lane < nwarps ? sm[k][lane] : 0.0;
+        w = th_warp_sum(w);
+        tot[k] = __shfl_sync(0xffffffffu, w, 0);
+    }
+    if (tid == 0) *ticket = 0u;
+    return true;
+}
+
+__device__ __forceinline__ real th_guarded_invert(real d) {     // GuardedInvertType.CERES, gauss_newton.t:641-648
+    const real s = (real)1 + th_sqrt(d);
+    return (real)1 / (s * s);
+}
+
+__device__ __forceinline__ real th_alpha(const ThScalars* S) {   // safeDivideIfNotLM, gauss_newton.t:226-234
+    const real num = (real)S->rz[S->it & 1], den = (real)S->aD;
+#if TH_LM
+    return num / den;
+#else
+    return den != (real)0 ? num / den : (real)0;
+#endif
+}
+__device__ __forceinline__ real th_beta(const ThScalars* S) {
+    const real num = (real)S->rz[(S->it + 1) & 1], den = (real)S->rz[S->it & 1];
+#if TH_LM
+    return num / den;
+#else
+    return den != (real)0 ? num / den : (real)0;
+#endif
+}
+
+// beta as seen by th_pcg_a of iteration `it` (> 0): the previous iteration has been closed, so the
+// newest numerator sits in rz[it&1] and the one before in rz[(it+1)&1].
+__device__ __forceinline__ real th_beta_prev(const ThScalars* S) {
+    const real num = (real)S->rz[S->it & 1], den = (real)S->rz[(S->it + 1) & 1];
+#if TH_LM
+    return num / den;
+#else
+    return den != (real)0 ? num / den : (real)0;
+#endif
+}
+
+// Shared tail of both PCGInit forms: given the gradient entry g (=J^T F) and the true
+// diagonal d (=diag J^T J) of one unknown scalar, produce r, preconditioner, p (and in LM
+// CtC, b, SSq) and return r*p.
+__device__ __forceinline__ real th_init_scalar(const Params& P, const Vecs& V, long long off, real g, real d,
+                                               real pre_if_off, int first_nonlinear) {
+    const real r = -g;
+    real pre = TH_USEPRE ? th_guarded_invert(d) : pre_if_off;
+#if TH_LM
+    real ssq = pre;
+    if (first_nonlinear) V.SSq[off] = pre; else ssq = V.SSq[off];
+    const real radius = P.trust_region_radius;
+    const real ctc_raw = d / radius;
+    const real mult = ((real)1 / ssq) / radius;
+    const real ctc = th_fmin(th_fmax(ctc_raw, P.min_lm_diagonal * mult), P.max_lm_diagonal * mult);
+    pre = (real)1 / (ctc + radius * ctc_raw);
+    V.CtC[off] = ctc;
+    V.b[off] = r;
+#endif
+    const real p = pre * r;
+    V.delta[off] = (real)0;
+    V.r[off] = r;
+    V.pre[off] = pre;
+#if TH_TILED
+    V.z[off] = p;      // the first th_pcg_a of the linear solve takes p := z (beta = 0)
+#else
+    V.p[off] = p;
+#endif
+    return r * p;
+}
+__device__ __forceinline__ void th_zero_scalar(const Vecs& V, long long off) {
+    V.delta[off] = (real)0; V.r[off] = (real)0; V.pre[off] = (real)0; V.p[off] = (real)0;
+    V.z[off] = (real)0; V.Ap[off] = (real)0;
+#if TH_TILED
+    V.p2[off] = (real)0;
+#endif
+#if TH_LM
+    V.CtC[off] = (real)0; V.b[off] = (real)0; V.Adelta[off] = (real)0;
+#endif
+}
+__device__ __forceinline__ void th_begin_linear(ThScalars* S, double rz0) {
+    S->rz[0] = rz0; S->rz[1] = 0.0; S->aD = 0.0; S->q = 0.0; S->Q0 = 0.0;
+    S->it = 0; S->done = 0; S->lin_done = 0;
+}
+

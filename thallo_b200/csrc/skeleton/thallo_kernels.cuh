@@ -22,260 +22,7 @@
 // finish sums the partials in a fixed order (deterministic), replacing the reference's
 // one float atomic per warp (util.t:39-50, cuda_util.t:430-449) and its per-iteration memsets.
 #pragma once
-
-#define TH_BLOCK 256
-
-// ------------------------------------------------------------------ index helpers
-template <class Dom> struct ThIdx {
-    int c[TH_MAXD];
-    long long lin;
-    __device__ __forceinline__ bool from_linear(long long l) {
-        lin = l;
-        const long long n = Dom::D0 * Dom::D1 * Dom::D2;
-        if (l >= n) return false;
-        c[0] = (int)(l % Dom::D0);
-        c[1] = (int)((l / Dom::D0) % Dom::D1);
-        c[2] = (int)(l / (Dom::D0 * Dom::D1));
-        return true;
-    }
-    __device__ __forceinline__ bool from_coords(int x, int y, int z) {
-        c[0] = x; c[1] = y; c[2] = z;
-        lin = x + Dom::D0 * (y + Dom::D1 * (long long)z);
-        return x < Dom::D0 && y < Dom::D1 && z < Dom::D2;
-    }
-};
-
-// Unknownwise launch geometry: 1-D 256, 2-D 32x8, 3-D 8x8x4 threads per block
-// (the reference uses 256 / 16x16 / 8x8x4, util.t:715-725; 32-wide rows coalesce better).
-template <class Dom> __device__ __forceinline__ bool th_uw_index(ThIdx<Dom>& i) {
-    if (Dom::ND == 1) return i.from_linear((long long)blockIdx.x * blockDim.x + threadIdx.x);
-    return i.from_coords(blockIdx.x * blockDim.x + threadIdx.x, blockIdx.y * blockDim.y + threadIdx.y,
-                         blockIdx.z * blockDim.z + threadIdx.z);
-}
-
-// ------------------------------------------------------------------ global-memory accessor
-// Bounds-checked loads return 0 out of bounds (thallo.t:876-882); `vec` reads the
-// unknown-shaped vector argument (P / Delta).
-template <class Dom> struct GAcc {
-    ThIdx<Dom> i;
-    const real* __restrict__ v;
-    __device__ __forceinline__ GAcc(const ThIdx<Dom>& idx, const real* vec) : i(idx), v(vec) {}
-
-    template <int D> __device__ __forceinline__ int coord() const { return i.c[D]; }
-
-    template <int L0, int H0, int L1, int H1, int L2, int H2> __device__ __forceinline__ bool inb() const {
-        bool ok = true;
-        if (L0 < 0) ok = ok && (i.c[0] + L0 >= 0);
-        if (H0 > 0) ok = ok && (i.c[0] + H0 < Dom::D0);
-        if (Dom::ND > 1) {
-            if (L1 < 0) ok = ok && (i.c[1] + L1 >= 0);
-            if (H1 > 0) ok = ok && (i.c[1] + H1 < Dom::D1);
-        }
-        if (Dom::ND > 2) {
-            if (L2 < 0) ok = ok && (i.c[2] + L2 >= 0);
-            if (H2 > 0) ok = ok && (i.c[2] + H2 < Dom::D2);
-        }
-        return ok;
-    }
-    template <int O0, int O1, int O2> __device__ __forceinline__ long long elem() const {
-        return i.lin + O0 + Dom::D0 * (O1 + Dom::D1 * (long long)O2);
-    }
-    template <int SLOT, class CT, int C, int CH, int O0, int O1, int O2>
-    __device__ __forceinline__ real img(const Params& P) const {
-        if ((O0 | O1 | O2) != 0) { if (!inb<O0, O0, O1, O1, O2, O2>()) return (real)0; }
-        return ThLoad<CT, C, CH>::ld(P.ptr[SLOT], elem<O0, O1, O2>());
-    }
-    template <int K, int CH, int O0, int O1, int O2> __device__ __forceinline__ real vec() const {
-        if ((O0 | O1 | O2) != 0) { if (!inb<O0, O0, O1, O1, O2, O2>()) return (real)0; }
-        return ThLoad<real, TH_UIMG[K].channels, CH>::ld(v + TH_UIMG[K].offset, elem<O0, O1, O2>());
-    }
-    template <int K, int CH, int O0, int O1, int O2> __device__ __forceinline__ long long ucol() const {
-        if ((O0 | O1 | O2) != 0) { if (!inb<O0, O0, O1, O1, O2, O2>()) return -1; }
-        return TH_UIMG[K].offset + elem<O0, O1, O2>() * TH_UIMG[K].channels + CH;
-    }
-    // sparse (graph) accesses: the index array lives in ptr slot SP and is indexed by this element
-    template <int SP> __device__ __forceinline__ long long sidx(const Params& P) const {
-        return (long long)__ldg(((const int*)P.ptr[SP]) + i.lin);
-    }
-    template <int SLOT, class CT, int C, int CH, int SP> __device__ __forceinline__ real simg(const Params& P) const {
-        return ThLoad<CT, C, CH>::ld(P.ptr[SLOT], sidx<SP>(P));
-    }
-    template <int K, int CH, int SP> __device__ __forceinline__ real svec(const Params& P) const {
-        return ThLoad<real, TH_UIMG[K].channels, CH>::ld(v + TH_UIMG[K].offset, sidx<SP>(P));
-    }
-    template <int K, int CH, int SP> __device__ __forceinline__ long long sucol(const Params& P) const {
-        return TH_UIMG[K].offset + sidx<SP>(P) * TH_UIMG[K].channels + CH;
-    }
-    // bilinear sample, floor/ceil lerp with zero outside (thallo.t:899-907)
-    template <int SLOT> __device__ __forceinline__ real samp(const Params& P, real x, real y) const {
-        const real* im = (const real*)P.ptr[SLOT];
-        const int x0 = (int)th_floor(x), x1 = (int)th_ceil(x);
-        const int y0 = (int)th_floor(y), y1 = (int)th_ceil(y);
-        const real xn = x - (real)x0, yn = y - (real)y0;
-        auto get = [&](int xx, int yy) -> real {
-            return (xx >= 0 && xx < Dom::D0 && yy >= 0 && yy < Dom::D1) ? __ldg(im + xx + Dom::D0 * (long long)yy) : (real)0;
-        };
-        const real u = ((real)1 - xn) * get(x0, y0) + xn * get(x1, y0);
-        const real b = ((real)1 - xn) * get(x0, y1) + xn * get(x1, y1);
-        return ((real)1 - yn) * u + yn * b;
-    }
-};
-
-// ------------------------------------------------------------------ scatter sink (atomics)
-// WHICH selects the target vector (0: r / Ap / Adelta, 1: preconditioner diagonal);
-// out-of-bounds targets are dropped (thallo.t:3355-3390).
-template <class Dom> struct GScatter {
-    ThIdx<Dom> i;
-    real* t0; real* t1;
-    __device__ __forceinline__ GScatter(const ThIdx<Dom>& idx, real* a, real* b) : i(idx), t0(a), t1(b) {}
-    template <int WHICH, int K, int CH, int O0, int O1, int O2> __device__ __forceinline__ void add(real val) {
-        const int x = i.c[0] + O0, y = i.c[1] + O1, z = i.c[2] + O2;
-        bool ok = x >= 0 && x < Dom::D0;
-        if (Dom::ND > 1) ok = ok && y >= 0 && y < Dom::D1;
-        if (Dom::ND > 2) ok = ok && z >= 0 && z < Dom::D2;
-        if (!ok) return;
-        const long long e = i.lin + O0 + Dom::D0 * (O1 + Dom::D1 * (long long)O2);
-        atomicAdd((WHICH ? t1 : t0) + TH_UIMG[K].offset + e * TH_UIMG[K].channels + CH, val);
-    }
-    template <int WHICH, int K, int CH, int SP> __device__ __forceinline__ void sadd(const Params& P, real val) {
-        const long long e = (long long)__ldg(((const int*)P.ptr[SP]) + i.lin);
-        atomicAdd((WHICH ? t1 : t0) + TH_UIMG[K].offset + e * TH_UIMG[K].channels + CH, val);
-    }
-};
-
-// ------------------------------------------------------------------ deterministic block/grid reduction
-__device__ __forceinline__ double th_warp_sum(double v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
-    return v;
-}
-
-// Every thread of every block calls this with K per-thread values.  partials holds
-// K * gridsize doubles.  Returns true (in all threads of exactly one block, the last to
-// arrive) with tot[k] = sum over blocks in block order.
-template <int K> __device__ __forceinline__ bool th_grid_reduce(double (&val)[K], double (&tot)[K], double* partials,
-                                                               unsigned int* ticket) {
-    __shared__ double sm[K][32];
-    __shared__ bool last;
-    const int tid = threadIdx.x + blockDim.x * (threadIdx.y + blockDim.y * threadIdx.z);
-    const int nthreads = blockDim.x * blockDim.y * blockDim.z;
-    const int lane = tid & 31, warp = tid >> 5, nwarps = (nthreads + 31) >> 5;
-    const unsigned int nblocks = gridDim.x * gridDim.y * gridDim.z;
-    const unsigned int bid = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
-#pragma unroll
-    for (int k = 0; k < K; ++k) {
-        const double w = th_warp_sum(val[k]);
-        if (lane == 0) sm[k][warp] = w;
-    }
-    __syncthreads();
-    if (warp == 0) {
-#pragma unroll
-        for (int k = 0; k < K; ++k) {
-            double w = lane < nwarps ? sm[k][lane] : 0.0;
-            w = th_warp_sum(w);
-            if (lane == 0) partials[(size_t)k * nblocks + bid] = w;
-        }
-    }
-    if (tid == 0) {
-        __threadfence();
-        const unsigned int t = atomicAdd(ticket, 1u);
-        last = (t == nblocks - 1);
-    }
-    __syncthreads();
-    if (!last) return false;
-    __threadfence();
-#pragma unroll
-    for (int k = 0; k < K; ++k) {
-        double s = 0.0;
-        for (unsigned int b = tid; b < nblocks; b += nthreads) s += __ldcg(partials + (size_t)k * nblocks + b);
-        s = th_warp_sum(s);
-        __syncthreads();
-        if (lane == 0) sm[k][warp] = s;
-        __syncthreads();
-        double w = lane < nwarps ? sm[k][lane] : 0.0;
-        w = th_warp_sum(w);
-        tot[k] = __shfl_sync(0xffffffffu, w, 0);
-    }
-    if (tid == 0) *ticket = 0u;
-    return true;
-}
-
-__device__ __forceinline__ real th_guarded_invert(real d) {     // GuardedInvertType.CERES, gauss_newton.t:641-648
-    const real s = (real)1 + th_sqrt(d);
-    return (real)1 / (s * s);
-}
-
-__device__ __forceinline__ real th_alpha(const ThScalars* S) {   // safeDivideIfNotLM, gauss_newton.t:226-234
-    const real num = (real)S->rz[S->it & 1], den = (real)S->aD;
-#if TH_LM
-    return num / den;
-#else
-    return den != (real)0 ? num / den : (real)0;
-#endif
-}
-__device__ __forceinline__ real th_beta(const ThScalars* S) {
-    const real num = (real)S->rz[(S->it + 1) & 1], den = (real)S->rz[S->it & 1];
-#if TH_LM
-    return num / den;
-#else
-    return den != (real)0 ? num / den : (real)0;
-#endif
-}
-
-// beta as seen by th_pcg_a of iteration `it` (> 0): the previous iteration has been closed, so the
-// newest numerator sits in rz[it&1] and the one before in rz[(it+1)&1].
-__device__ __forceinline__ real th_beta_prev(const ThScalars* S) {
-    const real num = (real)S->rz[S->it & 1], den = (real)S->rz[(S->it + 1) & 1];
-#if TH_LM
-    return num / den;
-#else
-    return den != (real)0 ? num / den : (real)0;
-#endif
-}
-
-// Shared tail of both PCGInit forms: given the gradient entry g (=J^T F) and the true
-// diagonal d (=diag J^T J) of one unknown scalar, produce r, preconditioner, p (and in LM
-// CtC, b, SSq) and return r*p.
-__device__ __forceinline__ real th_init_scalar(const Params& P, const Vecs& V, long long off, real g, real d,
-                                               real pre_if_off, int first_nonlinear) {
-    const real r = -g;
-    real pre = TH_USEPRE ? th_guarded_invert(d) : pre_if_off;
-#if TH_LM
-    real ssq = pre;
-    if (first_nonlinear) V.SSq[off] = pre; else ssq = V.SSq[off];
-    const real radius = P.trust_region_radius;
-    const real ctc_raw = d / radius;
-    const real mult = ((real)1 / ssq) / radius;
-    const real ctc = th_fmin(th_fmax(ctc_raw, P.min_lm_diagonal * mult), P.max_lm_diagonal * mult);
-    pre = (real)1 / (ctc + radius * ctc_raw);
-    V.CtC[off] = ctc;
-    V.b[off] = r;
-#endif
-    const real p = pre * r;
-    V.delta[off] = (real)0;
-    V.r[off] = r;
-    V.pre[off] = pre;
-#if TH_TILED
-    V.z[off] = p;      // the first th_pcg_a of the linear solve takes p := z (beta = 0)
-#else
-    V.p[off] = p;
-#endif
-    return r * p;
-}
-__device__ __forceinline__ void th_zero_scalar(const Vecs& V, long long off) {
-    V.delta[off] = (real)0; V.r[off] = (real)0; V.pre[off] = (real)0; V.p[off] = (real)0;
-    V.z[off] = (real)0; V.Ap[off] = (real)0;
-#if TH_TILED
-    V.p2[off] = (real)0;
-#endif
-#if TH_LM
-    V.CtC[off] = (real)0; V.b[off] = (real)0; V.Adelta[off] = (real)0;
-#endif
-}
-__device__ __forceinline__ void th_begin_linear(ThScalars* S, double rz0) {
-    S->rz[0] = rz0; S->rz[1] = 0.0; S->aD = 0.0; S->q = 0.0; S->Q0 = 0.0;
-    S->it = 0; S->done = 0; S->lin_done = 0;
-}
+#include "thallo_access.cuh"
 
 // ================================================================== at-output (unknownwise) kernels
 #if TH_AT_OUTPUT
@@ -350,11 +97,6 @@ th_step1_uw(const __grid_constant__ Params P, const __grid_constant__ Vecs V, Th
 // ================================================================== flat vector kernels
 // Excluded unknowns hold zeros in every solver vector (written by the init kernels), so
 // these streaming kernels need no mask: 0 stays 0 and contributes 0 to every dot product.
-#if TH_DOUBLE
-typedef double4 real4;
-#else
-typedef float4 real4;
-#endif
 
 // current search direction: the tiled schedule ping-pongs p between V.p and V.p2 (iteration `it`
 // reads buffer it&1 and writes buffer (it+1)&1, see th_pcg_a); the other schedules keep V.p.
@@ -985,6 +727,137 @@ th_step1_finish(const __grid_constant__ Params P, const __grid_constant__ Vecs V
         if (threadIdx.x == 0) S->aD = tot[0];
     }
 }
+
+// ================================================================== gather schedule (graph domains, materialised J)
+#if TH_GATHER
+__device__ constexpr ThSpace TH_SPACE[TH_NSPACES] = TH_SPACE_TABLE;
+__device__ constexpr ThSlot TH_SLOT[TH_NSPACES][TH_MAXSLOTS] = TH_SLOT_TABLE;
+__device__ constexpr int TH_NNZP[TH_NGROUPS] = TH_GROUP_NNZP;
+
+__device__ __forceinline__ real th_warp_sum_real(real v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Operator of one index space: Ap[n] = sum over the residual elements incident to unknown element
+// n of (their partials at n) * (J p of that residual) [+ CtC p in LM], and <p, Ap>.  Replaces the
+// clear of Ap + PCGStep1 residualwise (gauss_newton.t:1006-1016) + PCGStep1_Finish (:774-799), and
+// for materialised groups the second (transposed) csrmv of cusparseJTJMatVec (:1497-1510).
+// One thread per unknown element, or one warp when many residuals meet at an element
+// (TH_SPACE[].lanes == 32, e.g. the cameras of bundle adjustment).  which = 1: Adelta = A delta.
+#define TH_GATHER_KERNEL(SP)                                                                                        \
+    extern "C" __global__ void __launch_bounds__(TH_BLOCK)                                                          \
+    th_gather_s##SP(const __grid_constant__ Params P, const __grid_constant__ Vecs V,                               \
+                    const __grid_constant__ ThGather G, ThScalars* S, double* partials, int which, int first) {     \
+        if (S->done) return;                                                                                        \
+        constexpr int LANES = TH_SPACE[SP].lanes;                                                                   \
+        constexpr int NS = TH_SPACE[SP].nslots;                                                                     \
+        const long long gt = (long long)blockIdx.x * blockDim.x + threadIdx.x;                                      \
+        const int lane = (int)(threadIdx.x % LANES);                                                                \
+        const real* __restrict__ in = which ? V.delta : V.p;                                                        \
+        real* __restrict__ out = which ? V.Adelta : V.Ap;                                                           \
+        double acc1[1] = {0.0};                                                                                     \
+        ThIdx<th::dom_s##SP> t;                                                                                     \
+        if (t.from_linear(gt / LANES)) {                                                                            \
+            GAcc<th::dom_s##SP> ta(t, nullptr);                                                                     \
+            const bool ex = th::exclude_s##SP(ta, P);                                                               \
+            real acc[NS];                                                                                           \
+            _Pragma("unroll") for (int j = 0; j < NS; ++j) acc[j] = (real)0;                                        \
+            if (!ex) {                                                                                              \
+                if (which) th::gather_s##SP<1, LANES>(t, lane, P, G, in, acc);                                      \
+                else th::gather_s##SP<0, LANES>(t, lane, P, G, in, acc);                                            \
+            }                                                                                                       \
+            if (LANES > 1) { _Pragma("unroll") for (int j = 0; j < NS; ++j) acc[j] = th_warp_sum_real(acc[j]); }    \
+            if (lane == 0) {                                                                                        \
+                real dot = (real)0;                                                                                 \
+                _Pragma("unroll") for (int j = 0; j < NS; ++j) {                                                    \
+                    const int k = TH_SLOT[SP][j].image;                                                             \
+                    const long long off = TH_UIMG[k].offset + t.lin * TH_UIMG[k].channels + TH_SLOT[SP][j].channel; \
+                    if (ex) { out[off] = (real)0; continue; }                                                       \
+                    const real pv = in[off];                                                                        \
+                    real val = acc[j];                                                                              \
+                    if (TH_LM) val += V.CtC[off] * pv;                                                              \
+                    out[off] = val;                                                                                 \
+                    dot += pv * val;                                                                                \
+                }                                                                                                   \
+                acc1[0] = (double)dot;                                                                              \
+            }                                                                                                       \
+        }                                                                                                           \
+        if (which) return;                                                                                          \
+        double tot[1];                                                                                              \
+        if (th_grid_reduce<1>(acc1, tot, partials, &S->ticket[1])) {                                                \
+            if (threadIdx.x == 0) S->aD = (first ? 0.0 : S->aD) + tot[0];                                           \
+        }                                                                                                           \
+    }
+TH_SPACE_LIST(TH_GATHER_KERNEL)
+
+// Materialised Jacobian of one residual group (sparse_materialize schedules): the partial
+// derivatives are stored once per nonlinear iteration (precomputeJ, gauss_newton.t:1019-1025; no
+// sort / transpose as in cusparseOuter :1332-1446 -- the column structure is the caller's index
+// arrays), and every PCG iteration forms J p per residual row from the stored values (the first
+// csrmv of cusparseJTJMatVec, :1478-1490).
+#define TH_MAT_KERNELS(G_)                                                                                          \
+    extern "C" __global__ void __launch_bounds__(TH_BLOCK)                                                          \
+    th_computejv_g##G_(const __grid_constant__ Params P, const __grid_constant__ ThGather G) {                      \
+        ThIdx<th::dom_g##G_> idx;                                                                                   \
+        if (idx.from_linear((long long)blockIdx.x * blockDim.x + threadIdx.x)) {                                    \
+            GAcc<th::dom_g##G_> a(idx, nullptr);                                                                    \
+            real jv[TH_NNZP[G_]];                                                                                   \
+            th::computeJv_g##G_(a, P, jv);                                                                          \
+            real4* __restrict__ dst = (real4*)(G.jvals[G_] + idx.lin * TH_NNZP[G_]);                                \
+            _Pragma("unroll") for (int i = 0; i < TH_NNZP[G_] / 4; ++i) {                                           \
+                real4 q; q.x = jv[4 * i]; q.y = jv[4 * i + 1]; q.z = jv[4 * i + 2]; q.w = jv[4 * i + 3];            \
+                dst[i] = q;                                                                                         \
+            }                                                                                                       \
+        }                                                                                                           \
+    }                                                                                                               \
+    extern "C" __global__ void __launch_bounds__(TH_BLOCK)                                                          \
+    th_matj_g##G_(const __grid_constant__ Params P, const __grid_constant__ Vecs V,                                 \
+                  const __grid_constant__ ThGather G, const ThScalars* S) {                                         \
+        if (S->done) return;                                                                                        \
+        ThIdx<th::dom_g##G_> idx;                                                                                   \
+        if (idx.from_linear((long long)blockIdx.x * blockDim.x + threadIdx.x)) {                                    \
+            GAcc<th::dom_g##G_> a(idx, V.p);                                                                        \
+            real jpv[TH_GROUPS[G_].nterms];                                                                         \
+            th::matJ_g##G_(a, P, G.jvals[G_] + idx.lin * TH_NNZP[G_], jpv);                                         \
+            _Pragma("unroll") for (int t = 0; t < TH_GROUPS[G_].nterms; ++t)                                        \
+                G.jp[G_][idx.lin * TH_GROUPS[G_].nterms + t] = jpv[t];                                              \
+        }                                                                                                           \
+    }
+TH_MAT_LIST(TH_MAT_KERNELS)
+
+// Hoisted per-element invariants of one index space (transcendentals of a single unknown element, e.g.
+// sin/cos of a vertex's angles): evaluated once per nonlinear iteration into the plan-owned image
+// __coef_s<i>, which the endpoint functions read through their own index.
+__device__ constexpr int TH_SCOEF_CH[TH_NSPACES] = TH_SCOEF_N;
+__device__ constexpr int TH_SCOEF_PTR[TH_NSPACES] = TH_SCOEF_SLOT;
+#define TH_SCOEF_KERNEL(SP)                                                                                         \
+    extern "C" __global__ void __launch_bounds__(TH_BLOCK)                                                          \
+    th_precompute_scoef_s##SP(const __grid_constant__ Params P) {                                                   \
+        ThIdx<th::dom_s##SP> idx;                                                                                   \
+        if (idx.from_linear((long long)blockIdx.x * blockDim.x + threadIdx.x)) {                                    \
+            GAcc<th::dom_s##SP> a(idx, nullptr);                                                                    \
+            real c[TH_SCOEF_CH[SP]];                                                                                \
+            th::scoef_s##SP(a, P, c);                                                                               \
+            real* __restrict__ out = (real*)P.ptr[TH_SCOEF_PTR[SP]];                                                \
+            _Pragma("unroll") for (int i = 0; i < TH_SCOEF_CH[SP]; ++i) out[idx.lin * TH_SCOEF_CH[SP] + i] = c[i];  \
+        }                                                                                                           \
+    }
+TH_SCOEF_LIST(TH_SCOEF_KERNEL)
+
+// 64-bit position-weighted checksum of an index array: lets the plan notice that a caller changed
+// the contents of a sparse index array between solves (the adjacency lists are then rebuilt)
+extern "C" __global__ void __launch_bounds__(TH_BLOCK)
+th_index_checksum(const int* __restrict__ a, long long n, unsigned long long* out) {
+    unsigned long long h = 0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        h += ((unsigned long long)(unsigned int)__ldg(a + i) + 0x9E3779B97F4A7C15ull) * (2ull * (unsigned long long)i + 1ull);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) h += __shfl_down_sync(0xffffffffu, h, o);
+    if ((threadIdx.x & 31) == 0) atomicAdd(out, h);
+}
+#endif  // TH_GATHER
 
 // ================================================================== per-residual-group kernels
 #define TH_GROUP_KERNELS(G)                                                                                         \

@@ -12,6 +12,20 @@ typedef double real;
 #else
 typedef float real;
 #endif
+#if TH_DOUBLE
+typedef double4 real4;
+#else
+typedef float4 real4;
+#endif
+// read-only 4-scalar chunk c of a 16-byte aligned array
+__device__ __forceinline__ real4 th_ld4(const real* p, int c) {
+#if TH_DOUBLE
+    const double2 a = __ldg(((const double2*)p) + 2 * c), b = __ldg(((const double2*)p) + 2 * c + 1);
+    return make_double4(a.x, a.y, b.x, b.y);
+#else
+    return __ldg(((const float4*)p) + c);
+#endif
+}
 typedef real th_real;
 typedef float th_float;
 typedef unsigned char th_uchar;
@@ -68,6 +82,25 @@ struct ThGroup { int ndim; int dim[TH_MAXD]; int nterms; int nnz; };
 __device__ constexpr ThUImg TH_UIMG[TH_NUM_UIMG] = TH_UIMG_TABLE;
 __device__ constexpr ThGroup TH_GROUPS[TH_NGROUPS] = TH_GROUP_TABLE;
 __device__ constexpr long long TH_DIMS[TH_NDIMS] = TH_DIM_SIZES;
+
+// ---- gather schedule (graph domains / materialised Jacobians): per sparse endpoint the residual
+// elements incident to every unknown element, as CSR offsets + a permutation (nullptr when the
+// index array is already sorted, i.e. the identity), built by the plan from the caller's index
+// arrays; per residual group the stored partial derivatives (TH_GROUP_NNZP scalars per element,
+// endpoint-major) and J p per residual row.
+#ifndef TH_GATHER
+#define TH_GATHER 0
+#endif
+#if TH_GATHER
+struct ThGather {
+    const int* ptr[TH_NEP_S > 0 ? TH_NEP_S : 1];
+    const int* perm[TH_NEP_S > 0 ? TH_NEP_S : 1];
+    real* jvals[TH_NGROUPS];
+    real* jp[TH_NGROUPS];
+};
+struct ThSpace { int nslots; int lanes; long long elements; };
+struct ThSlot { int image; int channel; };
+#endif
 
 // ---- multi-GPU slab partition: the plan is compiled for the rank-local extent of the
 // slowest axis INCLUDING TH_GHOST_LO / TH_GHOST_HI ghost layers that belong to the neighbouring

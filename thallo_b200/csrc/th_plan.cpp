@@ -41,7 +41,11 @@ bool parse_descriptor(const std::string& text, PlanDesc& d, std::string& err) {
         else if (key == "lm") { int v; ls >> v; d.lm = v != 0; }
         else if (key == "real") { std::string v; ls >> v; d.is_double = (v == "double"); }
         else if (key == "usepreconditioner") { int v; ls >> v; d.usepre = v != 0; }
-        else if (key == "schedule") { ls >> d.schedule; d.at_output = (d.schedule == "at_output"); }
+        else if (key == "schedule") { ls >> d.schedule; d.at_output = (d.schedule == "at_output"); d.gather = (d.schedule == "gather"); }
+        else if (key == "space") { SpaceDesc sp; ls >> sp.elements >> sp.lanes >> sp.nslots; d.spaces.push_back(sp); }
+        else if (key == "sep") { SparseEndpointDesc e; ls >> e.sid >> e.group >> e.slot >> e.count >> e.targets; d.seps.push_back(e); }
+        else if (key == "scoef") { SpaceCoefDesc c; ls >> c.space >> c.slot >> c.channels; d.scoefs.push_back(c); }
+        else if (key == "gmat") { int gi; GroupMatDesc g; ls >> gi >> g.nnzp >> g.nterms; d.gmats.push_back(g); }
         else if (key == "dims") { int n; ls >> n; d.dims.resize(n); for (auto& x : d.dims) ls >> x; }
         else if (key == "nunk") ls >> d.nunk;
         else if (key == "ptrs") { int n; ls >> n; d.ptr_pidx.resize(n); for (auto& x : d.ptr_pidx) ls >> x; }
@@ -254,7 +258,28 @@ Plan::Plan(const StateOptions* opts, const PlanDesc& desc, const std::string& so
         if (d_.tiled) maxblocks = std::max<long long>(maxblocks, (long long)sms * 32);   // persistent grid <= SMs x resident CTAs
     }
     for (auto& g : d_.groups) maxblocks = std::max(maxblocks, (g.count + 255) / 256);
+    for (auto& sp : d_.spaces) maxblocks = std::max(maxblocks, (sp.elements * sp.lanes + 255) / 256);
     CD(cudaMalloc((void**)&d_partials_, sizeof(double) * 2 * (size_t)maxblocks));
+    if (d_.gather) {
+        adj_.resize(d_.seps.size());
+        jvals_.assign(d_.groups.size(), nullptr);
+        jp_.assign(d_.groups.size(), nullptr);
+        for (size_t g = 0; g < d_.groups.size(); ++g) {
+            if (!d_.groups[g].materialize) continue;
+            CD(cudaMalloc(&jvals_[g], (size_t)d_.groups[g].count * d_.gmats[g].nnzp * real_size_));
+            CD(cudaMalloc(&jp_[g], (size_t)d_.groups[g].count * d_.gmats[g].nterms * real_size_));
+        }
+        scoef_.assign(d_.spaces.size(), nullptr);
+        for (auto& c : d_.scoefs)
+            CD(cudaMalloc(&scoef_[c.space], (size_t)d_.spaces[c.space].elements * c.channels * real_size_));
+        CD(cudaMalloc((void**)&d_checksum_, 8));
+        const size_t ns = std::max<size_t>(1, d_.seps.size());
+        gather_buf_.assign(8 * (2 * ns + 2 * d_.groups.size()), 0);
+        for (size_t g = 0; g < d_.groups.size(); ++g) {
+            memcpy(gather_buf_.data() + 8 * (2 * ns + g), &jvals_[g], 8);
+            memcpy(gather_buf_.data() + 8 * (2 * ns + d_.groups.size() + g), &jp_[g], 8);
+        }
+    }
 
     // kernel-argument images of the device structs
     const size_t nptr = std::max<size_t>(1, d_.ptr_pidx.size()), nsc = std::max<size_t>(1, d_.scalars.size());
@@ -341,6 +366,11 @@ void Plan::build_vector_maps() {
 Plan::~Plan() {
     for (int i = 0; i < 2; ++i) if (peer_[i]) cudaIpcCloseMemHandle(peer_[i]);
     if (comm_) nccl().CommDestroy(comm_);
+    for (auto& a : adj_) { if (a.ptr) cudaFree(a.ptr); if (a.perm) cudaFree(a.perm); }
+    for (void* q : jvals_) if (q) cudaFree(q);
+    for (void* q : jp_) if (q) cudaFree(q);
+    for (void* q : scoef_) if (q) cudaFree(q);
+    if (d_checksum_) cudaFree(d_checksum_);
     if (vec_block_) cudaFree(vec_block_);
     if (coef_) cudaFree(coef_);
     if (d_scalars_) cudaFree(d_scalars_);
@@ -417,12 +447,96 @@ void Plan::launch_group(CUfunction f, int g, void** args) {
 }
 void Plan::clear(void* p) { CD(cudaMemsetAsync(p, 0, (size_t)d_.nunk * real_size_, stream())); }
 
+// ------------------------------------------------------------------ gather schedule: adjacency lists
+// For every sparse endpoint (residual group g reaching an unknown index space through index array
+// I): the residual elements e grouped by target I[e], as CSR offsets + a stable permutation.  Built
+// on the host from one copy of the index array (counting sort), when the caller's pointer changes
+// or (checked at every Thallo_ProblemInit with a device-side checksum) its contents do.  An index
+// array that is already sorted -- e.g. the reference's own per-vertex edge lists,
+// examples/shared/ThalloGraph.h:67-79 -- needs no permutation.
+void Plan::build_adjacency(bool verify_contents) {
+    const size_t ns = std::max<size_t>(1, d_.seps.size());
+    for (size_t i = 0; i < d_.seps.size(); ++i) {
+        const SparseEndpointDesc& e = d_.seps[i];
+        Adjacency& a = adj_[e.sid];
+        const void* src = nullptr;
+        memcpy(&src, params_buf_.data() + 8 * e.slot, 8);
+        // contents are what matter: a caller that passes a copy of the same index array keeps the lists
+        bool rebuild = !a.valid;
+        unsigned long long sum = a.checksum;
+        if (!a.valid || a.src != src || verify_contents) {
+            CD(cudaMemsetAsync(d_checksum_, 0, 8, stream()));
+            long long n = e.count;
+            void* args[] = {&src, &n, &d_checksum_};
+            launch(fn("th_index_checksum"), dim3((unsigned)std::min<long long>((n + 255) / 256, (long long)sms_ * 8)), dim3(256), args);
+            CD(cudaMemcpyAsync(&sum, d_checksum_, 8, cudaMemcpyDeviceToHost, stream()));
+            CD(cudaStreamSynchronize(stream()));
+            rebuild = rebuild || sum != a.checksum;
+            a.src = src;
+        }
+        if (!rebuild) continue;
+        std::vector<int> idx((size_t)e.count);
+        CD(cudaMemcpyAsync(idx.data(), src, sizeof(int) * (size_t)e.count, cudaMemcpyDeviceToHost, stream()));
+        CD(cudaStreamSynchronize(stream()));
+        std::vector<int> ptr((size_t)e.targets + 1, 0), perm((size_t)e.count);
+        for (long long k = 0; k < e.count; ++k) {
+            if (idx[k] < 0 || idx[k] >= e.targets) {
+                fprintf(stderr, "thallo_b200: sparse index %d out of range [0, %lld) at element %lld\n", idx[k], e.targets, k);
+                exit(1);
+            }
+            ++ptr[(size_t)idx[k] + 1];
+        }
+        for (long long t = 0; t < e.targets; ++t) ptr[t + 1] += ptr[t];
+        std::vector<int> cur(ptr.begin(), ptr.end() - 1);
+        bool identity = true;
+        for (long long k = 0; k < e.count; ++k) {
+            const int pos = cur[idx[k]]++;
+            perm[pos] = (int)k;
+            identity = identity && pos == k;
+        }
+        if (!a.ptr) CD(cudaMalloc((void**)&a.ptr, sizeof(int) * ((size_t)e.targets + 1)));
+        CD(cudaMemcpyAsync(a.ptr, ptr.data(), sizeof(int) * ptr.size(), cudaMemcpyHostToDevice, stream()));
+        if (identity) { if (a.perm) { cudaFree(a.perm); a.perm = nullptr; } }
+        else {
+            if (!a.perm) CD(cudaMalloc((void**)&a.perm, sizeof(int) * (size_t)e.count));
+            CD(cudaMemcpyAsync(a.perm, perm.data(), sizeof(int) * perm.size(), cudaMemcpyHostToDevice, stream()));
+        }
+        CD(cudaStreamSynchronize(stream()));
+        a.src = src; a.checksum = sum; a.valid = true;
+        log("adjacency of sparse endpoint %d: %lld residuals -> %lld unknown elements%s\n", e.sid, e.count, e.targets, identity ? " (sorted, no permutation)" : "");
+    }
+    for (size_t i = 0; i < d_.seps.size(); ++i) {
+        const Adjacency& a = adj_[i];
+        memcpy(gather_buf_.data() + 8 * i, &a.ptr, 8);
+        memcpy(gather_buf_.data() + 8 * (ns + i), &a.perm, 8);
+    }
+}
+// Ap (which = 0) or Adelta (which = 1) in the gather schedule: J p of the materialised groups, then one kernel per index space
+void Plan::launch_gather(int which) {
+    void* P = params_buf_.data();
+    void* V = vecs_buf_.data();
+    void* G = gather_buf_.data();
+    if (!which)
+        for (size_t g = 0; g < d_.groups.size(); ++g) {
+            if (!d_.groups[g].materialize) continue;
+            void* a[] = {P, V, G, &d_scalars_};
+            launch_group(fn("th_matj_g" + std::to_string(g)), (int)g, a);
+        }
+    for (size_t s = 0; s < d_.spaces.size(); ++s) {
+        int first = s == 0;
+        void* a[] = {P, V, G, &d_scalars_, &d_partials_, &which, &first};
+        const long long threads = d_.spaces[s].elements * d_.spaces[s].lanes;
+        launch(fn("th_gather_s" + std::to_string(s)), dim3((unsigned)((threads + 255) / 256)), dim3(256), a);
+    }
+}
+
 // util.initParameters, util.t:609-643: images / sparse = device pointers, scalars read through host pointers
 void Plan::bind(void** params) {
     char* buf = params_buf_.data();
     const size_t nptr = std::max<size_t>(1, d_.ptr_pidx.size()), nsc = std::max<size_t>(1, d_.scalars.size());
     for (size_t i = 0; i < d_.ptr_pidx.size(); ++i) {
-        if (d_.ptr_pidx[i] < 0) memcpy(buf + 8 * i, &coef_, 8);          // plan-owned coefficient image
+        if (d_.ptr_pidx[i] < -1) memcpy(buf + 8 * i, &scoef_[-(d_.ptr_pidx[i] + 2)], 8);   // plan-owned per-space coefficient image
+        else if (d_.ptr_pidx[i] < 0) memcpy(buf + 8 * i, &coef_, 8);          // plan-owned coefficient image
         else memcpy(buf + 8 * i, &params[d_.ptr_pidx[i]], 8);
     }
     if (d_.tiled) {
@@ -454,6 +568,7 @@ void Plan::bind(void** params) {
     }
     (void)nsc;
     write_lm_params();
+    if (d_.gather) build_adjacency(false);
 }
 void Plan::write_lm_params() {
     const size_t nptr = std::max<size_t>(1, d_.ptr_pidx.size()), nsc = std::max<size_t>(1, d_.scalars.size());
@@ -536,6 +651,7 @@ void Plan::init(void** params) {
     radius_ = round_real(sp_.trust_region_radius);
     decrease_factor_ = round_real(sp_.radius_decrease_factor);
     bind(params);
+    if (d_.gather) build_adjacency(true);
     // solver vectors start from zero so that excluded unknowns stay zero everywhere
     CD(cudaMemsetAsync(vec_block_, 0, vec_stride_ * 10, stream()));
     CD(cudaMemsetAsync(vecs_[V_P2], 0, vec_stride_, stream()));
@@ -586,6 +702,8 @@ void Plan::linear_iteration(int l) {
     } else if (d_.at_output) {
         void* a[] = {P, V, &d_scalars_, &d_partials_, &zero};
         launch_uw(fn("th_step1_uw"), a);
+    } else if (d_.gather) {
+        launch_gather(0);
     } else {
         clear(vecs_[V_AP]);
         for (size_t g = 0; g < d_.groups.size(); ++g) {
@@ -612,6 +730,8 @@ void Plan::linear_iteration(int l) {
         } else if (d_.at_output) {
             void* a[] = {P, V, &d_scalars_, &d_partials_, &one};
             launch_uw(fn("th_step1_uw"), a);
+        } else if (d_.gather) {
+            launch_gather(1);        // materialised groups contribute nothing to A*delta (gauss_newton.t:1058-1065: no applyJTJ exists for them)
         } else {
             clear(vecs_[V_ADELTA]);
             for (size_t g = 0; g < d_.groups.size(); ++g) {
@@ -656,6 +776,10 @@ int Plan::step(void** params) {
         void* a[] = {P};
         launch_uw(fn("th_precompute_coef"), a);
     }
+    for (auto& c : d_.scoefs) {   // gather schedule: per-element invariants of each index space
+        void* a[] = {P};
+        launch(fn("th_precompute_scoef_s" + std::to_string(c.space)), dim3((unsigned)((d_.spaces[c.space].elements + 255) / 256)), dim3(256), a);
+    }
     if (d_.at_output) {
         void* a[] = {P, V, &d_scalars_, &d_partials_, &first};
         launch_uw(fn("th_init_uw"), a);
@@ -672,6 +796,12 @@ int Plan::step(void** params) {
         }
         void* a[] = {P, V, &d_scalars_, &d_partials_, &first};
         launch_flat(fn("th_init_finish"), a);
+        if (d_.gather)          // precomputeJ (gauss_newton.t:1019-1025, cusparseOuter :1332): store the partial derivatives
+            for (size_t g = 0; g < d_.groups.size(); ++g) {
+                if (!d_.groups[g].materialize) continue;
+                void* aj[] = {P, gather_buf_.data()};
+                launch_group(fn("th_computejv_g" + std::to_string(g)), (int)g, aj);
+            }
     }
     span_end(cur_phase_, ev_setup_);
     span_begin(cur_phase_);

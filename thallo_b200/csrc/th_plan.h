@@ -20,9 +20,19 @@ struct ScalarDesc { int pidx; std::string ctype; };
 struct VTileDesc { int roww = 0, zoff = 0, poff = 0, bytes = 0, padl = 0, coff = -1, croww = 0, cbytes = 0; };
 struct StageDesc { int slot = 0; std::string ctype; int es = 4, channels = 1, roww = 0, off = 0, bytes = 0, padl = 0, center = 0; };
 
+struct SpaceDesc { long long elements = 0; int lanes = 1, nslots = 0; };
+struct SparseEndpointDesc { int sid = 0, group = 0, slot = 0; long long count = 0, targets = 0; };
+struct GroupMatDesc { int nnzp = 0, nterms = 0; };
+struct SpaceCoefDesc { int space = 0, slot = 0, channels = 0; };
+
 struct PlanDesc {
     std::string name, kind, schedule;
-    bool lm = false, is_double = false, usepre = false, at_output = false;
+    bool lm = false, is_double = false, usepre = false, at_output = false, gather = false;
+    // gather schedule ("space" / "sep" / "gmat" lines): index spaces of the unknowns, sparse endpoints, stored-J layout
+    std::vector<SpaceDesc> spaces;
+    std::vector<SparseEndpointDesc> seps;
+    std::vector<GroupMatDesc> gmats;
+    std::vector<SpaceCoefDesc> scoefs;      // plan-owned per-space coefficient images ("scoef" lines; ptr_pidx = -(2 + space))
     std::vector<long long> dims;
     long long nunk = 0;
     std::vector<int> ptr_pidx;
@@ -148,6 +158,15 @@ private:
     void allreduce(size_t scalars_offset, int count);
     void halo_push(int vec, int check_done);
     void* dscalar(size_t off) const { return (char*)d_scalars_ + off; }
+    // gather schedule state: adjacency lists of the sparse endpoints (rebuilt when the caller's index array
+    // changes), stored partial derivatives and J p of the materialised groups
+    struct Adjacency { const void* src = nullptr; unsigned long long checksum = 0; bool valid = false; int* ptr = nullptr; int* perm = nullptr; };
+    std::vector<Adjacency> adj_;
+    std::vector<void*> jvals_, jp_, scoef_;
+    std::vector<char> gather_buf_;          // host image of the device struct ThGather
+    unsigned long long* d_checksum_ = nullptr;
+    void build_adjacency(bool verify_contents);
+    void launch_gather(int which);
     unsigned tiled_grid_[2] = {1, 1};   // persistent grid of th_pcg_a_ld / th_pcg_a
     unsigned tiled_smem_[2] = {0, 0};
     int sms_ = 148;

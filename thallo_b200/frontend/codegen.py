@@ -21,10 +21,27 @@ arguments are read: global memory with bounds checks, or TMA-staged shared-memor
 tiles) and a scatter sink `S` (how contributions are accumulated), both supplied
 by the hand-written skeleton in csrc/skeleton/.
 """
+from collections import namedtuple
+
 from . import ad
 from .dsl import ImageAccess, Bounds, IndexValue, Param, VecArg
 
 MAXD = 3
+
+# variables of the materialised-Jacobian functions: stored partial derivative i of the current
+# residual element, and (J p) of its term t
+# (namedtuples compare as plain tuples and expression nodes are hash-consed on their key, so every
+# key type carries a distinguishing tag)
+_JVal = namedtuple("JVal", "tag i")
+_JpVal = namedtuple("JpVal", "tag t")
+
+
+def JVal(i):
+    return _JVal("jval", i)
+
+
+def JpVal(t):
+    return _JpVal("jpval", t)
 
 
 class Lowered:
@@ -199,10 +216,15 @@ class Generator:
         can_at_output = (len(udoms) == 1 and all((not g["sparse"]) and g["domain"] == next(iter(udoms))
                                                  for g in self.groups)
                          and not any(g["materialize"] for g in self.groups))
+        self._find_endpoints()
         if schedule == "auto":
-            schedule = "at_output" if can_at_output else "residualwise"
+            schedule = "at_output" if can_at_output else ("gather" if self.can_gather else "residualwise")
         if schedule == "at_output":
             assert can_at_output, "compute_at_output needs every residual domain to equal the unknown domain"
+        if schedule == "residualwise":
+            assert not any(g["materialize"] for g in self.groups), "materialised Jacobians need the gather schedule"
+        if schedule == "gather":
+            assert self.can_gather, "the gather schedule needs every unknown access to be a sparse index or a dense offset of the residual's own domain"
         self.schedule = schedule
         self.udomain = next(iter(udoms)) if len(udoms) == 1 else None
         # tiled form of the unknownwise operator (shared-memory stencil tiles, TMA-staged): 2-D / 3-D image domains
@@ -257,6 +279,10 @@ class Generator:
             return "(real)(a.template coord<%d>() + (%d))" % (dom.index(k.dim), k.off)
         if isinstance(k, Param):
             return "P.sc[%d]" % self.sc_slot[k.name]
+        if isinstance(k, _JVal):
+            return "jq%d.%s" % (k.i // 4, "xyzw"[k.i % 4])
+        if isinstance(k, _JpVal):
+            return "jpv[%d]" % k.t
         raise NotImplementedError(k)
 
     def _fn(self, sig, roots, outs, dom, pre_lines=()):
@@ -513,6 +539,292 @@ class Generator:
                         cur[pos] = max(cur[pos], abs(c[2]))
         return dict(img=img, vec=vec)
 
+    # ---- gather schedule (graph domains, materialised Jacobians): index spaces and endpoints
+    # The reference applies J^T J residual by residual and scatters with float atomics into a
+    # cleared Ap (createapplyjtjResidualwise thallo.t:3536-3569, PCGStep1 gauss_newton.t:1006-1016,
+    # then PCGStep1_Finish :774-799).  Here the operator is applied unknown by unknown: every
+    # distinct way a residual group reaches an unknown element (an "endpoint": through a sparse
+    # index array, or at a dense offset of the group's own domain) gets a function that returns
+    # that residual element's contribution to the unknowns at that endpoint, and one kernel per
+    # index space walks the residual elements incident to each unknown element (adjacency lists
+    # built by the plan from the index arrays) and sums them in registers: no atomics, no clear
+    # of Ap, no finishing pass, deterministic.  Groups with a materialised Jacobian read their
+    # stored partial derivatives instead of re-evaluating them (CSR SpMV / SpMV^T role,
+    # gauss_newton.t:1448-1525, without storing column indices: they are implied by the index arrays).
+    def _find_endpoints(self):
+        spaces, space_of = [], {}
+        for im in self.unknowns:
+            dom = tuple(d.idx for d in im.dims)
+            if dom not in space_of:
+                space_of[dom] = len(spaces)
+                spaces.append(dict(dims=dom, images=[], slots={}, nslots=0, endpoints=[]))
+            sp = spaces[space_of[dom]]
+            sp["images"].append(im)
+            for ch in range(im.channels):
+                sp["slots"][(im.name, ch)] = sp["nslots"]
+                sp["nslots"] += 1
+        self.spaces, self.space_of = spaces, space_of
+        self.endpoints = []
+        self.can_gather = True
+        for gi, g in enumerate(self.groups):
+            dom = tuple(g["domain"])
+            seen = {}
+            for ti, t in enumerate(g["terms"]):
+                for u, p in zip(t.unknowns, t.partials):
+                    index = u.key.index
+                    if index not in seen:
+                        first = index[0]
+                        if first[0] == "s":
+                            ok = len(dom) == 1 and first[2] == dom[0] and first[3] == 0
+                            tdom = tuple(d.idx for d in self.images[u.key.image].dims)
+                            ep = dict(kind="sparse", sparse=first[1], off=[0] * MAXD)
+                        else:
+                            tdom = tuple(c[1] for c in index)
+                            ok = tdom == dom and len(dom) <= MAXD
+                            ep = dict(kind="dense", sparse=None, off=self._offs(index, dom) if ok else [0] * MAXD)
+                        if not ok or tdom not in space_of:
+                            self.can_gather = False
+                            return
+                        ep.update(group=gi, index=index, space=space_of[tdom], parts=[], id=len(self.endpoints))
+                        seen[index] = ep
+                        self.endpoints.append(ep)
+                        spaces[ep["space"]]["endpoints"].append(ep)
+                    seen[index]["parts"].append((ti, u, p))
+        sid = 0
+        for ep in self.endpoints:               # sparse endpoints own an adjacency list (ThGather.ptr / .perm)
+            ep["sid"] = -1
+            if ep["kind"] == "sparse":
+                ep["sid"] = sid
+                sid += 1
+        self.n_sparse_ep = sid
+
+    # ---- hoisting for the gather schedule: sub-expressions rooted at a transcendental whose image
+    # reads all go through ONE index (the same sparse index array, or the residual's own element)
+    # depend on a single element of an unknown index space and not on the PCG iteration: they are
+    # evaluated once per nonlinear iteration into a plan-owned coefficient image over that space
+    # ("__coef_s<i>") and fetched through the same index (arap_mesh: sin/cos of the three angles of
+    # v0, evaluated by the reference 12 times per vertex in every PCG iteration).
+    def _single_index(self, e, memo):
+        """("none",) no image reads below e; ("ix", index) all image reads use `index`; ("bad",) otherwise."""
+        r = memo.get(e.id)
+        if r is not None:
+            return r
+        if e.kind == "const":
+            r = ("none",)
+        elif e.kind == "var":
+            k = e.key
+            if isinstance(k, ImageAccess):
+                ix = k.index
+                if ix[0][0] == "s":
+                    ok = ix[0][3] == 0
+                else:
+                    ok = all(c[2] == 0 for c in ix) and tuple(c[1] for c in ix) in self.space_of
+                r = ("ix", ix) if ok and not k.image.startswith("__") else ("bad",)
+            elif isinstance(k, Param):
+                r = ("none",)
+            else:
+                r = ("bad",)
+        else:
+            r = ("none",)
+            for a in e.args:
+                ra = self._single_index(a, memo)
+                if ra[0] == "bad" or (ra[0] == "ix" and r[0] == "ix" and ra[1] != r[1]):
+                    r = ("bad",)
+                    break
+                if ra[0] == "ix":
+                    r = ra
+            if e.op == "sample":
+                r = ("bad",)
+        memo[e.id] = r
+        return r
+
+    def _space_of_index(self, ix, e):
+        if ix[0][0] == "s":
+            ims = ad.variables(e, lambda v: isinstance(v.key, ImageAccess))
+            dom = tuple(d.idx for d in self.images[ims[0].key.image].dims)
+        else:
+            dom = tuple(c[1] for c in ix)
+        return self.space_of.get(dom), dom
+
+    def _hoist_gather(self, e, memo, pmemo):
+        if e.id in memo:
+            return memo[e.id]
+        r = e
+        if e.kind == "apply":
+            st = self._single_index(e, pmemo)
+            if st[0] == "ix" and e.op in self._EXPENSIVE and e.type == ad.REAL and self._space_of_index(st[1], e)[0] is not None:
+                si, dom = self._space_of_index(st[1], e)
+                dense = tuple(("d", d, 0) for d in dom)
+                # the defining expression, rewritten to read the space's own element
+                base = ad.substitute(e, lambda v: ad.var(v.key._replace(index=dense), v.type) if isinstance(v.key, ImageAccess) else v)
+                lst = self.scoef[si]
+                ch = self._scoef_index[si].get(base.id)
+                if ch is None:
+                    ch = len(lst)
+                    self._scoef_index[si][base.id] = ch
+                    lst.append(base)
+                r = ad.var(ImageAccess("__coef_s%d" % si, st[1], ch))
+            else:
+                r = ad.rebuild(e, [self._hoist_gather(a, memo, pmemo) for a in e.args])
+        memo[e.id] = r
+        return r
+
+    def _value_layout(self, gi):
+        """Storage order of a materialised group's partial derivatives within one residual element:
+        endpoint-major (each endpoint's transposed product reads one contiguous run), then
+        term-major, padded to a multiple of four scalars for 128-bit loads."""
+        pos, i = {}, 0
+        for ep in self.endpoints:
+            if ep["group"] != gi:
+                continue
+            for (ti, u, p) in ep["parts"]:
+                pos[(ti, u.key)] = i
+                i += 1
+        return pos, i, -(-i // 4) * 4
+
+    def _prepare_gather(self):
+        """Value layouts of the materialised groups, the endpoint expressions, and hoisting of their
+        per-element invariants into plan-owned coefficient images; must run before the header is emitted."""
+        L = self.L
+        zero = ad.const(0.0)
+        for gi, g in enumerate(self.groups):
+            g["vpos"], g["nnz_stored"], g["nnzp"] = self._value_layout(gi)
+        self.scoef = [[] for _ in self.spaces]
+        self._scoef_index = [{} for _ in self.spaces]
+        hmemo, pmemo = {}, {}
+        for ep in self.endpoints:
+            g = self.groups[ep["group"]]
+            sp = self.spaces[ep["space"]]
+            acc, jp = {}, {}
+            for (ti, u, p) in ep["parts"]:
+                if ti not in jp:
+                    jp[ti] = g["terms"][ti].jp("P")
+                j = sp["slots"][(u.key.image, u.key.channel)]
+                acc[j] = acc.get(j, zero) + p * jp[ti]
+            if self.hoist_enabled and not g["materialize"]:
+                acc = dict((j, self._hoist_gather(x, hmemo, pmemo)) for j, x in acc.items())
+            ep["roots"] = acc
+        from .dsl import Image
+        for si, sp in enumerate(self.spaces):       # plan-owned coefficient images (must exist before any function is emitted)
+            if self.scoef[si]:
+                nm = "__coef_s%d" % si
+                self.images[nm] = Image(nm, "real", len(self.scoef[si]), [L.dims[d] for d in sp["dims"]], -(2 + si), "plan")
+                self.ptr_slot[nm] = len(self.ptr_pidx)
+                self.ptr_pidx.append(-(2 + si))
+
+    def gen_gather(self):
+        L = self.L
+        src = []
+        zero = ad.const(0.0)
+
+        def jq_lines(roots):
+            used = sorted(set(v.key.i // 4 for e in roots for v in ad.variables(e, lambda v: isinstance(v.key, _JVal))))
+            return ["const real4 jq%d = th_ld4(jv, %d);" % (c, c) for c in used]
+        # per materialised group: store the partial derivatives; J p per residual row
+        for gi, g in enumerate(self.groups):
+            if not g["materialize"]:
+                continue
+            dom = g["domain"]
+            vals = [zero] * g["nnzp"]
+            for ti, t in enumerate(g["terms"]):
+                for u, p in zip(t.unknowns, t.partials):
+                    vals[g["vpos"][(ti, u.key)]] = p
+            src.append(self._fn(
+                "template <class A> __device__ __forceinline__ void computeJv_g%d(const A& a, const Params& P, real* __restrict__ jv)" % gi,
+                vals, lambda r: ["jv[%d] = %s;" % (i, x) for i, x in enumerate(r)], dom))
+            rows = []
+            for ti, t in enumerate(g["terms"]):
+                r = zero
+                for u, p in zip(t.unknowns, t.partials):
+                    k = u.key
+                    r = r + ad.var(JVal(g["vpos"][(ti, k)])) * ad.var(VecArg("P", k.image, k.index, k.channel))
+                rows.append(r)
+            g["jv_roots"], g["matj_roots"] = vals, rows        # kept for the NumPy interpreter (frontend/interp.py)
+            src.append(self._fn(
+                "template <class A> __device__ __forceinline__ void matJ_g%d(const A& a, const Params& P, const real* __restrict__ jv, real* __restrict__ jpv)" % gi,
+                rows, lambda r: ["jpv[%d] = %s;" % (i, x) for i, x in enumerate(r)], dom, jq_lines(rows)))
+        # per endpoint: contribution of one residual element to the unknowns at that endpoint
+        for si, sp in enumerate(self.spaces):
+            if self.scoef[si]:
+                nc = len(self.scoef[si])
+                src.append(self._fn(
+                    "template <class A> __device__ __forceinline__ void scoef_s%d(const A& a, const Params& P, real* __restrict__ out)" % si,
+                    list(self.scoef[si]), lambda r, nc=nc: ["out[%d] = %s;" % (i, r[i]) for i in range(nc)], sp["dims"]))
+        for ep in self.endpoints:
+            g = self.groups[ep["group"]]
+            sp = self.spaces[ep["space"]]
+            dom = g["domain"]
+            acc = ep["roots"]
+            js = sorted(acc)
+            src.append(self._fn(
+                "template <class A> __device__ __forceinline__ void jtj_ep%d(const A& a, const Params& P, real* __restrict__ acc)" % ep["id"],
+                [acc[j] for j in js], lambda r, js=js: ["acc[%d] += %s;" % (j, x) for j, x in zip(js, r)], dom))
+            if g["materialize"]:
+                macc = {}
+                for (ti, u, p) in ep["parts"]:
+                    j = sp["slots"][(u.key.image, u.key.channel)]
+                    macc[j] = macc.get(j, zero) + ad.var(JVal(g["vpos"][(ti, u.key)])) * ad.var(JpVal(ti))
+                roots = [macc[j] for j in js]
+                ep["mat_roots"] = dict(zip(js, roots))
+                src.append(self._fn(
+                    "__device__ __forceinline__ void jt_ep%d(const real* __restrict__ jv, const real* __restrict__ jpv, real* __restrict__ acc)" % ep["id"],
+                    roots, lambda r, js=js: ["acc[%d] += %s;" % (j, x) for j, x in zip(js, r)], dom, jq_lines(roots)))
+        # per index space: walk the residual elements incident to one unknown element
+        part_a, src = "\n".join(src), []
+        for si, sp in enumerate(self.spaces):
+            elements = _prod(L.dims[d].size for d in sp["dims"])
+            deg = 0.0
+            for ep in sp["endpoints"]:
+                if ep["kind"] == "sparse":
+                    deg += _prod(L.dims[d].size for d in self.groups[ep["group"]]["domain"]) / float(elements)
+            sp["elements"] = elements
+            sp["lanes"] = 32 if deg >= 64.0 else 1          # many residuals per unknown: one warp per unknown element
+            body = []
+            for ep in sp["endpoints"]:
+                gi = ep["group"]
+                g = self.groups[gi]
+                mat = bool(g["materialize"])
+                call_free = "jtj_ep%d(a, P, acc);" % ep["id"]
+                call_mat = ("jt_ep%d(G.jvals[%d] + e * %d, G.jp[%d] + e * %d, acc);" % (ep["id"], gi, g["nnzp"], gi, len(g["terms"])))
+                if ep["kind"] == "sparse":
+                    sid = ep["sid"]
+                    body.append("{   // endpoint %d: group %s through %s" % (ep["id"], g["name"], ep["sparse"]))
+                    if mat:
+                        body.append("    if (WHICH == 0) {")      # A*delta of the LM reset skips materialised groups (gauss_newton.t:1058-1065)
+                    body.append("    const int lo = __ldg(G.ptr[%d] + t.lin), hi = __ldg(G.ptr[%d] + t.lin + 1);" % (sid, sid))
+                    body.append("    const int* __restrict__ perm = G.perm[%d];" % sid)
+                    body.append("    for (int i = lo + lane; i < hi; i += LANES) {")
+                    body.append("        const long long e = perm ? (long long)__ldg(perm + i) : (long long)i;")
+                    if mat:
+                        body.append("        " + call_mat)
+                    else:
+                        body.append("        ThIdx<dom_g%d> idx; idx.from_linear(e);" % gi)
+                        body.append("        GAcc<dom_g%d> a(idx, vec);" % gi)
+                        body.append("        " + call_free)
+                    body.append("    }")
+                    if mat:
+                        body.append("    }")
+                    body.append("}")
+                else:
+                    o = ep["off"]
+                    body.append("if (lane == 0%s) {   // endpoint %d: group %s at offset (%d, %d, %d)"
+                                % (" && WHICH == 0" if mat else "", ep["id"], g["name"], o[0], o[1], o[2]))
+                    body.append("    const int x = t.c[0] - (%d), y = t.c[1] - (%d), z = t.c[2] - (%d);" % (o[0], o[1], o[2]))
+                    body.append("    ThIdx<dom_g%d> idx;" % gi)
+                    body.append("    if (x >= 0 && y >= 0 && z >= 0 && idx.from_coords(x, y, z)) {")
+                    if mat:
+                        body.append("        const long long e = idx.lin;")
+                        body.append("        " + call_mat)
+                    else:
+                        body.append("        GAcc<dom_g%d> a(idx, vec);" % gi)
+                        body.append("        " + call_free)
+                    body.append("    }")
+                    body.append("}")
+            src.append("template <int WHICH, int LANES> __device__ __forceinline__ void gather_s%d(const ThIdx<dom_s%d>& t, int lane, "
+                       "const Params& P, const ThGather& G, const real* __restrict__ vec, real* __restrict__ acc) {\n    %s\n}\n"
+                       % (si, si, "\n    ".join(body)))
+        return part_a, "\n".join(src)
+
     def gen_exclude(self):
         src = []
         for k, im in enumerate(self.unknowns):
@@ -524,6 +836,10 @@ class Generator:
             src.append(self._fn(
                 "template <class A> __device__ __forceinline__ bool exclude_u%d(const A& a, const Params& P)" % k,
                 [e], lambda r: ["return %s;" % r[0]], dom))
+            if self.schedule == "gather" and self.spaces[self.space_of[dom]]["images"][0] is im:
+                src.append(self._fn(
+                    "template <class A> __device__ __forceinline__ bool exclude_s%d(const A& a, const Params& P)" % self.space_of[dom],
+                    [e], lambda r: ["return %s;" % r[0]], dom))
         return "\n".join(src)
 
     # ---- residualwise functions (per group)
@@ -607,12 +923,15 @@ class Generator:
         out = Lowered()
         if self.schedule == "at_output":
             self._prepare_unknownwise()
+        if self.schedule == "gather":
+            self._prepare_gather()
         hdr = []
         hdr.append("// generated by thallo_b200.frontend.codegen for energy '%s' (%s)" % (self.name, self.kind))
         hdr.append("#define TH_DOUBLE %d" % int(self.double))
         hdr.append("#define TH_LM %d" % int(self.lm))
         hdr.append("#define TH_USEPRE %d" % int(L.usepreconditioner))
         hdr.append("#define TH_AT_OUTPUT %d" % int(self.schedule == "at_output"))
+        hdr.append("#define TH_GATHER %d" % int(self.schedule == "gather"))
         if self.partition is not None:
             assert self.tiled, "multi-GPU partitioning needs the tiled at-output schedule (2-D / 3-D image domain)"
             assert all(tuple(g["domain"]) == tuple(self.udomain) for g in self.groups), \
@@ -665,6 +984,28 @@ class Generator:
         for gi, g in enumerate(self.groups):
             body.append(self.gen_group(gi, g))
             gl.append("X(%d)" % gi)
+        gather_b = ""
+        if self.schedule == "gather":
+            gather_a, gather_b = self.gen_gather()
+            body.append(gather_a)
+            hdr.append("#define TH_NEP_S %d" % self.n_sparse_ep)
+            hdr.append("#define TH_NSPACES %d" % len(self.spaces))
+            hdr.append("#define TH_SPACE_LIST(X) %s" % " ".join("X(%d)" % i for i in range(len(self.spaces))))
+            hdr.append("#define TH_MAT_LIST(X) %s" % " ".join("X(%d)" % gi for gi, g in enumerate(self.groups) if g["materialize"]))
+            hdr.append("#define TH_SPACE_TABLE {%s}" % ", ".join("{%d, %d, %dLL}" % (sp["nslots"], sp["lanes"], sp["elements"])
+                                                                 for sp in self.spaces))
+            mx = max(sp["nslots"] for sp in self.spaces)
+            hdr.append("#define TH_MAXSLOTS %d" % mx)
+            rows = []
+            for sp in self.spaces:
+                sl = [(self.uidx[im.name], ch) for im in sp["images"] for ch in range(im.channels)]
+                sl += [(0, 0)] * (mx - len(sl))
+                rows.append("{%s}" % ", ".join("{%d, %d}" % x for x in sl))
+            hdr.append("#define TH_SLOT_TABLE {%s}" % ", ".join(rows))
+            hdr.append("#define TH_GROUP_NNZP {%s}" % ", ".join(str(g["nnzp"]) for g in self.groups))
+            hdr.append("#define TH_SCOEF_N {%s}" % ", ".join(str(len(c)) for c in self.scoef))
+            hdr.append("#define TH_SCOEF_SLOT {%s}" % ", ".join(str(self.ptr_slot.get("__coef_s%d" % si, 0)) for si in range(len(self.spaces))))
+            hdr.append("#define TH_SCOEF_LIST(X) %s" % " ".join("X(%d)" % si for si in range(len(self.spaces)) if self.scoef[si]))
         if self.schedule != "at_output":
             hdr.append("#define TH_TILED 0\n#define TH_NCOEF 0")
         hdr.append("#define TH_GROUP_LIST(X) %s" % " ".join(gl))
@@ -686,8 +1027,14 @@ class Generator:
             doms.append(dom_struct("dom_uw", list(self.udomain)))
         for gi, g in enumerate(self.groups):
             doms.append(dom_struct("dom_g%d" % gi, list(g["domain"])))
+        if self.schedule == "gather":
+            for si, sp in enumerate(self.spaces):
+                doms.append(dom_struct("dom_s%d" % si, list(sp["dims"])))
         src = ("\n".join(hdr) + "\n#include \"thallo_prelude.cuh\"\nnamespace th {\n" + "\n".join(doms) + "\n"
-               + "\n".join(body) + "\n} // namespace th\n#include \"thallo_kernels.cuh\"\n")
+               + "\n".join(body) + "\n} // namespace th\n")
+        if gather_b:
+            src += "#include \"thallo_access.cuh\"\nnamespace th {\n" + gather_b + "\n} // namespace th\n"
+        src += "#include \"thallo_kernels.cuh\"\n"
         out.source = src
         # ---- descriptor
         d = dict(
@@ -701,6 +1048,15 @@ class Generator:
                          count=_prod(L.dims[x].size for x in g["domain"]), materialize=int(g["materialize"]),
                          nnz_per_elem=g["nnz_per_elem"], row_nnz=g["row_nnz"]) for g in self.groups],
         )
+        if self.schedule == "gather":
+            d["gather"] = dict(
+                spaces=[dict(elements=sp["elements"], lanes=sp["lanes"], nslots=sp["nslots"]) for sp in self.spaces],
+                sparse_endpoints=[dict(sid=ep["sid"], group=ep["group"], slot=self.ptr_slot[ep["sparse"]],
+                                       count=_prod(L.dims[x].size for x in self.groups[ep["group"]]["domain"]),
+                                       targets=self.spaces[ep["space"]]["elements"])
+                                  for ep in self.endpoints if ep["kind"] == "sparse"],
+                groups=[dict(nnzp=g["nnzp"], nterms=len(g["terms"])) for g in self.groups],
+                scoef=[dict(space=si, slot=self.ptr_slot["__coef_s%d" % si], channels=len(c)) for si, c in enumerate(self.scoef) if c])
         if self.schedule == "at_output":
             d["U"] = self.U
             d["uw_dims"] = [L.dims[x].size for x in self.udomain]
@@ -742,6 +1098,16 @@ def descriptor_text(d):
         ln.append("group %s %d %d %d %d %d %s | %s" % (g["name"], g["count"], g["nterms"], g["materialize"], g["nnz_per_elem"],
                                                       len(g["domain"]), " ".join(map(str, g["domain"])),
                                                       " ".join(map(str, g["row_nnz"]))))
+    if d["schedule"] == "gather":
+        ga = d["gather"]
+        for sp in ga["spaces"]:
+            ln.append("space %d %d %d" % (sp["elements"], sp["lanes"], sp["nslots"]))
+        for ep in ga["sparse_endpoints"]:
+            ln.append("sep %d %d %d %d %d" % (ep["sid"], ep["group"], ep["slot"], ep["count"], ep["targets"]))
+        for gi, g in enumerate(ga["groups"]):
+            ln.append("gmat %d %d %d" % (gi, g["nnzp"], g["nterms"]))
+        for c in ga["scoef"]:
+            ln.append("scoef %d %d %d" % (c["space"], c["slot"], c["channels"]))
     if d["schedule"] == "at_output":
         ln.append("U %d" % d["U"])
         ln.append("uw_dims %d %s" % (len(d["uw_dims"]), " ".join(map(str, d["uw_dims"]))))

@@ -28,6 +28,8 @@ def _shifted(arr, offs):
 
 
 class Interp:
+    shared = {}      # per gather_apply call: coefficient images of the index spaces
+
     def __init__(self, gen, params, dom, vec=None, dtype=np.float64):
         self.gen, self.params, self.dom, self.vec, self.dt = gen, params, list(dom), vec, dtype
         L = gen.L
@@ -54,12 +56,29 @@ class Interp:
 
     def var(self, k):
         g = self.gen
+        if isinstance(k, ImageAccess) and k.image.startswith("__coef_s"):
+            si = int(k.image[len("__coef_s"):])
+            ck = ("scoef", si)
+            if ck not in Interp.shared:
+                sub = Interp(g, self.params, g.spaces[si]["dims"], None, self.dt)
+                Interp.shared[ck] = np.stack([np.broadcast_to(v, sub.shape).astype(self.dt).reshape(-1)
+                                              for v in sub.eval(list(g.scoef[si]))], axis=-1)
+            arr = Interp.shared[ck]
+            if k.index[0][0] == "s":
+                return arr[self._sparse(k.index[0][1]), k.channel]
+            return arr[:, k.channel].reshape(self.shape)
         if isinstance(k, ImageAccess):
-            assert k.index[0][0] == "d", "sparse accesses are not interpreted"
+            if k.index[0][0] == "s":        # 1-D residual domain reaching a 1-D image through an index array
+                im = g.images[k.image]
+                a = np.asarray(self.params[im.pidx]).astype(self.dt).reshape(-1, im.channels)
+                return a[self._sparse(k.index[0][1]), k.channel]
             return _shifted(self._image(k.image), self._offs(k.index))[..., k.channel]
         if isinstance(k, VecArg):
             im = g.images[k.image]
             off = g.uoff[k.image]
+            if k.index[0][0] == "s":
+                a = self.vec[off:off + im.cardinality].astype(self.dt).reshape(-1, im.channels)
+                return a[self._sparse(k.index[0][1]), k.channel]
             a = self.vec[off:off + im.cardinality].astype(self.dt).reshape(self.shape + (im.channels,))
             return _shifted(a, self._offs(k.index))[..., k.channel]
         if isinstance(k, Bounds):
@@ -74,7 +93,14 @@ class Interp:
         if isinstance(k, Param):
             pd = [p for p in g.L.params if p.name == k.name][0]
             return self.dt(np.asarray(self.params[pd.pidx]).reshape(-1)[0])
+        if type(k).__name__ == "JVal":          # stored partial derivative i of every residual element
+            return self.jvals[k.i]
+        if type(k).__name__ == "JpVal":
+            return self.jp[k.t]
         raise NotImplementedError(k)
+
+    def _sparse(self, name):
+        return np.asarray(self.params[self.gen.sparses[name].pidx]).reshape(-1).astype(np.int64)
 
     def eval(self, roots):
         val = self.cache
@@ -143,3 +169,53 @@ def unknownwise(gen, params, vec=None, dtype=np.float64):
     g, d = pack(vals[:U]), pack(vals[U:2 * U])
     out = pack(vals[2 * U:]) if vec is not None else None
     return g, d, out
+
+
+def gather_apply(gen, params, vec, dtype=np.float64, materialised=False):
+    """Evaluate the gather schedule's endpoint functions (codegen.gen_gather) over every residual
+    element and sum them per unknown element the way the th_gather_s<i> kernels do.  Returns
+    J^T J vec as a flat vector in the solver's unknown layout.  materialised: groups with a
+    materialised Jacobian go through their stored-value functions (computeJv -> matJ -> jt_ep)."""
+    out = np.zeros(gen.nunk, dtype)
+    stored = {}
+    Interp.shared = {}
+    for ep in gen.endpoints:
+        gi = ep["group"]
+        g = gen.groups[gi]
+        sp = gen.spaces[ep["space"]]
+        it = Interp(gen, params, g["domain"], vec, dtype)
+        js = sorted(ep["roots"])
+        if materialised and g["materialize"]:
+            if gi not in stored:
+                jv = [np.array(v) for v in Interp(gen, params, g["domain"], vec, dtype).eval(g["jv_roots"])]
+                it2 = Interp(gen, params, g["domain"], vec, dtype)
+                it2.jvals = jv
+                stored[gi] = (jv, [np.array(v) for v in it2.eval(g["matj_roots"])])
+            it.jvals, it.jp = stored[gi]
+            vals = it.eval([ep["mat_roots"][j] for j in js])
+        else:
+            vals = it.eval([ep["roots"][j] for j in js])
+        if ep["kind"] == "sparse":
+            tgt = it._sparse(ep["sparse"])
+        else:
+            # residual element e at coordinates c contributes to the unknown element at c + off
+            nd = len(g["domain"])
+            ok = np.ones(it.shape, bool)
+            lin = np.zeros(it.shape, np.int64)
+            stride = 1
+            for i, d in enumerate(g["domain"]):
+                c = it.coord[d] + ep["off"][i]
+                n = gen.L.dims[d].size
+                ok &= (c >= 0) & (c < n)
+                lin += np.clip(c, 0, n - 1) * stride
+                stride *= n
+            tgt = lin.reshape(-1)
+            vals = [np.where(ok, v, 0.0) for v in vals]
+        slot_to = {}
+        for im in sp["images"]:
+            for ch in range(im.channels):
+                slot_to[sp["slots"][(im.name, ch)]] = (gen.uoff[im.name], im.channels, ch)
+        for j, v in zip(js, vals):
+            base, C, ch = slot_to[j]
+            np.add.at(out, base + tgt * C + ch, np.asarray(v, dtype).reshape(-1))
+    return out

@@ -190,3 +190,58 @@ def arap_mesh_inputs(nx, ny, seed=1, w_fit=4.0, w_reg=1.0, handle_fraction=0.01)
 def arap_mesh_params(d):
     return [np.array([d["w_fitSqrt"]], np.float32), np.array([d["w_regSqrt"]], np.float32),
             d["Position"], d["Angle"], d["Original"], d["Constraints"], d["V0"], d["V1"]]
+
+
+def _angle_axis_rotate(aa, pt):
+    """Rodrigues rotation, rows of `aa` (n,3) applied to rows of `pt` (n,3) (lib.t:514-555)."""
+    th2 = np.sum(aa * aa, -1, keepdims=True)
+    th = np.sqrt(np.maximum(th2, 1e-30))
+    w = aa / th
+    c, s = np.cos(th), np.sin(th)
+    large = pt * c + np.cross(w, pt) * s + w * (np.sum(w * pt, -1, keepdims=True) * (1.0 - c))
+    small = pt + np.cross(aa, pt)
+    return np.where(th2 > 1e-8, large, small)
+
+
+def bundle_adjustment_inputs(C, P, obs_per_point=5, seed=1, noise_px=0.5, perturb=0.01):
+    """Config 5 synthetic shape: C cameras on a ring looking at a unit cube of P
+    points, every point seen by `obs_per_point` distinct seeded-random cameras; observations =
+    Snavely projection (bundle_adjustment.t:15-32) + N(0, noise_px) pixels; cameras and points
+    then perturbed by `perturb` (relative).  Observations are listed point-major (like BAL files),
+    so oToP is sorted and oToC is not.  Camera = angle-axis 3, translation 3, focal, k1, k2."""
+    rng = np.random.RandomState(seed)
+    k = int(obs_per_point)
+    assert C >= k
+    theta = 2.0 * np.pi * np.arange(C) / C
+    cams = np.zeros((C, 9), np.float64)
+    cams[:, 1] = theta                       # rotation about the y axis: the ring
+    cams[:, 0] = 0.05 * rng.randn(C)
+    cams[:, 2] = 0.05 * rng.randn(C)
+    cams[:, 3:5] = 0.1 * rng.randn(C, 2)
+    cams[:, 5] = -5.0                        # points end up at z ~ -5 in the camera frame (BAL looks down -z)
+    cams[:, 6] = 800.0 + 20.0 * rng.randn(C)
+    cams[:, 7] = 1e-2 * rng.randn(C)
+    cams[:, 8] = 1e-3 * rng.randn(C)
+    pts = rng.uniform(-1.0, 1.0, (P, 3))
+    # k distinct cameras per point: a random start and k random distinct strides would correlate; use
+    # the first k entries of a per-point random offset walk (distinct by construction, vectorised)
+    base = rng.randint(0, C, P)
+    steps = 1 + rng.randint(0, max(1, (C - 1) // k), (P, k))
+    steps[:, 0] = 0
+    cam_of = np.sort((base[:, None] + np.cumsum(steps, 1)) % C, 1)
+    o2c = cam_of.reshape(-1).astype(np.int32)
+    o2p = np.repeat(np.arange(P, dtype=np.int32), k)
+    cam = cams[o2c]
+    p = _angle_axis_rotate(cam[:, 0:3], pts[o2p]) + cam[:, 3:6]
+    cod = -p[:, 0:2] / p[:, 2:3]
+    r2 = np.sum(cod * cod, -1, keepdims=True)
+    obs = cod * cam[:, 6:7] * (1.0 + r2 * (cam[:, 7:8] + cam[:, 8:9] * r2))
+    obs = obs + noise_px * rng.randn(*obs.shape)
+    cams0 = cams * (1.0 + perturb * rng.randn(*cams.shape))
+    pts0 = pts + perturb * rng.randn(*pts.shape)
+    return dict(cameras=cams0.astype(np.float32), points=pts0.astype(np.float32), observations=obs.astype(np.float32),
+                oToC=o2c, oToP=o2p)
+
+
+def bundle_adjustment_params(d):
+    return [d["cameras"], d["points"], d["observations"], d["oToC"], d["oToP"]]
