@@ -26,6 +26,7 @@ REGISTRY = {
     "volumetric_mesh_deformation.t": "volumetric_mesh_deformation",
     "arap_mesh_deformation.t": "arap_mesh_deformation",
     "bundle_adjustment.t": "bundle_adjustment",
+    "shape_from_shading.t": "shape_from_shading",
 }
 
 

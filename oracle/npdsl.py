@@ -65,6 +65,10 @@ class NBool:
 
     __rmul__ = __mul__
 
+    def get(self, *idx):                 # a stored boolean is a 0/1 image of the solver's scalar type
+        L = idx[0].dim.L
+        return Dual(self.v.astype(L.dtype)).get(*idx)
+
 
 class Dual:
     __array_priority__ = 1000
@@ -138,6 +142,23 @@ class Dual:
 
     def __len__(self):
         return 1
+
+    def get(self, *idx):
+        """`exp:get(x+ox, y+oy)`: the expression as a stored image over its domain (ComputedArray,
+        thallo.t:1777-1822), read at an offset with zero outside the domain (thallo.t:876-882).  Its
+        derivatives travel with it as the gradient image, read at the same offset and re-keyed to
+        the unknown accesses they belong to, shifted by that offset (thallo.t:1551-1561)."""
+        offs = [iv.off for iv in idx]
+        shape = tuple(iv.dim.size for iv in reversed(idx))
+
+        def moved(a):
+            full = np.ascontiguousarray(np.broadcast_to(np.asarray(a), shape))
+            return _shift(full[..., None], offs)[..., 0]
+        d = {}
+        for (iname, ikey, ch), dv in self.d.items():
+            assert ikey[0] == "d", "computed arrays over sparse accesses are not supported"
+            d[(iname, ("d", tuple(o + s for o, s in zip(ikey[1], offs))), ch)] = moved(dv)
+        return Dual(moved(self.val), d)
 
 
 def _recip(o):

@@ -7,6 +7,7 @@ every PCG kernel against its algorithmic bytes (SURVEY.md 8d formulas, restated 
   python scripts/bench_workloads.py bundle_adjustment --cameras 2000 --points 1000000
   python scripts/bench_workloads.py optical_flow --size 4096
   python scripts/bench_workloads.py volumetric --size 160
+  python scripts/bench_workloads.py sfs --size 4096
 Prints one JSON line per run.  Not the driver's bench contract (that is bench.py)."""
 import argparse
 import json
@@ -20,7 +21,7 @@ sys.path.insert(0, ROOT)
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("workload", choices=["arap_mesh", "bundle_adjustment", "optical_flow", "volumetric", "image_warping"])
+    ap.add_argument("workload", choices=["arap_mesh", "bundle_adjustment", "optical_flow", "volumetric", "image_warping", "sfs"])
     ap.add_argument("--size", type=int, default=0)
     ap.add_argument("--cameras", type=int, default=2000)
     ap.add_argument("--points", type=int, default=1000000)
@@ -68,6 +69,13 @@ def main():
         dims, energy, kind = [n, n, n], "volumetric_mesh_deformation", a.kind or "gauss_newton"
         params = wl.volumetric_params(d)
         bytes_iter = {"th_pcg_a": 4 * n ** 3 * (4 * 6 + 9), "th_pcg_b": 4 * n ** 3 * 8 * 6}
+    elif a.workload == "sfs":
+        n = a.size or 4096
+        d = wl.sfs_inputs(n, n)
+        dims, energy, kind = [n, n], "shape_from_shading", a.kind or "gauss_newton"
+        params = wl.sfs_params(d)
+        # th_pcg_a: z, p_old, p_new, Ap (4) + gradient image (3) + validity image (1) + D_i (1) + two uint8 edge masks (0.5)
+        bytes_iter = {"th_pcg_a": int(4 * n * n * 9.5), "th_pcg_b": 4 * n * n * 7}
     else:
         n = a.size or 2048
         d = wl.image_warping_inputs(n, n)

@@ -119,3 +119,27 @@ def test_materialised_laplacian_gather_matches_oracle():
     low = _check_gather("laplacian", [13, 11], [X.astype(np.float64) * 1.3, A.astype(np.float64)],
                         dict(variant="committed", materialize=True))
     assert all(g["materialize"] for g in low.desc["groups"])
+
+
+# ---- computed arrays (`exp:get()`): value + gradient images, chain rule through the gradient image
+def _sfs_params64(d):
+    return [np.asarray(p, np.float64) if np.asarray(p).dtype == np.float32 else p for p in wl.sfs_params(d)]
+
+
+def test_shape_from_shading_synthetic_matches_oracle():
+    W, H = 40, 32
+    d = wl.sfs_inputs(W, H)
+    low_check = _check("shape_from_shading", [W, H], _sfs_params64(d))
+
+
+def test_shape_from_shading_reference_crop_matches_oracle():
+    import os
+    d, W, H = wl.sfs_fixture_inputs(os.path.join(os.path.dirname(__file__), "golden", "sfs_crop.npz"))
+    _check("shape_from_shading", [W, H], _sfs_params64(d))
+
+
+def test_shape_from_shading_lowering_has_two_computed_arrays():
+    low = codegen.lower(energies.load("shape_from_shading"), [64, 48], "gauss_newton", "shape_from_shading")
+    assert low.desc["computed"] == [dict(elements=64 * 48, ngrad=3), dict(elements=64 * 48, ngrad=0)]
+    assert low.desc["tiled"] == 1 and low.desc["tile"]["halo"][:2] == [2, 2]
+    assert "th_precompute_c0" in low.source or "TH_COMPUTED_LIST(X) X(0) X(1)" in low.source

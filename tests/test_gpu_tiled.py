@@ -106,3 +106,31 @@ def test_optical_flow_tiled_matches_oracle():
     assert s.lowered.desc["tiled"] == 1
     _close(c, cref, 1e-5, 1e-3)
     assert np.abs(dp[2].cpu().numpy() - po[2]).max() < 2e-3
+
+
+# ---- computed arrays (shape_from_shading): precompute kernels, gradient images staged through the tiles (halo 2)
+def _sfs_params(d, dtype):
+    return [np.array(p, dtype=dtype) if np.asarray(p).dtype == np.float32 else p for p in wl.sfs_params(d)]
+
+
+@pytest.mark.parametrize("kind", ["gauss_newton", "levenberg_marquardt"])
+def test_shape_from_shading_reference_crop_matches_oracle(kind):
+    """A crop of the reference's own example input (tests/golden/sfs_crop.npz), 6 nonlinear x 10 PCG
+    iterations as examples/shape_from_shading/src/main.cpp:44-45 (60 x 10 there)."""
+    d, W, H = wl.sfs_fixture_inputs(os.path.join(os.path.dirname(__file__), "golden", "sfs_crop.npz"))
+    o, cref = _trajectory_oracle("shape_from_shading", [W, H], kind, _sfs_params(d, np.float32), np.float32, 6, 10)
+    _, cref64 = _trajectory_oracle("shape_from_shading", [W, H], kind, _sfs_params(d, np.float64), np.float64, 6, 10)
+    s, c, lin, dp = _trajectory_gpu("shape_from_shading", [W, H], kind, _sfs_params(d, np.float32), range(16, 21), np.float32, 6, 10)
+    assert s.lowered.desc["tiled"] == 1 and len(s.lowered.desc["computed"]) == 2
+    _close(c, cref, 1e-5, 1e-3, cref64)
+    if kind == "levenberg_marquardt":
+        assert lin == [it["n_lin"] for it in o.trace][:len(lin)]
+
+
+def test_shape_from_shading_synthetic_f64():
+    W, H = 72, 52
+    d = wl.sfs_inputs(W, H)
+    o, cref = _trajectory_oracle("shape_from_shading", [W, H], "gauss_newton", _sfs_params(d, np.float64), np.float64, 4, 10)
+    s, c, lin, dp = _trajectory_gpu("shape_from_shading", [W, H], "gauss_newton", _sfs_params(d, np.float64), range(16, 21), np.float64, 4, 10)
+    _close(c, cref, 1e-10, 1e-6)
+    assert cref[-1] < cref[0]

@@ -37,10 +37,15 @@ template <class Dom> __device__ __forceinline__ bool th_uw_index(ThIdx<Dom>& i) 
 // ------------------------------------------------------------------ global-memory accessor
 // Bounds-checked loads return 0 out of bounds (thallo.t:876-882); `vec` reads the
 // unknown-shaped vector argument (P / Delta).
-template <class Dom> struct GAcc {
+// OWNSP >= 0 (gather schedule): the sparse index array in ptr slot OWNSP is known to hold `own` at
+// this element -- the unknown element whose adjacency list is being walked -- so reads through it
+// need no index load and are loop-invariant across the walk (the compiler hoists them).
+template <class Dom, int OWNSP = -1> struct GAcc {
     ThIdx<Dom> i;
     const real* __restrict__ v;
-    __device__ __forceinline__ GAcc(const ThIdx<Dom>& idx, const real* vec) : i(idx), v(vec) {}
+    long long own;
+    __device__ __forceinline__ GAcc(const ThIdx<Dom>& idx, const real* vec) : i(idx), v(vec), own(0) {}
+    __device__ __forceinline__ GAcc(const ThIdx<Dom>& idx, const real* vec, long long o) : i(idx), v(vec), own(o) {}
 
     template <int D> __device__ __forceinline__ int coord() const { return i.c[D]; }
 
@@ -76,6 +81,7 @@ template <class Dom> struct GAcc {
     }
     // sparse (graph) accesses: the index array lives in ptr slot SP and is indexed by this element
     template <int SP> __device__ __forceinline__ long long sidx(const Params& P) const {
+        if (SP == OWNSP) return own;
         return (long long)__ldg(((const int*)P.ptr[SP]) + i.lin);
     }
     template <int SLOT, class CT, int C, int CH, int SP> __device__ __forceinline__ real simg(const Params& P) const {

@@ -322,6 +322,9 @@ th_precompute_coef(const __grid_constant__ Params P) {
 #ifndef TH_PCG_A_MINB
 #define TH_PCG_A_MINB 3
 #endif
+#ifndef TH_PIPE
+#define TH_PIPE 2
+#endif
 __device__ __forceinline__ unsigned th_smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void th_mbar_init(unsigned long long* bar, unsigned count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(th_smem_u32(bar)), "r"(count) : "memory");
@@ -449,10 +452,11 @@ template <class Dom, bool UPD> struct TAcc {
 // mode 1: Adelta = (JtJ [+CtC]) delta   (LM residual reset, gauss_newton.t:755-762)
 //
 // Persistent CTAs (the host launches SMs x resident-CTAs-per-SM of them) walk the tile list with a
-// two-stage shared-memory pipeline: while tile i is processed, the TMA unit already fills the other
-// stage with tile i+1 (every array the operator reads, so no thread issues a global load), the
-// stage is handed back through an mbarrier the warps arrive on, and there is a single grid
-// reduction per CTA at the very end.
+// TH_PIPE-stage shared-memory pipeline (two stages when they fit beside TH_PCG_A_MINB resident
+// CTAs, else one): while tile i is processed, the TMA unit already fills the other stage with tile
+// i+1 (every array the operator reads, so no thread issues a global load), a stage is handed
+// back through an mbarrier the warps arrive on, and there is a single grid reduction per CTA at
+// the very end.
 #define TH_NTX ((int)((th::dom_uw::D0 + TH_TW - 1) / TH_TW))
 #define TH_NTY ((int)((th::dom_uw::D1 + TH_TH - 1) / TH_TH))
 #define TH_NTZ ((int)((th::dom_uw::D2 + TH_TD - 1) / TH_TD))
@@ -573,8 +577,8 @@ __device__ __forceinline__ real th_tile_apply(const unsigned char* sm, const Par
 
 template <bool TMA>
 __device__ __forceinline__ void th_pcg_a_impl(const Params& P, const Vecs& V, const ThMaps& M, ThScalars* S, double* partials, int mode) {
-    extern __shared__ __align__(128) unsigned char th_sm[];      // TMA: two stages of TH_SMEM_BYTES; otherwise one
-    __shared__ __align__(8) unsigned long long full[2], empty[2];
+    extern __shared__ __align__(128) unsigned char th_sm[];      // TMA: TH_PIPE stages of TH_SMEM_BYTES; otherwise one
+    __shared__ __align__(8) unsigned long long full[TH_PIPE], empty[TH_PIPE];
     if (S->done) return;
     const int it = S->it;
     const int tx = threadIdx.x, ty = threadIdx.y, tz = threadIdx.z;
@@ -585,28 +589,34 @@ __device__ __forceinline__ void th_pcg_a_impl(const Params& P, const Vecs& V, co
     real* __restrict__ pnew = ((it + 1) & 1) ? V.p2 : V.p;
     if (TMA) {
         if (tid == 0) {
-            th_mbar_init(&full[0], 1); th_mbar_init(&full[1], 1);
-            th_mbar_init(&empty[0], TH_TILE_THREADS / 32); th_mbar_init(&empty[1], TH_TILE_THREADS / 32);
+#pragma unroll
+            for (int s = 0; s < TH_PIPE; ++s) { th_mbar_init(&full[s], 1); th_mbar_init(&empty[s], TH_TILE_THREADS / 32); }
         }
         __syncthreads();
-        if (tid == 0 && (int)blockIdx.x < TH_NTILES) th_tile_issue(th_sm, &full[0], M, blockIdx.x, mode, it);
+        if (tid == 0) {
+#pragma unroll
+            for (int s = 0; s < TH_PIPE; ++s) {
+                const int t0 = (int)blockIdx.x + s * (int)gridDim.x;
+                if (t0 < TH_NTILES) th_tile_issue(th_sm + s * TH_SMEM_BYTES, &full[s], M, t0, mode, it);
+            }
+        }
     }
     double acc[1] = {0.0};
-    unsigned fphase = 0, ephase = 0;      // bit s: parity of the next completion of full[s] / empty[s]
+    unsigned phase = 0;                   // bit s: parity of the next completion of full[s] (and of empty[s])
     int stage = 0;
     for (int t = blockIdx.x; t < TH_NTILES; t += gridDim.x) {
         unsigned char* sm = th_sm + (TMA ? stage * TH_SMEM_BYTES : 0);
         if (TMA) {
-            const int tn = t + gridDim.x;
-            if (tid == 0 && tn < TH_NTILES) {
-                if (t != (int)blockIdx.x) {          // the other stage held the previous tile: wait until every warp released it
-                    th_mbar_wait(&empty[stage ^ 1], (ephase >> (stage ^ 1)) & 1u);
-                    ephase ^= 1u << (stage ^ 1);
+            if (TH_PIPE == 2) {
+                // two stages: the other stage held the previous tile; once every warp has released
+                // it, refill it with the next tile so that the copy overlaps this tile's arithmetic
+                const int tn = t + 2 * (int)gridDim.x, so = stage ^ 1;
+                if (tid == 0 && t != (int)blockIdx.x && tn - (int)gridDim.x < TH_NTILES) {
+                    th_mbar_wait(&empty[so], ((phase >> so) & 1u) ^ 1u);
+                    th_tile_issue(th_sm + so * TH_SMEM_BYTES, &full[so], M, tn - (int)gridDim.x, mode, it);
                 }
-                th_tile_issue(th_sm + (stage ^ 1) * TH_SMEM_BYTES, &full[stage ^ 1], M, tn, mode, it);
             }
-            th_mbar_wait(&full[stage], (fphase >> stage) & 1u);
-            fphase ^= 1u << stage;
+            th_mbar_wait(&full[stage], (phase >> stage) & 1u);
         } else {
             __syncthreads();                         // previous tile fully consumed
             th_tile_fill(sm, P, V, t, mode, it, tid);
@@ -618,8 +628,18 @@ __device__ __forceinline__ void th_pcg_a_impl(const Params& P, const Vecs& V, co
         if (TMA) {
             __syncwarp();
             if ((tid & 31) == 0) th_mbar_arrive(&empty[stage]);
+            if (TH_PIPE == 1) {
+                // one stage (tiles too large for two): refill as soon as every warp has released it;
+                // the other CTAs resident on the SM cover the copy
+                const int tn = t + (int)gridDim.x;
+                if (tid == 0 && tn < TH_NTILES) {
+                    th_mbar_wait(&empty[0], phase & 1u);
+                    th_tile_issue(sm, &full[0], M, tn, mode, it);
+                }
+            }
+            phase ^= 1u << stage;
+            stage = (stage + 1 == TH_PIPE) ? 0 : stage + 1;
         }
-        stage ^= 1;
     }
     if (mode) return;
     double tot[1];
@@ -858,6 +878,32 @@ th_index_checksum(const int* __restrict__ a, long long n, unsigned long long* ou
     if ((threadIdx.x & 31) == 0) atomicAdd(out, h);
 }
 #endif  // TH_GATHER
+
+// ================================================================== computed arrays
+// precompute (gauss_newton.t:979-986, createprecomputed thallo.t:4046-4094): every ComputedArray
+// (`exp:get(...)`) is stored as a plan-owned image together with its gradient image, refreshed
+// whenever the unknowns change (init, after every update, after a rejected LM step).
+#if TH_NCOMPUTED > 0
+struct ThComputed { int val_slot; int grad_slot; int ngrad; };
+__device__ constexpr ThComputed TH_COMPUTED[TH_NCOMPUTED] = TH_COMPUTED_TABLE;
+#define TH_COMPUTED_KERNEL(K)                                                                                       \
+    extern "C" __global__ void __launch_bounds__(TH_BLOCK)                                                          \
+    th_precompute_c##K(const __grid_constant__ Params P) {                                                          \
+        ThIdx<th::dom_c##K> idx;                                                                                    \
+        if (idx.from_linear((long long)blockIdx.x * blockDim.x + threadIdx.x)) {                                    \
+            GAcc<th::dom_c##K> a(idx, nullptr);                                                                     \
+            real v[1 + TH_COMPUTED[K].ngrad];                                                                       \
+            th::precompute_c##K(a, P, v);                                                                           \
+            ((real*)P.ptr[TH_COMPUTED[K].val_slot])[idx.lin] = v[0];                                                \
+            if (TH_COMPUTED[K].ngrad > 0) {                                                                         \
+                real* __restrict__ g = (real*)P.ptr[TH_COMPUTED[K].grad_slot >= 0 ? TH_COMPUTED[K].grad_slot : 0];  \
+                _Pragma("unroll") for (int i = 0; i < TH_COMPUTED[K].ngrad; ++i)                                    \
+                    g[idx.lin * TH_COMPUTED[K].ngrad + i] = v[1 + i];                                               \
+            }                                                                                                       \
+        }                                                                                                           \
+    }
+TH_COMPUTED_LIST(TH_COMPUTED_KERNEL)
+#endif
 
 // ================================================================== per-residual-group kernels
 #define TH_GROUP_KERNELS(G)                                                                                         \

@@ -91,6 +91,9 @@ __device__ constexpr long long TH_DIMS[TH_NDIMS] = TH_DIM_SIZES;
 #ifndef TH_GATHER
 #define TH_GATHER 0
 #endif
+#ifndef TH_OWN_ENDPOINT
+#define TH_OWN_ENDPOINT 1      // reads through the endpoint being walked use the walker's own element (no index load)
+#endif
 #if TH_GATHER
 struct ThGather {
     const int* ptr[TH_NEP_S > 0 ? TH_NEP_S : 1];

@@ -72,9 +72,11 @@ bool parse_descriptor(const std::string& text, PlanDesc& d, std::string& err) {
         } else if (key == "U") ls >> d.U;
         else if (key == "uw_dims") { int n; ls >> n; d.uw_dims.resize(n); for (auto& x : d.uw_dims) ls >> x; }
         else if (key == "ncoef") ls >> d.ncoef;
+        else if (key == "computed") { int k; long long n; int g; ls >> k >> n >> g; d.computed.push_back({n, g}); }
         else if (key == "partition") { ls >> d.ghost_lo >> d.ghost_hi; d.multi = true; }
         else if (key == "tile") {
             ls >> d.tile[0] >> d.tile[1] >> d.tile[2] >> d.halo[0] >> d.halo[1] >> d.halo[2] >> d.smem_bytes;
+            if (!(ls >> d.pipe)) d.pipe = 2;
             d.tiled = true;
         } else if (key == "vtile") { VTileDesc v; ls >> v.roww >> v.zoff >> v.poff >> v.bytes >> v.padl >> v.coff >> v.croww >> v.cbytes; d.vtiles.push_back(v); }
         else if (key == "stage") { StageDesc t; ls >> t.slot >> t.ctype >> t.es >> t.channels >> t.roww >> t.off >> t.bytes >> t.padl >> t.center; d.stages.push_back(t); }
@@ -218,7 +220,13 @@ Plan::Plan(const StateOptions* opts, const PlanDesc& desc, const std::string& so
     if (!api.ok) { error_ = "no CUDA device / driver available: thallo_b200 has no CPU fallback"; return; }
     std::vector<char> cubin;
     std::string clog;
-    if (!compile_cubin(source, skeleton_dir(), cubin, clog)) { error_ = "NVRTC compilation failed:\n" + clog; return; }
+    std::vector<std::string> xopts;           // tuning experiments: extra NVRTC options, e.g. "-DTH_OWN_ENDPOINT=0"
+    if (const char* e = getenv("THALLO_B200_NVRTC_OPTS")) {
+        std::stringstream ss(e);
+        std::string o;
+        while (ss >> o) xopts.push_back(o);
+    }
+    if (!compile_cubin(source, skeleton_dir(), cubin, clog, xopts)) { error_ = "NVRTC compilation failed:\n" + clog; return; }
     if (opts_->init.verbosityLevel > 1 && !clog.empty()) printf("%s\n", clog.c_str());
     CUresult r = api.ModuleLoadData(&module_, cubin.data());
     if (r != CUDA_SUCCESS) { error_ = "cuModuleLoadData failed (" + std::to_string((int)r) + ")"; return; }
@@ -228,6 +236,16 @@ Plan::Plan(const StateOptions* opts, const PlanDesc& desc, const std::string& so
     CD(cudaMalloc((void**)&vec_block_, vec_stride_ * kNumVecs));
     CD(cudaMemsetAsync(vec_block_, 0, vec_stride_ * kNumVecs, stream()));
     for (int i = 0; i < kNumVecs; ++i) vecs_[i] = vec_block_ + vec_stride_ * i;
+    for (auto& c : d_.computed) {     // ComputedArrays: value image + gradient image (ImageTemporary, thallo.t:1806-1815)
+        void* v = nullptr; void* g = nullptr;
+        CD(cudaMalloc(&v, (size_t)c.first * real_size_));
+        CD(cudaMemsetAsync(v, 0, (size_t)c.first * real_size_, stream()));
+        if (c.second > 0) {
+            CD(cudaMalloc(&g, (size_t)c.first * c.second * real_size_));
+            CD(cudaMemsetAsync(g, 0, (size_t)c.first * c.second * real_size_, stream()));
+        }
+        computed_.push_back(v); computed_.push_back(g);
+    }
     if (d_.ncoef > 0) {
         const size_t n = (size_t)d_.unknowns[0].elements * d_.ncoef * real_size_;
         CD(cudaMalloc(&coef_, n));
@@ -292,13 +310,13 @@ Plan::Plan(const StateOptions* opts, const PlanDesc& desc, const std::string& so
     if (d_.tiled) {
         maps_buf_.assign(128 * (5 * d_.unknowns.size() + std::max<size_t>(1, d_.stages.size())) + 64, 0);
         build_vector_maps();
-        // persistent grids: SMs x CTAs resident per SM (two pipeline stages of shared memory with TMA, one without)
+        // persistent grids: SMs x CTAs resident per SM (d_.pipe pipeline stages of shared memory with TMA, one without)
         long long ntiles = 1;
         for (size_t i = 0; i < d_.uw_dims.size(); ++i) ntiles *= (d_.uw_dims[i] + d_.tile[i] - 1) / d_.tile[i];
         const char* names[2] = {"th_pcg_a_ld", "th_pcg_a"};
         for (int v = 0; v < 2; ++v) {
             CUfunction f = fn(names[v]);
-            tiled_smem_[v] = (unsigned)d_.smem_bytes * (v ? 2u : 1u);
+            tiled_smem_[v] = (unsigned)d_.smem_bytes * (v ? (unsigned)d_.pipe : 1u);
             if (tiled_smem_[v] > 48 * 1024 && api.FuncSetAttribute)
                 CU(api.FuncSetAttribute(f, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)tiled_smem_[v]));
             int per_sm = 2;
@@ -370,6 +388,7 @@ Plan::~Plan() {
     for (void* q : jvals_) if (q) cudaFree(q);
     for (void* q : jp_) if (q) cudaFree(q);
     for (void* q : scoef_) if (q) cudaFree(q);
+    for (void* q : computed_) if (q) cudaFree(q);
     if (d_checksum_) cudaFree(d_checksum_);
     if (vec_block_) cudaFree(vec_block_);
     if (coef_) cudaFree(coef_);
@@ -535,7 +554,8 @@ void Plan::bind(void** params) {
     char* buf = params_buf_.data();
     const size_t nptr = std::max<size_t>(1, d_.ptr_pidx.size()), nsc = std::max<size_t>(1, d_.scalars.size());
     for (size_t i = 0; i < d_.ptr_pidx.size(); ++i) {
-        if (d_.ptr_pidx[i] < -1) memcpy(buf + 8 * i, &scoef_[-(d_.ptr_pidx[i] + 2)], 8);   // plan-owned per-space coefficient image
+        if (d_.ptr_pidx[i] <= -100) memcpy(buf + 8 * i, &computed_[-(d_.ptr_pidx[i] + 100)], 8);   // plan-owned ComputedArray value / gradient image
+        else if (d_.ptr_pidx[i] < -1) memcpy(buf + 8 * i, &scoef_[-(d_.ptr_pidx[i] + 2)], 8);   // plan-owned per-space coefficient image
         else if (d_.ptr_pidx[i] < 0) memcpy(buf + 8 * i, &coef_, 8);          // plan-owned coefficient image
         else memcpy(buf + 8 * i, &params[d_.ptr_pidx[i]], 8);
     }
@@ -583,6 +603,14 @@ void Plan::write_lm_params() {
 void Plan::read_scalars() {
     CD(cudaMemcpyAsync(h_scalars_, d_scalars_, sizeof(HScalars), cudaMemcpyDeviceToHost, stream()));
     CD(cudaStreamSynchronize(stream()));
+}
+
+// gpu.precompute (gauss_newton.t:979-986): refresh every ComputedArray and its gradient image from the current unknowns
+void Plan::run_precompute() {
+    for (size_t k = 0; k < d_.computed.size(); ++k) {
+        void* a[] = {params_buf_.data()};
+        launch(fn("th_precompute_c" + std::to_string(k)), dim3((unsigned)((d_.computed[k].first + 255) / 256)), dim3(256), a);
+    }
 }
 
 // computeCost, gauss_newton.t:1128-1136
@@ -655,6 +683,7 @@ void Plan::init(void** params) {
     // solver vectors start from zero so that excluded unknowns stay zero everywhere
     CD(cudaMemsetAsync(vec_block_, 0, vec_stride_ * 10, stream()));
     CD(cudaMemsetAsync(vecs_[V_P2], 0, vec_stride_, stream()));
+    run_precompute();                        // gauss_newton.t:1190-1191
     prev_cost_ = compute_cost();
     {   // initX = X (copyUnknownwise)
         int dir = 0;
@@ -853,6 +882,7 @@ int Plan::step(void** params) {
         void* a[] = {P, V};
         launch_flat(fn("th_update"), a);   // PCGLinearUpdate
     }
+    run_precompute();                        // gauss_newton.t:1701
     int ret = 1;
     if (d_.lm) {
         const double new_cost = compute_cost();   // also brings modelcost and lin_done back
@@ -881,6 +911,7 @@ int Plan::step(void** params) {
             int one = 1;
             void* a[] = {P, &vecs_[V_PREVX], &one};
             launch_flat(fn("th_copy_x"), a);   // revertUpdate
+            run_precompute();                // gauss_newton.t:1748
             radius_ = round_real(radius_ / decrease_factor_);
             decrease_factor_ = round_real(2.0 * decrease_factor_);
             if (radius_ < round_real(sp_.min_trust_region_radius)) {

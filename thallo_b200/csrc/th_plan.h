@@ -45,7 +45,9 @@ struct PlanDesc {
     int ncoef = 0;
     bool tiled = false;
     int tile[3] = {1, 1, 1}, halo[3] = {0, 0, 0};
+    std::vector<std::pair<long long, int>> computed;   // ComputedArrays: (elements, gradient channels); ptr_pidx = -(100 + 2k [+ 1 for the gradient image])
     int smem_bytes = 0;
+    int pipe = 2;                           // shared-memory pipeline stages of th_pcg_a (TMA variant)
     std::vector<VTileDesc> vtiles;
     std::vector<StageDesc> stages;
     // multi-GPU slab partition ("partition" line): ghost layers of the slowest axis included in dims
@@ -163,6 +165,8 @@ private:
     struct Adjacency { const void* src = nullptr; unsigned long long checksum = 0; bool valid = false; int* ptr = nullptr; int* perm = nullptr; };
     std::vector<Adjacency> adj_;
     std::vector<void*> jvals_, jp_, scoef_;
+    std::vector<void*> computed_;  // value image, gradient image per ComputedArray (2 entries each)
+    void run_precompute();         // gpu.precompute, gauss_newton.t:979-986
     std::vector<char> gather_buf_;          // host image of the device struct ThGather
     unsigned long long* d_checksum_ = nullptr;
     void build_adjacency(bool verify_contents);

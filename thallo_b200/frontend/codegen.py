@@ -21,6 +21,7 @@ arguments are read: global memory with bounds checks, or TMA-staged shared-memor
 tiles) and a scatter sink `S` (how contributions are accumulated), both supplied
 by the hand-written skeleton in csrc/skeleton/.
 """
+import os
 from collections import namedtuple
 
 from . import ad
@@ -106,13 +107,31 @@ class _Term:
     def __init__(self, L, exp):
         self.exp = exp
         ukeys = set(im.name for im in L.images if im.kind == "unknown")
-        self.unknowns = ad.variables(exp, lambda v: isinstance(v.key, ImageAccess) and v.key.image in ukeys)
-        memo = {}
-        self.partials = [ad.derivative(exp, u) for u in self.unknowns]
+        direct = ad.variables(exp, lambda v: isinstance(v.key, ImageAccess) and v.key.image in ukeys)
+        partial = {}                     # unknown access key -> d exp / d unknown
+        order = []
+        for u in direct:
+            partial[u.key] = ad.derivative(exp, u)
+            order.append(u.key)
+        # chain rule through computed arrays: d exp/d C(index) * gradient image of C at the same index,
+        # for every unknown access C's expression contains, shifted to `index` (thallo.t:1551-1561,1742-1747)
+        computed = dict((im.name, im) for im in L.images if im.kind == "computed")
+        for c in ad.variables(exp, lambda v: isinstance(v.key, ImageAccess) and v.key.image in computed):
+            im = computed[c.key.image]
+            dc = ad.derivative(exp, c)
+            s = dict((comp[1], comp[2]) for comp in c.key.index)
+            for i, u in enumerate(im.gunknowns):
+                g = im.gradient_at(i, c.key.index)
+                if g.is_const(0.0):
+                    continue
+                k = _shift_key(u.key, s)
+                if k not in partial:
+                    partial[k] = ad.const(0.0)
+                    order.append(k)
+                partial[k] = partial[k] + dc * g
         # keep only structurally non-zero partials
-        keep = [(u, p) for u, p in zip(self.unknowns, self.partials) if not p.is_const(0.0)]
-        self.unknowns = [u for u, _ in keep]
-        self.partials = [p for _, p in keep]
+        self.unknowns = [ad.var(k) for k in order if not partial[k].is_const(0.0)]
+        self.partials = [partial[u.key] for u in self.unknowns]
 
     def jp(self, arg):
         r = ad.const(0.0)
@@ -189,6 +208,7 @@ class Generator:
         self.sparses = {s.name: s for s in L.sparses}
         self.unknowns = sorted([im for im in L.images if im.kind == "unknown"], key=lambda i: i.pidx)
         assert self.unknowns, "energy declares no unknowns"
+        self.computed = [im for im in L.images if im.kind == "computed"]      # ComputedArrays, in creation order
         # parameter slots
         self.ptr_slot, self.ptr_pidx = {}, []
         for obj in sorted(list(L.images) + list(L.sparses), key=lambda o: o.pidx):
@@ -230,6 +250,7 @@ class Generator:
         # tiled form of the unknownwise operator (shared-memory stencil tiles, TMA-staged): 2-D / 3-D image domains
         self.tiled = self.schedule == "at_output" and len(self.udomain) in (2, 3)
         self.stage_center = self.tiled and len(self.udomain) == 2    # also stage centre-only arrays (2-D: shared memory to spare)
+        self.tile_pad = os.environ.get("THALLO_B200_TILE_PAD", "1") != "0"      # tuning switch
         self.coef_exprs = []          # hoisted PCG-invariant per-element expressions (channels of the __coef image)
         self._coef_index = {}
 
@@ -425,13 +446,32 @@ class Generator:
         off = 0
         stages = []
 
+        def conflict_degree(channels, es, row_bytes):
+            """Worst shared-memory bank-conflict degree of one warp reading channel 0 of its elements
+            (thread x fastest, 4-byte banks, same-word reads broadcast)."""
+            worst = 1
+            nthreads = tile[0] * tile[1] * tile[2]
+            for w0 in range(0, nthreads, 32):
+                banks = {}
+                for t in range(w0, min(w0 + 32, nthreads)):
+                    tx, ty, tz = t % tile[0], (t // tile[0]) % tile[1], t // (tile[0] * tile[1])
+                    word = (tx * channels * es + ty * row_bytes + tz * row_bytes * ext[1]) // 4
+                    banks.setdefault(word % 32, set()).add(word)
+                worst = max(worst, max(len(v) for v in banks.values()))
+            return worst
+
         def place(channels, es):
             # TMA requires the innermost start coordinate of a box to be 16-byte aligned (measured on
             # B200: an unaligned start raises "illegal instruction"), so the left halo is padded to
-            # 16 bytes: a row is [padl | tile | right halo] scalars, rounded up to 16 bytes.
+            # 16 bytes: a row is [padl | tile | right halo] scalars, rounded up to 16 bytes.  Rows are
+            # then widened by up to 7 more 16-byte units when that lowers the bank-conflict degree of a
+            # warp that spans several rows (8-wide 3-D tiles with 128-byte rows: 4-way -> none).
             nonlocal off
             padl = -(-(H[0] * channels * es) // 16) * 16 // es
             row_bytes = -(-((padl + (tile[0] + H[0]) * channels) * es) // 16) * 16
+            if self.tile_pad:
+                cands = [row_bytes + 16 * k for k in range(8) if (row_bytes + 16 * k) // es <= 256]
+                row_bytes = min(cands, key=lambda rb: (conflict_degree(channels, es, rb), rb))
             roww = row_bytes // es
             nbytes = row_bytes * ext[1] * ext[2]
             o = off
@@ -476,7 +516,12 @@ class Generator:
             slot_stage[self.ptr_slot[name]] = len(stages)
             stages.append(dict(name=name, slot=self.ptr_slot[name], ctype=im.ctype, es=es, channels=im.channels,
                                roww=roww, off=o, bytes=nb, padl=padl, center=center))
-        self.tl = dict(tile=tile, halo=H, ext=ext, vt=vt, stages=stages, slot_stage=slot_stage, smem=off)
+        # pipeline depth of th_pcg_a: two stages when they fit beside the other resident CTAs
+        # (TH_PCG_A_MINB = 3 per SM, 227 KB of shared memory), else one
+        pipe = 2 if 2 * max(128, off) * 3 + 3 * 1024 <= 227 * 1024 else 1
+        if os.environ.get("THALLO_B200_PIPE"):
+            pipe = int(os.environ["THALLO_B200_PIPE"])
+        self.tl = dict(tile=tile, halo=H, ext=ext, vt=vt, stages=stages, slot_stage=slot_stage, smem=off, pipe=pipe)
         return self.tl
 
     def gen_unknownwise(self):
@@ -799,7 +844,7 @@ class Generator:
                         body.append("        " + call_mat)
                     else:
                         body.append("        ThIdx<dom_g%d> idx; idx.from_linear(e);" % gi)
-                        body.append("        GAcc<dom_g%d> a(idx, vec);" % gi)
+                        body.append("        GAcc<dom_g%d, TH_OWN_ENDPOINT ? %d : -1> a(idx, vec, t.lin);" % (gi, self.ptr_slot[ep["sparse"]]))
                         body.append("        " + call_free)
                     body.append("    }")
                     if mat:
@@ -970,6 +1015,7 @@ class Generator:
                 hdr.append("#define TH_TW %d\n#define TH_TH %d\n#define TH_TD %d" % tuple(tl["tile"]))
                 hdr.append("#define TH_HX %d\n#define TH_HY %d\n#define TH_HZ %d" % tuple(tl["halo"]))
                 hdr.append("#define TH_SMEM_BYTES %d" % max(128, tl["smem"]))
+                hdr.append("#define TH_PIPE %d" % tl["pipe"])
                 hdr.append("#define TH_NSTAGE %d" % len(tl["stages"]))
                 hdr.append("#define TH_STAGE_TABLE {%s}" % (", ".join(
                     "{%d, %d, %d, %d, %d, %d, %d, %d}" % (st["slot"], st["es"], st["channels"], st["roww"], st["off"], st["padl"],
@@ -1008,6 +1054,21 @@ class Generator:
             hdr.append("#define TH_SCOEF_LIST(X) %s" % " ".join("X(%d)" % si for si in range(len(self.spaces)) if self.scoef[si]))
         if self.schedule != "at_output":
             hdr.append("#define TH_TILED 0\n#define TH_NCOEF 0")
+        # ComputedArrays: value + gradient channels of one element (createprecomputed, thallo.t:4046-4094)
+        hdr.append("#define TH_NCOMPUTED %d" % len(self.computed))
+        if self.computed:
+            assert self.partition is None, "computed arrays are not supported by the multi-GPU slab partition yet"
+            rows = []
+            for k, ca in enumerate(self.computed):
+                grads = [g for g, ch in zip(ca.gradients, ca.gchannel) if ch >= 0]
+                ng = len(grads)
+                body.append(self._fn(
+                    "template <class A> __device__ __forceinline__ void precompute_c%d(const A& a, const Params& P, real* __restrict__ out)" % k,
+                    [ca.expression] + grads, lambda r: ["out[%d] = %s;" % (i, x) for i, x in enumerate(r)],
+                    tuple(d.idx for d in ca.dims)))
+                rows.append("{%d, %d, %d}" % (self.ptr_slot[ca.name], self.ptr_slot[ca.gradient_image.name] if ng else -1, ng))
+            hdr.append("#define TH_COMPUTED_TABLE {%s}" % ", ".join(rows))
+            hdr.append("#define TH_COMPUTED_LIST(X) %s" % " ".join("X(%d)" % k for k in range(len(self.computed))))
         hdr.append("#define TH_GROUP_LIST(X) %s" % " ".join(gl))
         # group domain table
         rows = []
@@ -1030,6 +1091,8 @@ class Generator:
         if self.schedule == "gather":
             for si, sp in enumerate(self.spaces):
                 doms.append(dom_struct("dom_s%d" % si, list(sp["dims"])))
+        for k, ca in enumerate(self.computed):
+            doms.append(dom_struct("dom_c%d" % k, [x.idx for x in ca.dims]))
         src = ("\n".join(hdr) + "\n#include \"thallo_prelude.cuh\"\nnamespace th {\n" + "\n".join(doms) + "\n"
                + "\n".join(body) + "\n} // namespace th\n")
         if gather_b:
@@ -1048,6 +1111,7 @@ class Generator:
                          count=_prod(L.dims[x].size for x in g["domain"]), materialize=int(g["materialize"]),
                          nnz_per_elem=g["nnz_per_elem"], row_nnz=g["row_nnz"]) for g in self.groups],
         )
+        d["computed"] = [dict(elements=ca.elements, ngrad=sum(1 for ch in ca.gchannel if ch >= 0)) for ca in self.computed]
         if self.schedule == "gather":
             d["gather"] = dict(
                 spaces=[dict(elements=sp["elements"], lanes=sp["lanes"], nslots=sp["nslots"]) for sp in self.spaces],
@@ -1098,6 +1162,8 @@ def descriptor_text(d):
         ln.append("group %s %d %d %d %d %d %s | %s" % (g["name"], g["count"], g["nterms"], g["materialize"], g["nnz_per_elem"],
                                                       len(g["domain"]), " ".join(map(str, g["domain"])),
                                                       " ".join(map(str, g["row_nnz"]))))
+    for k, c in enumerate(d.get("computed", [])):
+        ln.append("computed %d %d %d" % (k, c["elements"], c["ngrad"]))
     if d["schedule"] == "gather":
         ga = d["gather"]
         for sp in ga["spaces"]:
@@ -1116,7 +1182,7 @@ def descriptor_text(d):
             ln.append("partition %d %d" % tuple(d["partition"]))
         if d.get("tiled"):
             tl = d["tile"]
-            ln.append("tile %s %s %d" % (" ".join(map(str, tl["tile"])), " ".join(map(str, tl["halo"])), max(128, tl["smem"])))
+            ln.append("tile %s %s %d %d" % (" ".join(map(str, tl["tile"])), " ".join(map(str, tl["halo"])), max(128, tl["smem"]), tl["pipe"]))
             for v in tl["vt"]:
                 ln.append("vtile %d %d %d %d %d %d %d %d" % (v["roww"], v["zoff"], v["poff"], v["bytes"], v["padl"], v["coff"],
                                                              v["croww"], v["cbytes"]))

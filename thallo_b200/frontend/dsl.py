@@ -122,6 +122,54 @@ class Image:
         return "%s<%s%d>" % (self.name, self.ctype, self.channels)
 
 
+class ComputedArray(Image):
+    """`exp:get(...)` (reference thallo.t:1777-1822,1868-1893): the expression is stored as a
+    plan-owned single-channel image over its index domains, re-evaluated by the `precompute`
+    pass whenever the unknowns change, together with a gradient image holding its partial
+    derivatives with respect to the unknown accesses it contains (one channel per unknown;
+    constant derivatives are not stored, thallo.t:1551-1561).  Residuals read both images
+    like ordinary arrays (zero outside the domain); the chain rule runs through the gradient image."""
+
+    def __init__(self, L, k, exp):
+        dims = sorted(set(c[1] for v in ad.variables(exp) for c in _dense_components(v.key)))
+        assert dims, "computed array without index domains"
+        Image.__init__(self, "StoredExp_%d" % k, "real", 1, [L.dims[d] for d in dims], -(100 + 2 * k), "computed")
+        if exp.type == ad.BOOL:
+            exp = ad.select(exp, 1.0, 0.0)
+        self.expression = exp
+        ukeys = set(im.name for im in L.images if im.kind == "unknown")
+        assert not ad.variables(exp, lambda v: isinstance(v.key, ImageAccess) and v.key.image.startswith("StoredExp_")), \
+            "nested computed arrays are not supported"
+        self.gunknowns = ad.variables(exp, lambda v: isinstance(v.key, ImageAccess) and v.key.image in ukeys)
+        self.gradients = [ad.derivative(exp, u) for u in self.gunknowns]
+        self.gchannel, n = [], 0                 # stored channel of every unknown's derivative (-1: constant, not stored)
+        for g in self.gradients:
+            if g.kind == "const":
+                self.gchannel.append(-1)
+            else:
+                self.gchannel.append(n)
+                n += 1
+        self.gradient_image = None
+        if n:
+            self.gradient_image = Image(self.name + "_gradient", "real", n, self.dims, -(101 + 2 * k), "computed_gradient")
+
+    def gradient_at(self, i, index):
+        """d(stored value at `index`) / d(unknown i shifted to `index`)."""
+        if self.gchannel[i] < 0:
+            return self.gradients[i]
+        return ad.var(ImageAccess(self.gradient_image.name, index, self.gchannel[i]))
+
+
+def _dense_components(key):
+    if isinstance(key, (ImageAccess, VecArg)):
+        return [c for c in key.index if c[0] == "d"]
+    if isinstance(key, Bounds):
+        return [("d", d, 0) for (d, lo, hi) in key.ranges]
+    if isinstance(key, IndexValue):
+        return [("d", key.dim, 0)]
+    return []
+
+
 class Sparse:
     def __init__(self, name, frm, to, pidx):
         self.name, self.frm, self.to, self.pidx = name, list(frm), list(to), pidx
@@ -191,6 +239,17 @@ class SymbolicL:
         self.dims, self.images, self.sparses, self.params = [], [], [], []
         self.usepreconditioner = False       # thallo.t:115
         self.residuals = None
+        self.computed = {}                   # expression id -> ComputedArray (ComputedArrayCache, thallo.t:69,1879-1885)
+
+    def computed_get(self, exp, idx):
+        ca = self.computed.get(exp.id)
+        if ca is None:
+            ca = ComputedArray(self, len(self.computed), exp)
+            self.computed[exp.id] = ca
+            self.images.append(ca)
+            if ca.gradient_image is not None:
+                self.images.append(ca.gradient_image)
+        return ca(*idx)
 
     def Dims(self, *names):
         assert len(names) <= len(self.dim_sizes), "energy needs %d dimensions, got %d" % (len(names), len(self.dim_sizes))
@@ -306,6 +365,10 @@ class SymbolicL:
 def build_spec(define, dim_sizes, **kw):
     """Run an energy definition symbolically; returns the populated SymbolicL."""
     L = SymbolicL(dim_sizes)
-    define(L, **kw)
+    ad.Exp.get = lambda self, *idx: L.computed_get(self, idx)       # exp:get(...) binds to the problem being defined
+    try:
+        define(L, **kw)
+    finally:
+        del ad.Exp.get
     assert L.residuals is not None, "energy did not call Residuals{}"
     return L

@@ -51,6 +51,12 @@ class Interp:
                                                  for v in self.eval(self.gen.coef_exprs)], axis=-1)
             return self.cache["__coef"]
         im = self.gen.images[name]
+        if im.kind in ("computed", "computed_gradient"):     # plan-owned ComputedArray images: evaluate `precompute` in place
+            if name not in self.cache:
+                ca = im if im.kind == "computed" else self.gen.images[name[:-len("_gradient")]]
+                roots = [ca.expression] if im.kind == "computed" else [g for g, ch in zip(ca.gradients, ca.gchannel) if ch >= 0]
+                self.cache[name] = np.stack([np.broadcast_to(v, self.shape).astype(self.dt) for v in self.eval(roots)], axis=-1)
+            return self.cache[name]
         a = np.asarray(self.params[im.pidx]).astype(self.dt).reshape(self.shape + (im.channels,))
         return a
 

@@ -245,3 +245,43 @@ def bundle_adjustment_inputs(C, P, obs_per_point=5, seed=1, noise_px=0.5, pertur
 
 def bundle_adjustment_params(d):
     return [d["cameras"], d["points"], d["observations"], d["oToC"], d["oToP"]]
+
+
+def sfs_inputs(W, H, seed=1, w_p=100.0, w_s=100.0, w_g=1.0):
+    """Config 3b synthetic shape: target depth = spherical cap over a plane at 0.5 with
+    a seeded 0.1 % ripple, invalid (-10000, what the reference's loader turns -inf into,
+    examples/shape_from_shading/src/SimpleBuffer.cpp:30-40) outside a centred ellipse; initial depth =
+    target + seeded noise on valid pixels; target intensity = band-limited texture in (0, 1); edge
+    masks all 1; intrinsics f = W, u = (W/2, H/2); lighting and weights as in the reference's
+    data/shape_from_shading/default.SFSSolverParameters (w_p 100, w_s 100, w_g 1)."""
+    ys, xs = np.mgrid[0:H, 0:W].astype(np.float64)
+    u, v = (xs - W / 2.0) / (W / 2.0), (ys - H / 2.0) / (H / 2.0)
+    r2 = u * u + v * v
+    depth = 0.5 - 0.08 * np.sqrt(np.maximum(0.0, 1.0 - np.minimum(r2, 1.0)))
+    depth += 0.0005 * np.sin(0.37 * xs + 0.11 * ys) * np.cos(0.23 * ys - 0.05 * xs)
+    valid = r2 < 0.81
+    D = np.where(valid, depth, -10000.0)
+    rng = np.random.RandomState(seed)
+    X0 = np.where(valid, depth + 0.0008 * rng.standard_normal((H, W)), -10000.0)
+    Im = 0.5 + 0.2 * np.sin(0.05 * xs + 0.02 * ys) + 0.15 * np.cos(0.031 * ys - 0.017 * xs) + 0.05 * np.sin(0.4 * xs) * np.sin(0.3 * ys)
+    f = lambda a: np.ascontiguousarray(a.reshape(-1), np.float32)
+    light = [0.6908317804336548, 0.044598858803510666, 0.01812959648668766, -0.1773163229227066, -0.04067882522940636,
+             0.14467650651931763, 0.02393525093793869, -0.24658696353435516, 0.005797004792839289]
+    return dict(w_p=w_p, w_s=w_s, w_g=w_g, f_x=float(W), f_y=float(W), u_x=W / 2.0, u_y=H / 2.0, light=light,
+                X=f(X0), D_i=f(D), Im=f(Im), edgeMaskR=np.ones(W * H, np.uint8), edgeMaskC=np.ones(W * H, np.uint8))
+
+
+def sfs_params(d):
+    """problemparams of energies/shape_from_shading.py: slots 0-15 host scalars, 16-20 images."""
+    sc = [d["w_p"], d["w_s"], d["w_g"], d["f_x"], d["f_y"], d["u_x"], d["u_y"]] + list(d["light"])
+    return [np.array([x], np.float32) for x in sc] + [d["X"], d["D_i"], d["Im"], d["edgeMaskR"], d["edgeMaskC"]]
+
+
+def sfs_fixture_inputs(path):
+    """The crop of the reference's own shape_from_shading input committed under tests/golden/
+    (made by tests/golden/make_sfs_fixture.py)."""
+    z = np.load(path)
+    return dict(w_p=float(z["w_p"]), w_s=float(z["w_s"]), w_g=float(z["w_g"]), f_x=float(z["f_x"]), f_y=float(z["f_y"]),
+                u_x=float(z["u_x"]), u_y=float(z["u_y"]), light=[float(x) for x in z["light"]],
+                X=z["X"].astype(np.float32), D_i=z["D_i"].astype(np.float32), Im=z["Im"].astype(np.float32),
+                edgeMaskR=z["edgeMaskR"].astype(np.uint8), edgeMaskC=z["edgeMaskC"].astype(np.uint8)), int(z["W"]), int(z["H"])
