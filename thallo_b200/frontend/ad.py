@@ -10,10 +10,24 @@ Not a port: the reference canonicalises n-ary sum/prod/powc with polynomial
 simplification and then schedules instructions for register pressure itself;
 here nvcc/NVRTC does CSE and scheduling, so the DAG stays binary and the emitter
 is a plain topological walk.
+
+What the constructors do normalise (the role of ad.t:841-964 `polysimplify` for the
+patterns the operators are made of -- guarded, weighted sums of partial * vector):
+  * guards move outward:  select(c,x,0)*y -> select(c,x*y,0);  select(c,x,0)*select(d,y,0) ->
+    select(c&&d, x*y, 0);  select(c,x,0) +- select(c,y,0) -> select(c, x+-y, 0);
+    select(c, select(d,x,0), 0) -> select(c&&d, x, 0).  Every partial derivative of a bounds- or
+    mask-guarded residual carries the guard; J p and partial * (J p) then cost one select per
+    residual instead of one per partial.  Values are unchanged wherever the operands are finite.
+  * uniform factors (constants, scalar Params) move to the outside-left of products and out of
+    guards, and a common uniform factor is taken out of a sum:  w*x + w*y -> w*(x+y).
+  * multiplication by -1 becomes subtraction where a sum absorbs it.
+Set THALLO_B200_SIMPLIFY=0 to switch these rewrites off (tuning / bisecting).
 """
 import math
+import os
 
 REAL, BOOL = "real", "bool"
+SIMPLIFY = os.environ.get("THALLO_B200_SIMPLIFY", "1") != "0"
 
 _UNARY = ("sqrt", "sin", "cos", "tan", "exp", "log", "abs", "asin", "acos", "atan", "sinh", "cosh", "tanh")
 _CMP = ("eq", "neq", "less", "greater", "lesseq", "greatereq")
@@ -97,6 +111,47 @@ def _apply(op, args, type_=REAL, const_=None):
     return Exp._make("apply", op=op, args=args, type_=type_, const=const_)
 
 
+def _uniform(e):
+    """Same value for every element of a launch: a constant or a scalar Param."""
+    return e.kind == "const" or (e.kind == "var" and type(e.key).__name__ == "Param")
+
+
+def _urank(e):
+    return -1 if e.kind == "const" else e.id
+
+
+def _guard(e):
+    """(c, x) if e is select(c, x, 0), else None."""
+    if e.kind == "apply" and e.op == "select" and e.args[2].is_const(0.0):
+        return e.args[0], e.args[1]
+    return None
+
+
+def _ufactor(e):
+    """(w, x) if e is w*x with w uniform, else None."""
+    if e.kind == "apply" and e.op == "mul" and _uniform(e.args[0]):
+        return e.args
+    return None
+
+
+def _addsub(op, a, b):
+    """Rewrites shared by add and sub; None when none applies."""
+    if not SIMPLIFY:
+        return None
+    f = add if op == "add" else sub
+    ga, gb = _guard(a), _guard(b)
+    if ga and gb and ga[0] is gb[0]:
+        return select(ga[0], f(ga[1], gb[1]), 0.0)
+    fa, fb = _ufactor(a), _ufactor(b)
+    if fa and fb and fa[0] is fb[0]:
+        return mul(fa[0], f(fa[1], fb[1]))
+    if fb and fb[0].is_const(-1.0):                     # x + (-1)*y -> x - y;  x - (-1)*y -> x + y
+        return (sub if op == "add" else add)(a, fb[1])
+    if op == "add" and fa and fa[0].is_const(-1.0):     # (-1)*x + y -> y - x
+        return sub(b, fa[1])
+    return None
+
+
 def add(a, b):
     a, b = toexp(a), toexp(b)
     if a.type == BOOL: a = select(a, 1.0, 0.0)
@@ -107,6 +162,9 @@ def add(a, b):
     if b.is_const(0.0): return a
     if a.is_const():          # constants to the right, canonical order
         a, b = b, a
+    r = _addsub("add", a, b)
+    if r is not None:
+        return r
     return _apply("add", (a, b))
 
 
@@ -119,6 +177,9 @@ def sub(a, b):
     if b.is_const(0.0): return a
     if a.is_const(0.0): return mul(-1.0, b)
     if a is b: return const(0.0)
+    r = _addsub("sub", a, b)
+    if r is not None:
+        return r
     return _apply("sub", (a, b))
 
 
@@ -139,6 +200,26 @@ def mul(a, b):
         a, b = b, a                                   # constant first
     if a.is_const() and b.kind == "apply" and b.op == "mul" and b.args[0].is_const():
         return mul(const(a.value * b.args[0].value), b.args[1])
+    if SIMPLIFY:
+        if _uniform(b) and not _uniform(a):
+            a, b = b, a                               # uniform factor first
+        if _uniform(a):
+            fb = _ufactor(b)
+            if fb and _urank(fb[0]) < _urank(a):      # uniform factors ordered: constants, then Params by id
+                return mul(fb[0], mul(a, fb[1]))
+        else:
+            fa, fb = _ufactor(a), _ufactor(b)
+            if fa:                                    # (w*x)*y -> w*(x*y)
+                return mul(fa[0], mul(fa[1], b))
+            if fb:                                    # x*(w*y) -> w*(x*y)
+                return mul(fb[0], mul(a, fb[1]))
+            ga, gb = _guard(a), _guard(b)
+            if ga and gb:
+                return select(and_(ga[0], gb[0]), mul(ga[1], gb[1]), 0.0)
+            if ga:
+                return select(ga[0], mul(ga[1], b), 0.0)
+            if gb:
+                return select(gb[0], mul(a, gb[1]), 0.0)
     return _apply("mul", (a, b))
 
 
@@ -188,6 +269,15 @@ def select(c, a, b):
         a = a.args[1]
     if b.kind == "apply" and b.op == "select" and b.args[0] is c:
         b = b.args[2]
+    if SIMPLIFY and b.is_const(0.0):
+        if a.is_const(0.0):
+            return a
+        ga = _guard(a)
+        if ga:                                        # select(c, select(d, x, 0), 0) -> select(c && d, x, 0)
+            return select(and_(c, ga[0]), ga[1], 0.0)
+        fa = _ufactor(a)
+        if fa:                                        # select(c, w*x, 0) -> w*select(c, x, 0)
+            return mul(fa[0], select(c, fa[1], 0.0))
     return _apply("select", (c, a, b))
 
 
