@@ -64,6 +64,16 @@ int ThalloB200_PlanIpcHandle(Thallo_State* state, Thallo_Plan* plan, void* handl
 int ThalloB200_PlanConnect(Thallo_State* state, Thallo_Plan* plan, const void* handle_lo, long long extent_lo,
                            const void* handle_hi, long long extent_hi);
 
+/* Known-answer tests of the warp primitives behind the residualwise scatter path (ballot, peer
+ * discovery by key, by-key reduction before the atomic), written after the reference's
+ * tests/cuda_unit_tests/{ballot,get_peers,reduce_peers}.t; one warp each on the current device.
+ *   which = 0  ballot:       out[0] = max over lanes of ballot(lane id)            (reference asserts 0xfffffffe)
+ *   which = 1  get_peers:    out[0] = sum over lanes of (peers(lane % 4) & 0xff)   (reference asserts 255*32/4)
+ *   which = 2  reduce_peers: out[k] = float sums, out[nkeys + k] = double sums of the lane ids with lane % nkeys == k
+ *                                                                                  (reference, nkeys = 4: 112 + 8 k)
+ * `out` receives up to `capacity` doubles.  Returns the number written, or -1 on failure. */
+int ThalloB200_WarpSelfTest(int which, int nkeys, double* out, int capacity);
+
 /* Last error message of this thread ("" if none). */
 const char* ThalloB200_LastError(void);
 

@@ -64,3 +64,10 @@ def test_double_precision_compiles():
     low = codegen.lower(energies.load("image_warping"), [64, 64], "levenberg_marquardt", "image_warping", True)
     ok, log, size = api.compile_only(low.source)
     assert ok, log[-4000:]
+
+
+def test_warp_primitive_known_answer_kernels_compile():
+    # the translation unit ThalloB200_WarpSelfTest runs on a GPU box (tests/test_gpu_warp.py)
+    ok, log, size = api.compile_only('#define TH_WARP_KAT 1\n#include "thallo_warp.cuh"\n')
+    assert ok, log[-2000:]
+    assert size > 1000

@@ -1,0 +1,71 @@
+"""Known-answer tests of the warp primitives behind the residualwise scatter path, with the
+reference's own expected values (KAT-3..5: tests/cuda_unit_tests/ballot.t:11, get_peers.t:12,
+reduce_peers.t:12-16), and parity of the warp-aggregated scatter with the plain one atomic per
+contribution form on a graph energy."""
+import os
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+
+from thallo_b200 import api
+from thallo_b200 import workloads as wl
+
+pytestmark = pytest.mark.gpu
+
+from _parity import dev
+
+
+def test_kat3_ballot():
+    (v,) = api.warp_self_test(0)
+    assert int(v) == 0xFFFFFFFE            # the reference reads it back as a signed int: -2
+
+
+def test_kat4_get_peers():
+    (v,) = api.warp_self_test(1)
+    assert int(v) == 255 * 32 // 4
+
+
+@pytest.mark.parametrize("nkeys", [4, 1, 3, 7, 32])
+def test_kat5_reduce_peers(nkeys):
+    out = api.warp_self_test(2, nkeys)
+    want = [float(sum(l for l in range(32) if l % nkeys == k)) for k in range(nkeys)]
+    if nkeys == 4:
+        assert want == [112.0 + 8 * i for i in range(4)]       # reduce_peers.t:15
+    assert out[:nkeys] == want             # float sums (small integers: exact)
+    assert out[nkeys:] == want             # double sums
+
+
+def _solve(schedule, opts):
+    from thallo_b200.api import ThalloSolver
+    old = os.environ.get("THALLO_B200_NVRTC_OPTS")
+    if opts:
+        os.environ["THALLO_B200_NVRTC_OPTS"] = opts
+    try:
+        nx, ny = 40, 30
+        d = wl.arap_mesh_inputs(nx, ny)
+        dims = [nx * ny, len(d["V0"])]
+        pg = wl.arap_mesh_params(d)
+        dp = [dev(p) if i >= 2 else p for i, p in enumerate(pg)]
+        s = ThalloSolver(dims, "arap_mesh_deformation", "levenberg_marquardt", schedule=schedule)
+        s.set_parameters(nIterations=3, lIterations=20)
+        s.init(dp)
+        c = [s.current_cost()]
+        while s.step():
+            c.append(s.current_cost())
+        s.close()
+        return np.array(c)
+    finally:
+        if old is None:
+            os.environ.pop("THALLO_B200_NVRTC_OPTS", None)
+        else:
+            os.environ["THALLO_B200_NVRTC_OPTS"] = old
+
+
+def test_warp_aggregated_scatter_matches_plain_atomics():
+    agg = _solve("residualwise", "")
+    plain = _solve("residualwise", "-DTH_WARP_AGG=0")
+    assert len(agg) == len(plain)
+    # both forms add the same contributions; only the order of the float additions differs
+    np.testing.assert_allclose(agg, plain, rtol=2e-5)

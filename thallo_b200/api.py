@@ -83,10 +83,21 @@ def lib():
     L.ThalloB200_PlanIpcHandle.argtypes = [vp, vp, vp, C.POINTER(C.c_longlong)]
     L.ThalloB200_PlanConnect.restype = C.c_int
     L.ThalloB200_PlanConnect.argtypes = [vp, vp, vp, C.c_longlong, vp, C.c_longlong]
+    L.ThalloB200_WarpSelfTest.restype = C.c_int
+    L.ThalloB200_WarpSelfTest.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_double), C.c_int]
     L.ThalloB200_LastError.restype, L.ThalloB200_LastError.argtypes = cp, []
     L.ThalloB200_Version.restype, L.ThalloB200_Version.argtypes = cp, []
     _lib = L
     return L
+
+
+def warp_self_test(which, nkeys=4):
+    """Known-answer tests of the warp primitives (include/thallo_b200.h ThalloB200_WarpSelfTest)."""
+    out = (C.c_double * 64)()
+    n = lib().ThalloB200_WarpSelfTest(int(which), int(nkeys), out, 64)
+    if n < 0:
+        raise RuntimeError("ThalloB200_WarpSelfTest failed: " + lib().ThalloB200_LastError().decode())
+    return [out[i] for i in range(n)]
 
 
 def compile_only(source):

@@ -3,8 +3,14 @@
 // per-energy device functions (namespace th) and before the generated gather functions and
 // thallo_kernels.cuh.
 #pragma once
+#include "thallo_warp.cuh"
 
 #define TH_BLOCK 256
+// residualwise scatters through a sparse index array: reduce the contributions of the lanes of a
+// warp that target the same unknown element before the atomic (thallo.t:3361-3402)
+#ifndef TH_WARP_AGG
+#define TH_WARP_AGG 1
+#endif
 
 // ------------------------------------------------------------------ index helpers
 template <class Dom> struct ThIdx {
@@ -111,10 +117,23 @@ template <class Dom, int OWNSP = -1> struct GAcc {
 // ------------------------------------------------------------------ scatter sink (atomics)
 // WHICH selects the target vector (0: r / Ap / Adelta, 1: preconditioner diagonal);
 // out-of-bounds targets are dropped (thallo.t:3355-3390).
+// Sparse targets: `prepare<SP>` (emitted once per index array by the front end, before the
+// first scatter through it) loads this element's target and finds the lanes of the warp that hit
+// the same target -- one MATCH per endpoint, shared by all of its channels; `sadd` then sums the
+// peers' contributions with shuffles and lets the lowest peer issue the single atomic.
 template <class Dom> struct GScatter {
     ThIdx<Dom> i;
     real* t0; real* t1;
-    __device__ __forceinline__ GScatter(const ThIdx<Dom>& idx, real* a, real* b) : i(idx), t0(a), t1(b) {}
+    unsigned active;
+    long long se[TH_NPTR];
+    unsigned peers[TH_NPTR];
+    __device__ __forceinline__ GScatter(const ThIdx<Dom>& idx, real* a, real* b) : i(idx), t0(a), t1(b), active(__activemask()) {}
+    template <int SP> __device__ __forceinline__ void prepare(const Params& P) {
+        se[SP] = (long long)__ldg(((const int*)P.ptr[SP]) + i.lin);
+#if TH_WARP_AGG
+        peers[SP] = th_get_peers(active, (int)se[SP]);
+#endif
+    }
     template <int WHICH, int K, int CH, int O0, int O1, int O2> __device__ __forceinline__ void add(real val) {
         const int x = i.c[0] + O0, y = i.c[1] + O1, z = i.c[2] + O2;
         bool ok = x >= 0 && x < Dom::D0;
@@ -125,8 +144,12 @@ template <class Dom> struct GScatter {
         atomicAdd((WHICH ? t1 : t0) + TH_UIMG[K].offset + e * TH_UIMG[K].channels + CH, val);
     }
     template <int WHICH, int K, int CH, int SP> __device__ __forceinline__ void sadd(const Params& P, real val) {
-        const long long e = (long long)__ldg(((const int*)P.ptr[SP]) + i.lin);
-        atomicAdd((WHICH ? t1 : t0) + TH_UIMG[K].offset + e * TH_UIMG[K].channels + CH, val);
+        real* dst = (WHICH ? t1 : t0) + TH_UIMG[K].offset + se[SP] * TH_UIMG[K].channels + CH;
+#if TH_WARP_AGG
+        th_reduce_peers_atomic(active, dst, val, peers[SP]);
+#else
+        atomicAdd(dst, val);
+#endif
     }
 };
 

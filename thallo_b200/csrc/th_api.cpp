@@ -225,6 +225,48 @@ int ThalloB200_PlanConnect(Thallo_State*, Thallo_Plan* plan, const void* handle_
                            long long extent_hi) {
     return plan ? plan->plan->connect(handle_lo, extent_lo, handle_hi, extent_hi) : 1;
 }
+int ThalloB200_WarpSelfTest(int which, int nkeys, double* out, int capacity) {
+    if (!out || capacity <= 0 || which < 0 || which > 2) return -1;
+    if (nkeys < 1 || nkeys > 32) nkeys = 4;
+    const DriverApi& drv = DriverApi::get();
+    if (!drv.ok) { set_error("no CUDA device / driver available"); return -1; }
+    std::vector<char> cubin;
+    std::string log;
+    if (!compile_cubin("#define TH_WARP_KAT 1\n#include \"thallo_warp.cuh\"\n", skeleton_dir(), cubin, log)) {
+        set_error("warp self-test: NVRTC failed:\n" + log);
+        return -1;
+    }
+    CUmodule mod = nullptr;
+    CUfunction fn = nullptr;
+    const char* names[3] = {"th_kat_ballot", "th_kat_get_peers", "th_kat_reduce_peers"};
+    if (drv.ModuleLoadData(&mod, cubin.data()) != CUDA_SUCCESS || drv.ModuleGetFunction(&fn, mod, names[which]) != CUDA_SUCCESS) {
+        set_error("warp self-test: module load failed");
+        if (mod) drv.ModuleUnload(mod);
+        return -1;
+    }
+    unsigned char* dbuf = nullptr;                    // [32 x float/unsigned | 32 x double]
+    const size_t bytes = 32 * 4 + 32 * 8;
+    int written = -1;
+    if (cudaMalloc((void**)&dbuf, bytes) == cudaSuccess && cudaMemset(dbuf, 0, bytes) == cudaSuccess) {
+        void* a0 = dbuf;
+        void* a1 = dbuf + 32 * 4;
+        void* args[3] = {&a0, &a1, &nkeys};
+        if (drv.LaunchKernel(fn, 1, 1, 1, 32, 1, 1, 0, nullptr, args, nullptr) == CUDA_SUCCESS && cudaDeviceSynchronize() == cudaSuccess) {
+            unsigned char h[32 * 4 + 32 * 8];
+            if (cudaMemcpy(h, dbuf, bytes, cudaMemcpyDeviceToHost) == cudaSuccess) {
+                written = 0;
+                if (which < 2) out[written++] = (double)*(const unsigned*)h;
+                else {
+                    for (int k = 0; k < nkeys && written < capacity; ++k) out[written++] = (double)((const float*)h)[k];
+                    for (int k = 0; k < nkeys && written < capacity; ++k) out[written++] = ((const double*)(h + 32 * 4))[k];
+                }
+            }
+        } else set_error("warp self-test: launch failed");
+    }
+    if (dbuf) cudaFree(dbuf);
+    drv.ModuleUnload(mod);
+    return written;
+}
 const char* ThalloB200_LastError(void) { return g_last_error.c_str(); }
 const char* ThalloB200_Version(void) { return "thallo_b200 0.1.0 (sm_100a)"; }
 

@@ -81,7 +81,8 @@ bool compile_cubin(const std::string& source, const std::string& include_dir, st
                    const std::vector<std::string>& extra_opts) {
     // cache key: source + skeleton headers + options
     std::string key_src = source + "\n//--\n" + read_file(include_dir + "/thallo_prelude.cuh") + "\n//--\n" +
-                          read_file(include_dir + "/thallo_access.cuh") + "\n//--\n" + read_file(include_dir + "/thallo_kernels.cuh");
+                          read_file(include_dir + "/thallo_access.cuh") + "\n//--\n" + read_file(include_dir + "/thallo_kernels.cuh") +
+                          "\n//--\n" + read_file(include_dir + "/thallo_warp.cuh");
     for (auto& o : extra_opts) key_src += "\n" + o;
     const size_t h1 = std::hash<std::string>{}(key_src);
     const size_t h2 = std::hash<std::string>{}(key_src + "#salt");

@@ -924,10 +924,13 @@ class Generator:
                 tgmap[key][1] = tgmap[key][1] + p * p
         roots = [tgmap[k][0] for k in tg] + [tgmap[k][1] for k in tg]
         n = len(tg)
+        # one `prepare` per sparse index array the targets go through (target element + warp peers)
+        sps = sorted(set(self.ptr_slot[k.index[0][1]] for k in tg if k.index[0][0] == "s"))
+        prep = ["s.template prepare<%d>(P);" % sp for sp in sps]
         src.append(self._fn(
             "template <class A, class S> __device__ __forceinline__ void evalJTF_g%d(const A& a, const Params& P, S& s)" % gi,
             roots,
-            lambda r: [self._scatter_stmt(0, tg[i], r[i], dom) for i in range(n)] +
+            lambda r: prep + [self._scatter_stmt(0, tg[i], r[i], dom) for i in range(n)] +
                       [self._scatter_stmt(1, tg[i], r[n + i], dom) for i in range(n)], dom))
         # applyJTJ scatter: Ap[u] += partial*Jp
         tmap = {}
@@ -938,7 +941,7 @@ class Generator:
         roots = [tmap[k] for k in tg]
         src.append(self._fn(
             "template <class A, class S> __device__ __forceinline__ void applyJTJ_g%d(const A& a, const Params& P, S& s)" % gi,
-            roots, lambda r: [self._scatter_stmt(0, tg[i], r[i], dom) for i in range(n)], dom))
+            roots, lambda r: prep + [self._scatter_stmt(0, tg[i], r[i], dom) for i in range(n)], dom))
         # computeJ: partials term-major, unknown-minor; columns via accessor
         vals, cols = [], []
         for t in terms:
