@@ -110,7 +110,10 @@ def test_optical_flow_tiled_matches_oracle():
 
 # ---- computed arrays (shape_from_shading): precompute kernels, gradient images staged through the tiles (halo 2)
 def _sfs_params(d, dtype):
-    return [np.array(p, dtype=dtype) if np.asarray(p).dtype == np.float32 else p for p in wl.sfs_params(d)]
+    # images take the solver's precision; scalar Params are declared `float` in the energy
+    # (shape_from_shading.t:4-19) and stay float32 host scalars in both precisions
+    return [np.array(p, dtype=dtype) if (np.asarray(p).dtype == np.float32 and np.asarray(p).size > 1) else p
+            for p in wl.sfs_params(d)]
 
 
 @pytest.mark.parametrize("kind", ["gauss_newton", "levenberg_marquardt"])

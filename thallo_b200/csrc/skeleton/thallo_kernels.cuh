@@ -333,16 +333,26 @@ __device__ __forceinline__ void th_mbar_init(unsigned long long* bar, unsigned c
 __device__ __forceinline__ void th_mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(th_smem_u32(bar)), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void th_mbar_wait(unsigned long long* bar, unsigned parity) {
+// try_wait suspends the warp in hardware for a bounded time; between attempts the warp sleeps so that
+// a CTA waiting for its tile does not take issue slots from the CTAs that are computing
+// (profiles/r01i: the spin was 15 % of the executed instructions of the 3-D operator kernel)
+#ifndef TH_WAIT_SLEEP_NS
+#define TH_WAIT_SLEEP_NS 64
+#endif
+__device__ __forceinline__ bool th_mbar_try(unsigned long long* bar, unsigned parity) {
+    unsigned ok;
     asm volatile(
         "{\n"
         ".reg .pred P1;\n"
-        "LAB_WAIT:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
-        "@P1 bra DONE;\n"
-        "bra LAB_WAIT;\n"
-        "DONE:\n"
-        "}" ::"r"(th_smem_u32(bar)), "r"(parity) : "memory");
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, P1;\n"
+        "}" : "=r"(ok) : "r"(th_smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0u;
+}
+__device__ __forceinline__ void th_mbar_wait(unsigned long long* bar, unsigned parity) {
+    while (!th_mbar_try(bar, parity)) {
+        if (TH_WAIT_SLEEP_NS > 0) __nanosleep(TH_WAIT_SLEEP_NS);
+    }
 }
 // TMA: one bulk tensor copy of a whole (tile + halo) box into shared memory; coordinates may be
 // negative or run past the image, the hardware fills out-of-bounds elements with zeros -- exactly
@@ -754,9 +764,10 @@ __device__ constexpr ThSpace TH_SPACE[TH_NSPACES] = TH_SPACE_TABLE;
 __device__ constexpr ThSlot TH_SLOT[TH_NSPACES][TH_MAXSLOTS] = TH_SLOT_TABLE;
 __device__ constexpr int TH_NNZP[TH_NGROUPS] = TH_GROUP_NNZP;
 
-__device__ __forceinline__ real th_warp_sum_real(real v) {
+// sum over the LANES adjacent lanes that share one unknown element (LANES a power of two)
+template <int LANES> __device__ __forceinline__ real th_lanes_sum_real(real v) {
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    for (int o = LANES / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
 }
 
@@ -764,8 +775,10 @@ __device__ __forceinline__ real th_warp_sum_real(real v) {
 // n of (their partials at n) * (J p of that residual) [+ CtC p in LM], and <p, Ap>.  Replaces the
 // clear of Ap + PCGStep1 residualwise (gauss_newton.t:1006-1016) + PCGStep1_Finish (:774-799), and
 // for materialised groups the second (transposed) csrmv of cusparseJTJMatVec (:1497-1510).
-// One thread per unknown element, or one warp when many residuals meet at an element
-// (TH_SPACE[].lanes == 32, e.g. the cameras of bundle adjustment).  which = 1: Adelta = A delta.
+// TH_SPACE[].lanes adjacent lanes share one unknown element and split its adjacency list between
+// them: 1 for low-degree spaces whose walk is compute-bound, 2-8 to shorten the chain of dependent
+// loads (index -> neighbour data) each thread walks, 32 (a warp) when many residuals meet at an
+// element (the cameras of bundle adjustment).  which = 1: Adelta = A delta.
 #define TH_GATHER_KERNEL(SP)                                                                                        \
     extern "C" __global__ void __launch_bounds__(TH_BLOCK)                                                          \
     th_gather_s##SP(const __grid_constant__ Params P, const __grid_constant__ Vecs V,                               \
@@ -779,30 +792,32 @@ __device__ __forceinline__ real th_warp_sum_real(real v) {
         real* __restrict__ out = which ? V.Adelta : V.Ap;                                                           \
         double acc1[1] = {0.0};                                                                                     \
         ThIdx<th::dom_s##SP> t;                                                                                     \
-        if (t.from_linear(gt / LANES)) {                                                                            \
+        const bool valid = t.from_linear(gt / LANES);                                                               \
+        bool ex = true;                                                                                             \
+        real acc[NS];                                                                                               \
+        _Pragma("unroll") for (int j = 0; j < NS; ++j) acc[j] = (real)0;                                            \
+        if (valid) {                                                                                                \
             GAcc<th::dom_s##SP> ta(t, nullptr);                                                                     \
-            const bool ex = th::exclude_s##SP(ta, P);                                                               \
-            real acc[NS];                                                                                           \
-            _Pragma("unroll") for (int j = 0; j < NS; ++j) acc[j] = (real)0;                                        \
+            ex = th::exclude_s##SP(ta, P);                                                                          \
             if (!ex) {                                                                                              \
                 if (which) th::gather_s##SP<1, LANES>(t, lane, P, G, in, acc);                                      \
                 else th::gather_s##SP<0, LANES>(t, lane, P, G, in, acc);                                            \
             }                                                                                                       \
-            if (LANES > 1) { _Pragma("unroll") for (int j = 0; j < NS; ++j) acc[j] = th_warp_sum_real(acc[j]); }    \
-            if (lane == 0) {                                                                                        \
-                real dot = (real)0;                                                                                 \
-                _Pragma("unroll") for (int j = 0; j < NS; ++j) {                                                    \
-                    const int k = TH_SLOT[SP][j].image;                                                             \
-                    const long long off = TH_UIMG[k].offset + t.lin * TH_UIMG[k].channels + TH_SLOT[SP][j].channel; \
-                    if (ex) { out[off] = (real)0; continue; }                                                       \
-                    const real pv = in[off];                                                                        \
-                    real val = acc[j];                                                                              \
-                    if (TH_LM) val += V.CtC[off] * pv;                                                              \
-                    out[off] = val;                                                                                 \
-                    dot += pv * val;                                                                                \
-                }                                                                                                   \
-                acc1[0] = (double)dot;                                                                              \
+        }                                                                                                           \
+        if (LANES > 1) { _Pragma("unroll") for (int j = 0; j < NS; ++j) acc[j] = th_lanes_sum_real<LANES>(acc[j]); } \
+        if (valid && lane == 0) {                                                                                   \
+            real dot = (real)0;                                                                                     \
+            _Pragma("unroll") for (int j = 0; j < NS; ++j) {                                                        \
+                const int k = TH_SLOT[SP][j].image;                                                                 \
+                const long long off = TH_UIMG[k].offset + t.lin * TH_UIMG[k].channels + TH_SLOT[SP][j].channel;     \
+                if (ex) { out[off] = (real)0; continue; }                                                           \
+                const real pv = in[off];                                                                            \
+                real val = acc[j];                                                                                  \
+                if (TH_LM) val += V.CtC[off] * pv;                                                                  \
+                out[off] = val;                                                                                     \
+                dot += pv * val;                                                                                    \
             }                                                                                                       \
+            acc1[0] = (double)dot;                                                                                  \
         }                                                                                                           \
         if (which) return;                                                                                          \
         double tot[1];                                                                                              \

@@ -251,6 +251,8 @@ class Generator:
         self.tiled = self.schedule == "at_output" and len(self.udomain) in (2, 3)
         self.stage_center = self.tiled and len(self.udomain) == 2    # also stage centre-only arrays (2-D: shared memory to spare)
         self.tile_pad = os.environ.get("THALLO_B200_TILE_PAD", "1") != "0"      # tuning switch
+        gl = os.environ.get("THALLO_B200_GATHER_LANES")                          # tuning switch: lanes per unknown element (1..16)
+        self.gather_lanes = int(gl) if gl else None
         self.coef_exprs = []          # hoisted PCG-invariant per-element expressions (channels of the __coef image)
         self._coef_index = {}
 
@@ -439,6 +441,8 @@ class Generator:
             for v in tbl.values():
                 H = [max(a, b) for a, b in zip(H, v)]
         tile = list(self.tile_request) if self.tile_request else ([32, 8, 1] if nd == 2 else [8, 8, 4])
+        if os.environ.get("THALLO_B200_TILE"):                                   # tuning switch, e.g. "16,8,4"
+            tile = [int(x) for x in os.environ["THALLO_B200_TILE"].split(",")]
         tile = tile + [1] * (MAXD - len(tile))
         es_real = 8 if self.double else 4
         esz = dict(real=es_real, float=4, uchar=1, int=4, double=8)
@@ -516,12 +520,25 @@ class Generator:
             slot_stage[self.ptr_slot[name]] = len(stages)
             stages.append(dict(name=name, slot=self.ptr_slot[name], ctype=im.ctype, es=es, channels=im.channels,
                                roww=roww, off=o, bytes=nb, padl=padl, center=center))
-        # pipeline depth of th_pcg_a: two stages when they fit beside the other resident CTAs
-        # (TH_PCG_A_MINB = 3 per SM, 227 KB of shared memory), else one
-        pipe = 2 if 2 * max(128, off) * 3 + 3 * 1024 <= 227 * 1024 else 1
+        # pipeline depth and residency of th_pcg_a (227 KB of shared memory per SM, 64 K registers):
+        # two stages beside two other resident CTAs when they fit; otherwise (3-D tiles with wide
+        # halos) still two stages -- a one-stage CTA sits idle for the whole load of its next tile
+        # (profiles/r01i: a third of the warp samples of the 3-D operator) -- with as many CTAs as fit.
+        nthreads = tile[0] * tile[1] * tile[2]
+        stage = max(128, off)
+        minb = 3
+        if 2 * stage * 3 + 3 * 1024 <= 227 * 1024:
+            pipe = 2
+        else:
+            pipe, minb = 2, (227 * 1024 - 2048) // (2 * stage)
+            if minb < 1:
+                pipe, minb = 1, max(1, min(3, (227 * 1024 - 2048) // stage))
+        minb = max(1, min(minb, 2048 // nthreads))
         if os.environ.get("THALLO_B200_PIPE"):
             pipe = int(os.environ["THALLO_B200_PIPE"])
-        self.tl = dict(tile=tile, halo=H, ext=ext, vt=vt, stages=stages, slot_stage=slot_stage, smem=off, pipe=pipe)
+        if os.environ.get("THALLO_B200_MINB"):
+            minb = int(os.environ["THALLO_B200_MINB"])
+        self.tl = dict(tile=tile, halo=H, ext=ext, vt=vt, stages=stages, slot_stage=slot_stage, smem=off, pipe=pipe, minb=minb)
         return self.tl
 
     def gen_unknownwise(self):
@@ -823,7 +840,20 @@ class Generator:
                 if ep["kind"] == "sparse":
                     deg += _prod(L.dims[d].size for d in self.groups[ep["group"]]["domain"]) / float(elements)
             sp["elements"] = elements
-            sp["lanes"] = 32 if deg >= 64.0 else 1          # many residuals per unknown: one warp per unknown element
+            # lanes sharing one unknown element: a warp when many residuals meet there; otherwise a few
+            # lanes split the adjacency list so that each walks a shorter chain of dependent loads
+            # (index -> neighbour data), as long as most lanes get an element (measured on B200:
+            # arap_mesh, degree 2 x 6)
+            if deg >= 64.0:
+                lanes = 32
+            elif self.gather_lanes is not None:
+                lanes = self.gather_lanes
+            else:
+                per_list = deg / max(1, sum(1 for ep in sp["endpoints"] if ep["kind"] == "sparse"))
+                lanes = 1
+                while lanes < 8 and per_list >= 2.0 * lanes * 1.4:
+                    lanes *= 2
+            sp["lanes"] = lanes
             body = []
             for ep in sp["endpoints"]:
                 gi = ep["group"]
@@ -1019,6 +1049,7 @@ class Generator:
                 hdr.append("#define TH_HX %d\n#define TH_HY %d\n#define TH_HZ %d" % tuple(tl["halo"]))
                 hdr.append("#define TH_SMEM_BYTES %d" % max(128, tl["smem"]))
                 hdr.append("#define TH_PIPE %d" % tl["pipe"])
+                hdr.append("#define TH_PCG_A_MINB %d" % tl["minb"])
                 hdr.append("#define TH_NSTAGE %d" % len(tl["stages"]))
                 hdr.append("#define TH_STAGE_TABLE {%s}" % (", ".join(
                     "{%d, %d, %d, %d, %d, %d, %d, %d}" % (st["slot"], st["es"], st["channels"], st["roww"], st["off"], st["padl"],
