@@ -67,5 +67,11 @@ def test_warp_aggregated_scatter_matches_plain_atomics():
     agg = _solve("residualwise", "")
     plain = _solve("residualwise", "-DTH_WARP_AGG=0")
     assert len(agg) == len(plain)
-    # both forms add the same contributions; only the order of the float additions differs
-    np.testing.assert_allclose(agg, plain, rtol=2e-5)
+    # Both forms add the same contributions; only the order of the float additions differs.  The first
+    # nonlinear step (20 PCG iterations on identical operators) must agree to float32 rounding; after it
+    # the LM zeta test (gauss_newton.t:1666-1686) differences two nearly equal float32 sums, a borderline
+    # exit can fall one PCG iteration apart between the two orders, and the trajectories then differ at
+    # the percent level (observed on B200: 0.4165 vs 0.4139 at step 2) -- the same float32 noise floor
+    # tests/_parity.py measures for the oracle comparisons.
+    np.testing.assert_allclose(agg[:2], plain[:2], rtol=2e-5)
+    np.testing.assert_allclose(agg[2:], plain[2:], rtol=5e-2)

@@ -333,11 +333,13 @@ __device__ __forceinline__ void th_mbar_init(unsigned long long* bar, unsigned c
 __device__ __forceinline__ void th_mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(th_smem_u32(bar)), "r"(bytes) : "memory");
 }
-// try_wait suspends the warp in hardware for a bounded time; between attempts the warp sleeps so that
-// a CTA waiting for its tile does not take issue slots from the CTAs that are computing
-// (profiles/r01i: the spin was 15 % of the executed instructions of the 3-D operator kernel)
+// try_wait suspends the warp in hardware for a bounded time.  3-D tiles: between attempts the warp
+// sleeps so that a CTA waiting for its tile does not take issue slots from the CTAs that are computing
+// (profiles/r01i: the spin was 15 % of the executed instructions of the 3-D operator kernel).  2-D tiles
+// are bandwidth-bound and a late wake-up costs more than the spin (image_warping 2048x2048: th_pcg_a
+// 0.0731 ms with the sleep, 0.0689 ms without; profiles/r01j_sweep.txt), so they spin.
 #ifndef TH_WAIT_SLEEP_NS
-#define TH_WAIT_SLEEP_NS 64
+#define TH_WAIT_SLEEP_NS (TH_NDIMS == 3 ? 64 : 0)
 #endif
 __device__ __forceinline__ bool th_mbar_try(unsigned long long* bar, unsigned parity) {
     unsigned ok;

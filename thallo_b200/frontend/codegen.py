@@ -840,19 +840,18 @@ class Generator:
                 if ep["kind"] == "sparse":
                     deg += _prod(L.dims[d].size for d in self.groups[ep["group"]]["domain"]) / float(elements)
             sp["elements"] = elements
-            # lanes sharing one unknown element: a warp when many residuals meet there; otherwise a few
-            # lanes split the adjacency list so that each walks a shorter chain of dependent loads
-            # (index -> neighbour data), as long as most lanes get an element (measured on B200:
-            # arap_mesh, degree 2 x 6)
+            # lanes sharing one unknown element: a warp when many residuals meet there (the cameras of
+            # bundle adjustment), else one thread per element.  Splitting a short adjacency list over
+            # 2-8 lanes was measured on B200 and loses (arap_mesh 2000x2000, degree 2 x 6: th_gather_s0
+            # 0.319 ms with 1 lane, 0.466 with 2, 0.786 with 4; profiles/r01j_sweep.txt): the walk is bound
+            # by the per-edge arithmetic, and idle lanes of the narrower lists cost more than the
+            # shorter dependent-load chains save.  THALLO_B200_GATHER_LANES overrides for experiments.
             if deg >= 64.0:
                 lanes = 32
             elif self.gather_lanes is not None:
                 lanes = self.gather_lanes
             else:
-                per_list = deg / max(1, sum(1 for ep in sp["endpoints"] if ep["kind"] == "sparse"))
                 lanes = 1
-                while lanes < 8 and per_list >= 2.0 * lanes * 1.4:
-                    lanes *= 2
             sp["lanes"] = lanes
             body = []
             for ep in sp["endpoints"]:
