@@ -10,7 +10,9 @@ so the same workload definition drives both sides, the way the same `.t` file
 drives both the reference's GPU path and its cpuOnly path.
 
 `REGISTRY` maps the reference file a caller passes to Thallo_ProblemDefine to
-the module that restates it.
+the module that restates it.  When the file the caller names exists, it is read
+and evaluated as written (thallo_b200/frontend/tlang.py, the `.t` front end); the
+registered transcription is used only when no such file is present.
 """
 import importlib
 
@@ -57,3 +59,18 @@ def resolve(path):
         return base
     except ImportError:
         return None
+
+
+def define_for(energy):
+    """`define(L)` and a short name for what a caller handed Thallo_ProblemDefine: an existing `.t`
+    file is evaluated as written (reference thallo.t:5954-5975 loads the file the same way); otherwise
+    the name is looked up among the registered transcriptions.  THALLO_B200_NO_TLANG=1 forces the
+    transcriptions.  Returns (define, name) or (None, None)."""
+    import os
+    if energy.endswith(".t") and os.path.isfile(energy) and os.environ.get("THALLO_B200_NO_TLANG", "0") in ("", "0"):
+        from thallo_b200.frontend import tlang
+        return tlang.load(energy), os.path.basename(energy)[:-2]
+    mod = resolve(energy)
+    if mod is None:
+        return None, None
+    return load(mod), mod

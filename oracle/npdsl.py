@@ -148,6 +148,23 @@ class Dual:
         thallo.t:1777-1822), read at an offset with zero outside the domain (thallo.t:876-882).  Its
         derivatives travel with it as the gradient image, read at the same offset and re-keyed to
         the unknown accesses they belong to, shifted by that offset (thallo.t:1551-1561)."""
+        if len(idx) == 1 and isinstance(idx[0], SparseRef):
+            # exp:get(v(e)) (tests/minimal_sparse_materialize/minimal_sparse_materialize.t:17): the stored
+            # image and its gradient image are read at element v(e); the derivatives belong to the
+            # unknowns at that element
+            ref = idx[0]
+            L = ref.iv.dim.L
+            e = L._sparse_values(ref)
+            n = ref.sparse.to[0].size
+
+            def at(a):
+                return np.ascontiguousarray(np.broadcast_to(np.asarray(a), (n,)))[e]
+            d = {}
+            for (iname, ikey, ch), dv in self.d.items():
+                assert ikey[0] == "d" and not any(ikey[1]), \
+                    "a computed array fetched through a sparse index may only read unknowns at its own element"
+                d[(iname, ("s", ref.sparse.name, ref.iv.off), ch)] = at(dv)
+            return Dual(at(self.val), d)
         offs = [iv.off for iv in idx]
         shape = tuple(iv.dim.size for iv in reversed(idx))
 

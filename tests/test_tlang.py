@@ -1,0 +1,332 @@
+"""The `.t` front end (thallo_b200/frontend/tlang.py): Lua-subset semantics, the DSL library bound
+into it, and -- where the reference checkout is present -- that every configured energy file, read
+as written, lowers to exactly the CUDA source and plan descriptor of its registered transcription.
+The energy texts in this file are written for the tests (they are not reference files)."""
+import io
+import os
+
+import numpy as np
+import pytest
+
+import energies
+from thallo_b200.frontend import codegen, tlang
+
+REF = "/root/reference"
+
+
+def run(text, **globals_):
+    out = io.StringIO()
+    G = tlang._base_globals(out)
+    G.update(globals_)
+    r = tlang.Interpreter(G, "chunk").run(tlang.parse(text, "chunk"))
+    return r, G, out.getvalue()
+
+
+# ------------------------------------------------------------------ language semantics
+def test_arithmetic_precedence_and_associativity():
+    r, _, _ = run("return 2^3^2, -2^2, 1+2*3, (1+2)*3, 7 % 3, -7 % 3, 2^-1, 1 .. 2, 10/4, 3 - 2 - 1")
+    assert r == [512.0, -4.0, 7, 9, 1, 2, 0.5, "12", 2.5, 0]
+
+
+def test_comparison_and_logic_short_circuit():
+    r, _, _ = run("""
+        local calls = 0
+        local function f() calls = calls + 1; return true end
+        local a = false and f()
+        local b = nil or 5
+        local c = 0 and "zero is true"
+        return a, b, c, calls, 1 < 2, 2 <= 2, 3 ~= 3, "a" == "a", not nil, not 0
+    """)
+    assert r == [False, 5, "zero is true", 0, True, True, False, True, True, False]
+
+
+def test_locals_globals_shadowing_and_multiple_assignment():
+    r, G, _ = run("""
+        x, y = 1, 2
+        local x = 10
+        x, y = y, x          -- swap: right side evaluated first
+        do local y = 99 end
+        z = x + y
+        local a, b, c = 1
+        return x, y, z, a, b, c
+    """)
+    assert r == [2, 10, 12, 1, None, None]
+    assert G["x"] == 1 and G["y"] == 10 and G["z"] == 12
+
+
+def test_closures_recursion_and_varargs():
+    r, _, _ = run("""
+        local function counter()
+            local n = 0
+            return function() n = n + 1; return n end
+        end
+        local c1, c2 = counter(), counter()
+        c1(); c1()
+        local function fact(n) if n <= 1 then return 1 else return n * fact(n - 1) end end
+        local function pack(...) local t = {...}; return #t, select('#', ...), ... end
+        local function two() return 1, 2 end
+        local t = {two(), two()}          -- only the last call expands
+        return c1(), c2(), fact(6), #t, (two()), pack(7, 8, 9)
+    """)
+    assert r == [3, 1, 720, 3, 1, 3, 3, 7, 8, 9]
+
+
+def test_tables_length_keys_and_methods():
+    r, _, _ = run("""
+        local t = {10, 20, 30, name = "n", [5] = 50}
+        t[#t + 1] = 40
+        local obj = {v = 3}
+        function obj:add(k) self.v = self.v + k; return self end
+        function obj.static(a) return a * 2 end
+        obj:add(4):add(1)
+        local keys = 0
+        for k, v in pairs(t) do keys = keys + 1 end
+        local sum = 0
+        for i, v in ipairs(t) do sum = sum + i * v end
+        table.insert(t, 1, 5)
+        return #t, t.name, t[5], t[6], obj.v, obj.static(21), keys, sum
+    """)
+    assert r == [6, "n", 40, 50, 8, 42, 6, 10 + 40 + 90 + 160 + 250]
+
+
+def test_control_flow():
+    r, _, _ = run("""
+        local s = 0
+        for i = 10, 1, -3 do s = s + i end            -- 10 7 4 1
+        local n = 0
+        while true do n = n + 1; if n >= 5 then break end end
+        local m = 0
+        repeat local done = m >= 3; m = m + 1 until done
+        local kind
+        if s == 22 and n == 5 then kind = "a" elseif s == 0 then kind = "b" else kind = "c" end
+        for i = 1, 0 do kind = "never" end
+        return s, n, m, kind
+    """)
+    assert r == [22, 5, 4, "a"]
+
+
+def test_comments_and_strings():
+    r, _, out = run("""
+        --[[ a long
+             comment ]]
+        --[==[ another ]] still comment ]==]
+        local s = [[raw
+text]] .. 'q\\'s' .. "\\n" -- trailing comment
+        print("hello", 1, 2.5, nil, true)
+        return s, #s, string.format("%d-%s", 3, "x")
+    """)
+    assert r[0] == "raw\ntextq's\n" and r[1] == len(r[0]) and r[2] == "3-x"
+    assert out == "hello\t1\t2.5\tnil\ttrue\n"
+
+
+def test_python_objects_follow_lua_protocols():
+    class V:
+        def __init__(self, v): self.v = v
+        def __add__(self, o): return V(self.v + (o.v if isinstance(o, V) else o))
+        __radd__ = __add__
+        def __mul__(self, o): return V(self.v * o)
+        __rmul__ = __mul__
+        def __neg__(self): return V(-self.v)
+        def __call__(self, i): return self.v + i
+        def __getitem__(self, i): return self.v * 10 + i
+        def twice(self, k=1): return V(2 * self.v * k)
+
+    r, _, _ = run("local a = 2 * x + 1; return (-a).v, a(5), a[3], x:twice().v, x:twice(3).v, x.v", x=V(4))
+    assert r == [-9, 14, 93, 8, 24, 4]
+
+
+@pytest.mark.parametrize("text,line", [("local x = = 1", 1), ("x = 1\ny = (2", 2), ("for i = 1 do end", 1), ("\n\nlocal 5", 3)])
+def test_syntax_errors_report_chunk_and_line(text, line):
+    with pytest.raises(tlang.LuaError) as e:
+        tlang.parse(text, "bad.t")
+    assert str(e.value).startswith("bad.t:%d:" % line)
+
+
+def test_runtime_errors_report_line():
+    with pytest.raises(tlang.LuaError) as e:
+        run("local t = nil\n\nreturn t.x")
+    assert "chunk:3" in str(e.value)
+    with pytest.raises(tlang.LuaError) as e:
+        run("local function f() return undefined_function(1) end\nreturn f()")
+    assert "nil value" in str(e.value)
+
+
+# ------------------------------------------------------------------ energies written in the DSL
+HEAT_T = """
+-- masked smoothing whose stencil differences are rotated by an angle taken from the unknown itself: written for this test
+local W,H = Dims("W","H")
+Inputs {
+    U    = Unknown(thallo_float2,{W,H},0),
+    T    = Array(thallo_float2,{W,H},1),
+    M    = Array(thallo_float,{W,H},2),
+    w_d  = Param(float,3)
+}
+UsePreconditioner(true)
+local x,y = W(),H()
+U:Exclude(Not(eq(M(x,y),0)))
+local function weight(k) return 1.0/(1 + k) end       -- plain Lua arithmetic on numbers
+local terms = {}
+for dx,dy in Stencil { {1,0}, {0,1}, {1,1} } do
+    local d = U(x,y) - U(x+dx,y+dy)
+    local ok = InBounds(x+dx,y+dy) * eq(M(x,y),0) * eq(M(x+dx,y+dy),0)
+    terms[#terms+1] = Select(ok, weight(dx+dy) * Rotate2D(0.25*U(x,y)(0), d), 0)
+end
+r = Residuals {
+    data   = w_d * Select(eq(M(x,y),0), U(x,y) - T(x,y), 0),
+    smooth = terms
+}
+"""
+
+
+def heat_py(L):
+    from energies._lib import Rotate2D
+    W, H = L.Dims("W", "H")
+    I = L.Inputs(U=L.Unknown(L.float2, [W, H], 0), T=L.Array(L.float2, [W, H], 1), M=L.Array(L.float, [W, H], 2),
+                 w_d=L.Param(L.float, 3))
+    L.UsePreconditioner(True)
+    x, y = W(), H()
+    I.U.Exclude(L.Not(L.eq(I.M(x, y), 0)))
+    terms = []
+    for dx, dy in [(1, 0), (0, 1), (1, 1)]:
+        d = I.U(x, y) - I.U(x + dx, y + dy)
+        ok = L.InBounds(x + dx, y + dy) * L.eq(I.M(x, y), 0) * L.eq(I.M(x + dx, y + dy), 0)
+        terms.append(L.Select(ok, (1.0 / (1 + dx + dy)) * Rotate2D(L, 0.25 * I.U(x, y)(0), d), 0))
+    return L.Residuals(data=I.w_d * L.Select(L.eq(I.M(x, y), 0), I.U(x, y) - I.T(x, y), 0), smooth=terms)
+
+
+GRAPH_T = """
+N,E = Dims("N","E")
+Inputs {
+    P  = Unknown(thallo_float3,{N},0),
+    Q  = Array(thallo_float3,{N},1),
+    a  = Sparse({E},{N},2),
+    b  = Sparse({E},{N},3)
+}
+n,e = N(),E()
+local d = P(a(e)) - P(b(e))
+local rest = Q(a(e)) - Q(b(e))
+r = Residuals {
+    fit  = 0.5*(P(n) - Q(n)),
+    edge = dot(d,d) - dot(rest,rest)
+}
+r.edge.J:set_materialize(true)
+"""
+
+
+def graph_py(L):
+    from energies._lib import dot
+    N, E = L.Dims("N", "E")
+    I = L.Inputs(P=L.Unknown(L.float3, [N], 0), Q=L.Array(L.float3, [N], 1), a=L.Sparse([E], [N], 2), b=L.Sparse([E], [N], 3))
+    n, e = N(), E()
+    d = I.P(I.a(e)) - I.P(I.b(e))
+    rest = I.Q(I.a(e)) - I.Q(I.b(e))
+    r = L.Residuals(fit=0.5 * (I.P(n) - I.Q(n)), edge=dot(L, d, d) - dot(L, rest, rest))
+    r.edge.J.set_materialize(True)
+    return r
+
+
+@pytest.mark.parametrize("text,py,dims,kind", [(HEAT_T, heat_py, [24, 20], "levenberg_marquardt"),
+                                               (GRAPH_T, graph_py, [30, 80], "gauss_newton")])
+def test_t_text_lowers_like_the_python_definition(text, py, dims, kind):
+    a = codegen.lower(tlang.make_define(text, "case.t"), dims, kind, "case")
+    b = codegen.lower(py, dims, kind, "case")
+    assert codegen.descriptor_text(a.desc) == codegen.descriptor_text(b.desc)
+    assert a.source == b.source
+
+
+def test_t_text_runs_through_the_oracle_namespace():
+    """The same file drives the NumPy oracle (like the same `.t` drives the reference's GPU and cpuOnly paths)."""
+    from oracle import npdsl
+    rs = np.random.RandomState(3)
+    W, H = 12, 9
+    U = rs.rand(H, W, 2).astype(np.float32)
+    T = rs.rand(H, W, 2).astype(np.float32)
+    M = (rs.rand(H, W) < 0.2).astype(np.float32)
+    wd = np.float32(0.7)
+    _, F1, J1 = npdsl.evaluate(tlang.make_define(HEAT_T, "heat.t"), [W, H], [U, T, M, wd])
+    _, F2, J2 = npdsl.evaluate(heat_py, [W, H], [U, T, M, wd])
+    assert np.array_equal(F1, F2)
+    assert (J1 != J2).nnz == 0 and J1.nnz > 0
+
+
+def test_computed_array_fetched_through_a_sparse_index():
+    """`exp:get(v(e))` as in the reference's tests/minimal_sparse_materialize (text written for this test):
+    value + gradient image over N, read through the edge's index arrays; lowering against the oracle's J."""
+    from oracle import npdsl
+    from thallo_b200 import api
+    from thallo_b200.frontend import interp
+    text = """
+    local N,E = Dims("N","E")
+    Inputs { X = Unknown(float,{N},0), A = Array(float,{N},1), v0 = Sparse({E},{N},2), v1 = Sparse({E},{N},3) }
+    local n,e = N(),E()
+    local function warp(x) return sin(x) end
+    local s = warp(X(n)) * A(n)
+    r = Residuals { fit = X(n) - A(n), reg = s:get(v0(e)) - s:get(v1(e)) }
+    """
+    define = tlang.make_define(text, "get.t")
+    rs = np.random.RandomState(0)
+    N, E = 16, 40
+    params = [rs.rand(N), rs.rand(N), rs.randint(0, N, E).astype(np.int32), rs.randint(0, N, E).astype(np.int32)]
+    low = codegen.lower(define, [N, E], "gauss_newton", "get", True, "gather")
+    assert low.desc["computed"] == [dict(elements=N, ngrad=1)]
+    _, F, J = npdsl.evaluate(define, [N, E], params, np.float64)
+    p = rs.randn(J.shape[1])
+    want = J.T.tocsr() @ (J @ p)
+    for mat in (False, True):
+        got = interp.gather_apply(low.generator, params, p, materialised=mat)
+        assert np.abs(got - want).max() <= 1e-12 * max(1.0, np.abs(want).max())
+    ok, log, size = api.compile_only(codegen.lower(define, [N, E], "gauss_newton", "get").source)
+    assert ok and size > 0, log
+
+
+def test_define_for_prefers_an_existing_file(tmp_path):
+    p = tmp_path / "image_warping.t"        # same name as a registered transcription, different energy
+    p.write_text(GRAPH_T)
+    define, name = energies.define_for(str(p))
+    assert name == "image_warping"
+    low = codegen.lower(define, [30, 80], "gauss_newton", name)
+    assert "edge" in codegen.descriptor_text(low.desc)
+    define2, name2 = energies.define_for("image_warping.t")      # no such file in the cwd: the transcription
+    assert name2 == "image_warping" and define2 is energies.load("image_warping")
+    assert energies.define_for("no_such_energy.t") == (None, None)
+
+
+def test_frontend_cli_reads_t_files(tmp_path):
+    import subprocess
+    import sys
+    p = tmp_path / "heat.t"
+    p.write_text(HEAT_T)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, PYTHONPATH=root)
+    subprocess.check_call([sys.executable, "-m", "thallo_b200.frontend", "--energy", str(p), "--out", str(tmp_path),
+                           "--query-ndims"], env=env, cwd=str(tmp_path))
+    assert (tmp_path / "ndims.txt").read_text() == "2"
+    subprocess.check_call([sys.executable, "-m", "thallo_b200.frontend", "--energy", str(p), "--kind", "levenberg_marquardt",
+                           "--dims", "24,20", "--out", str(tmp_path)], env=env, cwd=str(tmp_path))
+    ref = codegen.lower(heat_py, [24, 20], "levenberg_marquardt", "heat")
+    assert (tmp_path / "energy.cu").read_text() == ref.source
+    assert (tmp_path / "plan.desc").read_text() == codegen.descriptor_text(ref.desc)
+
+
+# ------------------------------------------------------------------ the reference's own files, read as written
+REF_CASES = [
+    ("tests/minimal/laplacian.t", "laplacian", [48, 40], "gauss_newton", dict(variant="committed", materialize=True)),
+    ("tests/minimal_graph/laplacian.t", "graph_laplacian", [32, 31], "gauss_newton", dict(materialize=True)),
+    ("examples/image_warping/image_warping.t", "image_warping", [64, 48], "levenberg_marquardt", {}),
+    ("examples/optical_flow/optical_flow.t", "optical_flow", [64, 48], "gauss_newton", {}),
+    ("examples/volumetric_mesh_deformation/volumetric_mesh_deformation.t", "volumetric_mesh_deformation", [16, 12, 8],
+     "gauss_newton", {}),
+    ("examples/arap_mesh_deformation/arap_mesh_deformation.t", "arap_mesh_deformation", [100, 500], "gauss_newton", {}),
+    ("examples/bundle_adjustment/bundle_adjustment.t", "bundle_adjustment", [10, 100, 400], "levenberg_marquardt",
+     dict(materialize=False)),
+    ("examples/shape_from_shading/shape_from_shading.t", "shape_from_shading", [64, 48], "gauss_newton", {}),
+]
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference checkout not present (GPU box)")
+@pytest.mark.parametrize("path,mod,dims,kind,kw", REF_CASES, ids=[c[1] for c in REF_CASES])
+def test_reference_energy_files_lower_like_their_transcriptions(path, mod, dims, kind, kw):
+    a = codegen.lower(tlang.load(os.path.join(REF, path)), dims, kind, mod)
+    b = codegen.lower(energies.load(mod), dims, kind, mod, **kw)
+    assert codegen.descriptor_text(a.desc) == codegen.descriptor_text(b.desc)
+    assert a.source == b.source

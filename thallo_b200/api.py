@@ -132,8 +132,10 @@ class ThalloSolver:
         else:
             import energies
             from .frontend import codegen
-            mod = energies.resolve(energy) or energy
-            low = codegen.lower(energies.load(mod), self.dims, kind, mod, double, schedule, partition=partition,
+            define, mod = energies.define_for(energy)
+            if define is None:
+                raise RuntimeError("no energy file or registered energy named '%s'" % energy)
+            low = codegen.lower(define, self.dims, kind, mod, double, schedule, partition=partition,
                                 **(define_kwargs or {}))
             self.lowered = low
             self.problem = L.ThalloB200_ProblemDefineFromSource(

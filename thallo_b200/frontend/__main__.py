@@ -23,11 +23,11 @@ def main():
     a = ap.parse_args()
     import energies
     from thallo_b200.frontend import codegen, dsl
-    mod = energies.resolve(a.energy)
-    if mod is None:
-        sys.stderr.write("no energy definition registered for '%s' (see energies/__init__.py REGISTRY)\n" % a.energy)
+    define, mod = energies.define_for(a.energy)
+    if define is None:
+        sys.stderr.write("energy file '%s' does not exist and no transcription is registered under that name "
+                         "(energies/__init__.py REGISTRY)\n" % a.energy)
         return 2
-    define = energies.load(mod)
     if a.query_ndims:
         L = dsl.SymbolicL([1] * 8)
         try:

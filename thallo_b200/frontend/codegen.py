@@ -119,12 +119,20 @@ class _Term:
         for c in ad.variables(exp, lambda v: isinstance(v.key, ImageAccess) and v.key.image in computed):
             im = computed[c.key.image]
             dc = ad.derivative(exp, c)
-            s = dict((comp[1], comp[2]) for comp in c.key.index)
+            through_sparse = any(comp[0] == "s" for comp in c.key.index)
+            s = {} if through_sparse else dict((comp[1], comp[2]) for comp in c.key.index)
             for i, u in enumerate(im.gunknowns):
                 g = im.gradient_at(i, c.key.index)
                 if g.is_const(0.0):
                     continue
-                k = _shift_key(u.key, s)
+                if through_sparse:
+                    # C:get(v(e)) (tests/minimal_sparse_materialize): the unknowns C reads at its own element
+                    # are the unknowns at element v(e)
+                    assert all(comp[0] == "d" and comp[2] == 0 for comp in u.key.index), \
+                        "a computed array fetched through a sparse index may only read unknowns at its own element"
+                    k = u.key._replace(index=c.key.index)
+                else:
+                    k = _shift_key(u.key, s)
                 if k not in partial:
                     partial[k] = ad.const(0.0)
                     order.append(k)

@@ -76,6 +76,10 @@ class Interp:
         if isinstance(k, ImageAccess):
             if k.index[0][0] == "s":        # 1-D residual domain reaching a 1-D image through an index array
                 im = g.images[k.image]
+                if im.kind in ("computed", "computed_gradient"):      # plan-owned image over its own domain
+                    sub = Interp(g, self.params, [d.idx for d in im.dims], None, self.dt)
+                    a = sub._image(k.image).reshape(-1, im.channels)
+                    return a[self._sparse(k.index[0][1]), k.channel]
                 a = np.asarray(self.params[im.pidx]).astype(self.dt).reshape(-1, im.channels)
                 return a[self._sparse(k.index[0][1]), k.channel]
             return _shifted(self._image(k.image), self._offs(k.index))[..., k.channel]
