@@ -3,7 +3,7 @@ graph-domain ARAP: N vertices (Position, Angle float3), E directed edges."""
 from ._lib import Rotate3D
 
 
-def define(L):
+def define(L, jp=False):
     N, E = L.Dims("N", "E")
     I = L.Inputs(
         w_fitSqrt=L.Param(L.float, 0),
@@ -22,4 +22,7 @@ def define(L):
     e_fit = Position(n) - Constraints(n)
     valid = L.greatereq(Constraints(n)[0], -999999.9)
     arap = (Position(v0) - Position(v1)) - Rotate3D(L, Angle(v0), Original(v0) - Original(v1))
-    return L.Residuals(fit=L.Select(valid, I.w_fitSqrt * e_fit, 0), reg=I.w_regSqrt * arap)
+    r = L.Residuals(fit=L.Select(valid, I.w_fitSqrt * e_fit, 0), reg=I.w_regSqrt * arap)
+    if jp:          # schedule Jt[Jp] for the edge term (`r.reg.Jp:set_materialize(true)`, thallo.t:4121)
+        r.reg.Jp.set_materialize(True)
+    return r

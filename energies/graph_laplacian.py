@@ -1,7 +1,7 @@
 """tests/minimal_graph/laplacian.t (reference tests/minimal_graph/laplacian.t:1-23)."""
 
 
-def define(L, materialize=False):
+def define(L, materialize=False, jp=False):
     N, E = L.Dims("N", "E")
     I = L.Inputs(
         X=L.Unknown(L.float, [N], 0),
@@ -18,4 +18,6 @@ def define(L, materialize=False):
     )
     if materialize:
         r.fit.J.set_materialize(True)
+    if jp:
+        r.reg.Jp.set_materialize(True)
     return r

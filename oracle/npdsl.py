@@ -389,7 +389,7 @@ class _Sched:
 class _Group:
     def __init__(self, name, terms):
         self.name, self.terms = name, terms
-        self.J, self.JtJ = _Sched(), _Sched()
+        self.J, self.JtJ, self.Jp = _Sched(), _Sched(), _Sched()
 
 
 class _Residuals:

@@ -60,7 +60,7 @@ class OracleSolver:
     def _eval(self, params):
         L = NumpyL(self.dims, params, self.dtype)
         self.define(L, **self.kw)
-        F, J, _ = L.assemble()
+        F, J, self.ranges = L.assemble()
         return L, F, J
 
     def _cost(self, params):
@@ -158,6 +158,18 @@ class OracleSolver:
                 out = (out + C * v).astype(dt)
             return out
 
+        # LM residual reset (gauss_newton.t:1653-1660): computeAdelta exists only for groups that have an
+        # applyJTJ function, i.e. the INLINE schedule (:1058-1065); groups whose J or J p is materialised
+        # ([Jt][[J]p], Jt[Jp]) contribute nothing to A delta (SURVEY 8a quirk iii)
+        rows_inline = np.ones(Jk.shape[0], dtype=dt)
+        for g, (_, lo_, hi_) in zip(L.residuals.groups, self.ranges):
+            if self.materialized or g.J.materialize or g.Jp.materialize:
+                rows_inline[lo_:hi_] = 0
+
+        def applyA_reset(v):
+            out = (JT @ (rows_inline * (Jk @ v))).astype(dt)
+            return (out + C * v).astype(dt)
+
         nlin = 0
         forced = None
         if self.force_lin is not None and self.nIter < len(self.force_lin):
@@ -170,7 +182,7 @@ class OracleSolver:
                 alpha = dt(aN / aD) if (self.lm or aD != 0) else dt(0)
             if self.lm and ((l + 1) % int(P["residual_reset_period"])) == 0:
                 delta = (delta + alpha * p).astype(dt)
-                Ad = (C * delta).astype(dt) if self.materialized else applyA(delta)
+                Ad = applyA_reset(delta)
                 r = (b - Ad).astype(dt)
             else:
                 delta = (delta + alpha * p).astype(dt)

@@ -31,6 +31,7 @@ def main():
     ap.add_argument("--lit", type=int, default=50)
     ap.add_argument("--steps", type=int, default=2)
     ap.add_argument("--no-materialize", action="store_true")
+    ap.add_argument("--jp", action="store_true", help="arap_mesh: schedule Jt[Jp] for the edge term (J p stored per edge)")
     a = ap.parse_args()
     import numpy as np
     import torch
@@ -47,6 +48,10 @@ def main():
         N, E, U, A = n * n, len(d["V0"]), 6, 9
         # gather schedule: index arrays (V0 offsets + V1 + permutation + V0 through it) + own reads + writes, see DESIGN.md
         bytes_iter = {"th_gather_s0": 4 * (E * 3 + N * (1 + U + A + U)), "th_pcg_b": 4 * N * 8 * U, "th_step3": 4 * N * 3 * U}
+        if a.jp:    # J p (3 scalars per edge) written once by th_applyj_g1 and read once through each of the two endpoints
+            kw = dict(define_kwargs=dict(jp=True))
+            bytes_iter["th_applyj_g1"] = 4 * (E * (2 + 3) + N * (U + A))
+            bytes_iter["th_gather_s0"] += 4 * E * 2 * 3
     elif a.workload == "bundle_adjustment":
         d = wl.bundle_adjustment_inputs(a.cameras, a.points, 5)
         O = len(d["oToC"])

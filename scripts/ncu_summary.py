@@ -1,11 +1,12 @@
 #!/usr/bin/env python
 """Summarise ncu output of a gpurun pass into small text files for profiles/ (read on the CPU box).
 
-  python scripts/ncu_summary.py gpurun_out/<tag> profiles/<name>
+  python scripts/ncu_summary.py gpurun_out/<tag> profiles/<name> [--traffic]
 
 Writes <name>_launches.txt (per-kernel launch count, total/avg device time and share from the
 `--metrics gpu__time_duration.sum` launch list), <name>_kernels.txt (key metrics of every launch in
-the `--set full` capture) and updates profiles/traffic.json (DRAM bytes per launch per kernel).
+the `--set full` capture; one file per report when there are several) and, with --traffic (the capture
+of bench.py's own workload), updates profiles/traffic.json (DRAM bytes per launch per kernel).
 """
 import csv
 import glob
@@ -42,6 +43,7 @@ def to_bytes(v, unit):
 
 def main():
     src, dst = sys.argv[1], sys.argv[2]
+    update_traffic = "--traffic" in sys.argv[3:]
     os.makedirs(os.path.dirname(dst) or ".", exist_ok=True)
     # ---- launch list
     lf = os.path.join(src, "launches.csv")
@@ -63,7 +65,7 @@ def main():
                 f.write("%-28s %8d %12.1f %10.2f %6.1f%%\n" % (k, a[0], a[1], a[1] / a[0], 100 * a[1] / tot))
         print(open(dst + "_launches.txt").read())
     # ---- full capture
-    reps = glob.glob(os.path.join(src, "*.ncu-rep"))
+    reps = sorted(glob.glob(os.path.join(src, "*.ncu-rep")))
     traffic_path = os.path.join(os.path.dirname(dst) or ".", "traffic.json")
     traffic = json.load(open(traffic_path)) if os.path.exists(traffic_path) else {}
     for rep in reps:
@@ -72,7 +74,9 @@ def main():
         hdr, units = rows[0], rows[1]
         name_i = hdr.index("Kernel Name")
         per = {}
-        with open(dst + "_kernels.txt", "w") as f:
+        tag = os.path.basename(rep)[:-len(".ncu-rep")].split("_")[-1]
+        kfile = dst + ("_%s" % tag if len(reps) > 1 else "") + "_kernels.txt"
+        with open(kfile, "w") as f:
             f.write("# ncu --set full --clock-control none, from %s\n" % os.path.basename(rep))
             for r in rows[2:]:
                 f.write("== %s (id %s)\n" % (r[name_i], r[0]))
@@ -95,8 +99,9 @@ def main():
                     per.setdefault(r[name_i], []).append(to_bytes(r[ri], units[ri]) + to_bytes(r[wi], units[wi]))
         for k, v in per.items():
             traffic[k] = sum(v) / len(v)
-        print(open(dst + "_kernels.txt").read())
-    json.dump(traffic, open(traffic_path, "w"), indent=1, sort_keys=True)
+        print(open(kfile).read())
+    if update_traffic:
+        json.dump(traffic, open(traffic_path, "w"), indent=1, sort_keys=True)
 
 
 if __name__ == "__main__":

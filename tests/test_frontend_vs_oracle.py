@@ -143,3 +143,24 @@ def test_shape_from_shading_lowering_has_two_computed_arrays():
     assert low.desc["computed"] == [dict(elements=64 * 48, ngrad=3), dict(elements=64 * 48, ngrad=0)]
     assert low.desc["tiled"] == 1 and low.desc["tile"]["halo"][:2] == [2, 2]
     assert "th_precompute_c0" in low.source or "TH_COMPUTED_LIST(X) X(0) X(1)" in low.source
+
+
+# ---- Jt[Jp] schedule (APPLY_SEPARATELY, thallo.t:4121; a10 of SURVEY 8): J p stored per residual row, transposed
+# partials gathered per unknown
+def test_arap_mesh_jtjp_schedule_matches_oracle():
+    nx, ny = 8, 7
+    d = wl.arap_mesh_inputs(nx, ny)
+    rng = np.random.RandomState(9)
+    d["Position"] = d["Position"] + 0.3 * rng.randn(*d["Position"].shape).astype(np.float32)
+    d["Angle"] = d["Angle"] + 0.4 * rng.randn(*d["Angle"].shape).astype(np.float32)
+    params = [np.asarray(p, np.float64) if np.asarray(p).dtype == np.float32 else p for p in wl.arap_mesh_params(d)]
+    low = _check_gather("arap_mesh_deformation", [nx * ny, len(d["V0"])], params, dict(jp=True))
+    assert [g["materialize"] for g in low.desc["groups"]] == [0, 2]          # fit inline, reg Jt[Jp]
+    assert "th_applyj_g" in low.source or "TH_JP_LIST(X) X(1)" in low.source
+    assert "jtp_ep" in low.source
+
+
+def test_graph_laplacian_jtjp_schedule_matches_oracle():
+    X, A, v0, v1 = wl.minimal_graph_inputs(48)
+    low = _check_gather("graph_laplacian", [48, 47], [X.astype(np.float64) * 0.9, A.astype(np.float64), v0, v1], dict(jp=True))
+    assert [g["materialize"] for g in low.desc["groups"]] == [0, 2]

@@ -92,7 +92,7 @@ def _first_pcg_iteration_reference(name, dims, kind, params, dtype=np.float64, *
     return dict(preconditioner=pre, Ap_X=Ap, delta=alpha * p0, r=r0 - alpha * Ap)
 
 
-@pytest.mark.parametrize("case", ["arap_gather", "arap_residualwise", "ba_materialised", "ba_matrix_free", "laplacian_materialised"])
+@pytest.mark.parametrize("case", ["arap_gather", "arap_residualwise", "arap_jtjp", "ba_materialised", "ba_matrix_free", "laplacian_materialised"])
 @pytest.mark.parametrize("kind", ["gauss_newton", "levenberg_marquardt"])
 def test_first_pcg_iteration_vectors_match_oracle(case, kind):
     """Operator-level parity, independent of how truncated PCG amplifies rounding: after exactly one
@@ -107,7 +107,10 @@ def test_first_pcg_iteration_vectors_match_oracle(case, kind):
         d["Position"] = d["Position"] + 0.2 * rng.randn(*d["Position"].shape).astype(np.float32)
         d["Angle"] = d["Angle"] + 0.3 * rng.randn(*d["Angle"].shape).astype(np.float32)
         dims, name, params = [nx * ny, len(d["V0"])], "arap_mesh_deformation", wl.arap_mesh_params(d)
-        kw["schedule"] = case.split("_", 1)[1]
+        if case == "arap_jtjp":         # Jt[Jp]: J p stored per edge, transposed partials gathered per vertex
+            kw["define_kwargs"] = okw = dict(jp=True)
+        else:
+            kw["schedule"] = case.split("_", 1)[1]
         devslots = range(2, 8)
     elif case.startswith("ba"):
         d = wl.bundle_adjustment_inputs(10, 200, 4)
@@ -236,3 +239,36 @@ def test_config1b_materialised_laplacian_matches_oracle_and_golden():
     s = ThalloSolver([512, 512], "laplacian", "gauss_newton", define_kwargs=dict(materialize=True))
     s.solve([dX, dA])
     assert np.array_equal((dX.cpu().numpy().reshape(512, 512) * 255).astype(np.uint8), gold)
+
+
+@pytest.mark.parametrize("kind", ["gauss_newton", "levenberg_marquardt"])
+def test_arap_mesh_jtjp_schedule_matches_oracle_and_inline(kind):
+    """`r.reg.Jp:set_materialize(true)` (schedule Jt[Jp], thallo.t:4121): same operator as the
+    inline schedule, so GN follows the inline trajectory to float32 rounding; in LM the residual reset
+    (every 10th PCG iteration) leaves the group out of A delta as the reference does (no applyJTJ exists
+    for it, gauss_newton.t:1058-1065), which the oracle restates per group."""
+    from thallo_b200.api import ThalloSolver
+    nx, ny = 24, 18
+    nit, lit = 3, 25
+    dims = [nx * ny, len(wl.arap_mesh_inputs(nx, ny)["V0"])]
+    o, cref = _oracle_costs("arap_mesh_deformation", dims, kind, wl.arap_mesh_params(wl.arap_mesh_inputs(nx, ny)), nit, lit,
+                            define_kwargs=dict(jp=True))
+    p64 = [np.array(x, np.float64) if (i >= 2 and x.dtype == np.float32) else x
+           for i, x in enumerate(wl.arap_mesh_params(wl.arap_mesh_inputs(nx, ny)))]
+    _, cref64 = _oracle_costs("arap_mesh_deformation", dims, kind, p64, nit, lit, np.float64, define_kwargs=dict(jp=True))
+    runs = {}
+    for jp in (True, False):
+        pg = wl.arap_mesh_params(wl.arap_mesh_inputs(nx, ny))
+        dp = [dev(p) if i >= 2 else p for i, p in enumerate(pg)]
+        s = ThalloSolver(dims, "arap_mesh_deformation", kind, define_kwargs=dict(jp=jp))
+        assert [g["materialize"] for g in s.lowered.desc["groups"]] == ([0, 2] if jp else [0, 0])
+        s.set_parameters(nIterations=nit, lIterations=lit)
+        runs[jp] = _trajectory(s, dp)
+        s.close()
+    c, lin = runs[True]
+    assert_costs_close(c, cref, 1e-5, 1e-3, cref64)
+    assert abs(c[1] - cref[1]) <= 1e-5 * abs(cref[1])
+    if kind == "levenberg_marquardt":
+        assert lin == [it["n_lin"] for it in o.trace][:len(lin)]
+    else:
+        assert_costs_close(c, runs[False][0], 1e-5, 1e-3, cref64)

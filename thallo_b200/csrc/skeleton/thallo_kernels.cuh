@@ -140,6 +140,17 @@ __device__ __forceinline__ void th_close_iteration(ThScalars* S, real q_toleranc
     }
 }
 
+// Flat loop over the owned ranges of an unknown-sized vector: 128-bit body `fv(i)` over the aligned
+// middle (i counts real4's) and scalar body `fs(i)` over the at most three elements either side.
+template <class FV, class FS>
+__device__ __forceinline__ void th_for_owned(long long lo, long long hi, FV&& fv, FS&& fs) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const long long gtid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long v0 = (lo + 3) / 4, v1 = hi / 4 > v0 ? hi / 4 : v0;
+    for (long long i = v0 + gtid; i < v1; i += stride) fv(i);
+    for (long long i = lo + gtid; i < (v0 * 4 < hi ? v0 * 4 : hi); i += stride) fs(i);
+    for (long long i = v1 * 4 + gtid; i < hi; i += stride) fs(i);
+}
 // PCGStep2: alpha = rz/aD; delta += alpha p; r -= alpha Ap; z = M r; <z,r>; LM: q = 1/2 <delta, r + b>.
 // Pure streaming: 128-bit loads of every operand first, then the stores (the vectors never alias,
 // but the compiler cannot know that through the pointer table).
@@ -241,8 +252,14 @@ th_step2_first(const __grid_constant__ Vecs V, ThScalars* S) {
     real* __restrict__ vd = V.delta;
 #pragma unroll
     for (int k = 0; k < TH_NRANGES; ++k)
-        for (long long i = th_range_lo(k) + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < th_range_hi(k); i += (long long)gridDim.x * blockDim.x)
-            vd[i] = vd[i] + alpha * pp[i];
+        th_for_owned(th_range_lo(k), th_range_hi(k),
+            [&](long long i) {
+                const real4 p = ((const real4*)pp)[i];
+                real4 d = ((const real4*)vd)[i];
+                d.x = d.x + alpha * p.x; d.y = d.y + alpha * p.y; d.z = d.z + alpha * p.z; d.w = d.w + alpha * p.w;
+                ((real4*)vd)[i] = d;
+            },
+            [&](long long i) { vd[i] = vd[i] + alpha * pp[i]; });
 }
 
 // r = b - A delta; add_ctc: A delta still lacks the CtC*delta term (residualwise / materialized schedules)
@@ -257,21 +274,36 @@ th_step2_second(const __grid_constant__ Vecs V, ThScalars* S, double* partials, 
     const real* __restrict__ vpre = V.pre;
     real* __restrict__ vr = V.r;
     real* __restrict__ vz = V.z;
+    auto lane = [&](real delta, real Ax, real ctc, real b, real pre, real& r, real& z) {
+        if (add_ctc) Ax += ctc * delta;
+        r = b - Ax;
+        z = TH_USEPRE ? pre * r : r;
+        acc[0] += (double)(z * r);
+        acc[1] += (double)((real)0.5 * (delta * (r + b)));
+    };
 #pragma unroll
     for (int k = 0; k < TH_NRANGES; ++k)
-        for (long long i = th_range_lo(k) + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < th_range_hi(k); i += (long long)gridDim.x * blockDim.x) {
-            const real delta = vdl[i];
-            real Ax = vad[i];
-            if (add_ctc) Ax += vctc[i] * delta;
-            const real b = vb[i];
-            const real pre = TH_USEPRE ? vpre[i] : (real)1;
-            const real r = b - Ax;
-            const real z = TH_USEPRE ? pre * r : r;
-            vr[i] = r;
-            vz[i] = z;
-            acc[0] += (double)(z * r);
-            acc[1] += (double)((real)0.5 * (delta * (r + b)));
-        }
+        th_for_owned(th_range_lo(k), th_range_hi(k),
+            [&](long long i) {
+                const real4 dl = ((const real4*)vdl)[i];
+                const real4 ad = ((const real4*)vad)[i];
+                const real4 bb = ((const real4*)vb)[i];
+                real4 ct = dl, pr = dl, r, z;
+                if (add_ctc) ct = ((const real4*)vctc)[i];
+                if (TH_USEPRE) pr = ((const real4*)vpre)[i];
+                lane(dl.x, ad.x, ct.x, bb.x, pr.x, r.x, z.x);
+                lane(dl.y, ad.y, ct.y, bb.y, pr.y, r.y, z.y);
+                lane(dl.z, ad.z, ct.z, bb.z, pr.z, r.z, z.z);
+                lane(dl.w, ad.w, ct.w, bb.w, pr.w, r.w, z.w);
+                ((real4*)vr)[i] = r;
+                ((real4*)vz)[i] = z;
+            },
+            [&](long long i) {
+                real r, z;
+                lane(vdl[i], vad[i], add_ctc ? vctc[i] : (real)0, vb[i], TH_USEPRE ? vpre[i] : (real)1, r, z);
+                vr[i] = r;
+                vz[i] = z;
+            });
     double tot[2];
     if (th_grid_reduce<2>(acc, tot, partials, &S->ticket[2])) {
         if (threadIdx.x == 0) th_step2_publish(S, tot, q_tolerance, hf, epoch);
@@ -285,8 +317,14 @@ th_step3(const __grid_constant__ Vecs V, ThScalars* S, real q_tolerance, ThHostF
     const real beta = th_beta(S);
     const real* __restrict__ vz = V.z;
     real* __restrict__ vp = V.p;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < TH_NUNK; i += (long long)gridDim.x * blockDim.x)
-        vp[i] = vz[i] + beta * vp[i];
+    th_for_owned(0, TH_NUNK,
+        [&](long long i) {
+            const real4 z = ((const real4*)vz)[i];
+            real4 p = ((const real4*)vp)[i];
+            p.x = z.x + beta * p.x; p.y = z.y + beta * p.y; p.z = z.z + beta * p.z; p.w = z.w + beta * p.w;
+            ((real4*)vp)[i] = p;
+        },
+        [&](long long i) { vp[i] = vz[i] + beta * vp[i]; });
     __shared__ bool last;
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -333,13 +371,13 @@ __device__ __forceinline__ void th_mbar_init(unsigned long long* bar, unsigned c
 __device__ __forceinline__ void th_mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(th_smem_u32(bar)), "r"(bytes) : "memory");
 }
-// try_wait suspends the warp in hardware for a bounded time.  3-D tiles: between attempts the warp
-// sleeps so that a CTA waiting for its tile does not take issue slots from the CTAs that are computing
-// (profiles/r01i: the spin was 15 % of the executed instructions of the 3-D operator kernel).  2-D tiles
-// are bandwidth-bound and a late wake-up costs more than the spin (image_warping 2048x2048: th_pcg_a
-// 0.0731 ms with the sleep, 0.0689 ms without; profiles/r01j_sweep.txt), so they spin.
+// try_wait suspends the warp in hardware for a bounded time and is simply retried.  A __nanosleep
+// backoff between attempts (TH_WAIT_SLEEP_NS > 0) was measured and loses on every tiled workload: a late
+// wake-up costs more than the issue slots the spin takes (th_pcg_a, 64 ns vs none: image_warping 2048^2
+// 0.0731 / 0.0689 ms, volumetric 160^3 0.2360 / 0.2270 ms, shape_from_shading 4096^2 0.3891 / 0.3861 ms;
+// profiles/r01j_sweep.txt, r01k_sweep.txt).
 #ifndef TH_WAIT_SLEEP_NS
-#define TH_WAIT_SLEEP_NS (TH_NDIMS == 3 ? 64 : 0)
+#define TH_WAIT_SLEEP_NS 0
 #endif
 __device__ __forceinline__ bool th_mbar_try(unsigned long long* bar, unsigned parity) {
     unsigned ok;
@@ -863,6 +901,27 @@ TH_SPACE_LIST(TH_GATHER_KERNEL)
         }                                                                                                           \
     }
 TH_MAT_LIST(TH_MAT_KERNELS)
+
+// Jt[Jp] schedule of one residual group (APPLY_SEPARATELY, thallo.t:4121): J p per residual row, matrix-free,
+// stored for the gather kernels, which apply the transposed partials.  PCGStep1_J (gauss_newton.t:1027-1034);
+// the scattering PCGStep1_Jt (:1036-1047) and the clear of Jp (:1646) are not needed.
+#ifdef TH_JP_LIST
+#define TH_JP_KERNEL(G_)                                                                                            \
+    extern "C" __global__ void __launch_bounds__(TH_BLOCK)                                                          \
+    th_applyj_g##G_(const __grid_constant__ Params P, const __grid_constant__ Vecs V,                               \
+                    const __grid_constant__ ThGather G, const ThScalars* S) {                                       \
+        if (S->done) return;                                                                                        \
+        ThIdx<th::dom_g##G_> idx;                                                                                   \
+        if (idx.from_linear((long long)blockIdx.x * blockDim.x + threadIdx.x)) {                                    \
+            GAcc<th::dom_g##G_> a(idx, V.p);                                                                        \
+            real jpv[TH_GROUPS[G_].nterms];                                                                         \
+            th::applyJ_g##G_(a, P, jpv);                                                                            \
+            _Pragma("unroll") for (int t = 0; t < TH_GROUPS[G_].nterms; ++t)                                        \
+                G.jp[G_][idx.lin * TH_GROUPS[G_].nterms + t] = jpv[t];                                              \
+        }                                                                                                           \
+    }
+TH_JP_LIST(TH_JP_KERNEL)
+#endif
 
 // Hoisted per-element invariants of one index space (transcendentals of a single unknown element, e.g.
 // sin/cos of a vertex's angles): evaluated once per nonlinear iteration into the plan-owned image

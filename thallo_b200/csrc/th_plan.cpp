@@ -283,8 +283,9 @@ Plan::Plan(const StateOptions* opts, const PlanDesc& desc, const std::string& so
         jvals_.assign(d_.groups.size(), nullptr);
         jp_.assign(d_.groups.size(), nullptr);
         for (size_t g = 0; g < d_.groups.size(); ++g) {
-            if (!d_.groups[g].materialize) continue;
-            CD(cudaMalloc(&jvals_[g], (size_t)d_.groups[g].count * d_.gmats[g].nnzp * real_size_));
+            if (!d_.groups[g].materialize) continue;          // 1: J and J p stored ([Jt][[J]p]); 2: only J p stored (Jt[Jp])
+            if (d_.groups[g].materialize == 1)
+                CD(cudaMalloc(&jvals_[g], (size_t)d_.groups[g].count * d_.gmats[g].nnzp * real_size_));
             CD(cudaMalloc(&jp_[g], (size_t)d_.groups[g].count * d_.gmats[g].nterms * real_size_));
         }
         scoef_.assign(d_.spaces.size(), nullptr);
@@ -539,7 +540,7 @@ void Plan::launch_gather(int which) {
         for (size_t g = 0; g < d_.groups.size(); ++g) {
             if (!d_.groups[g].materialize) continue;
             void* a[] = {P, V, G, &d_scalars_};
-            launch_group(fn("th_matj_g" + std::to_string(g)), (int)g, a);
+            launch_group(fn((d_.groups[g].materialize == 1 ? "th_matj_g" : "th_applyj_g") + std::to_string(g)), (int)g, a);
         }
     for (size_t s = 0; s < d_.spaces.size(); ++s) {
         int first = s == 0;
@@ -827,7 +828,7 @@ int Plan::step(void** params) {
         launch_flat(fn("th_init_finish"), a);
         if (d_.gather)          // precomputeJ (gauss_newton.t:1019-1025, cusparseOuter :1332): store the partial derivatives
             for (size_t g = 0; g < d_.groups.size(); ++g) {
-                if (!d_.groups[g].materialize) continue;
+                if (d_.groups[g].materialize != 1) continue;
                 void* aj[] = {P, gather_buf_.data()};
                 launch_group(fn("th_computejv_g" + std::to_string(g)), (int)g, aj);
             }

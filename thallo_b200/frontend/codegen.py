@@ -168,7 +168,9 @@ class Emitter:
         for n in ad.toposort(roots):
             if n.kind == "const" or n.id in self.names:
                 continue
-            name = ("b%d" if n.type == ad.BOOL else "t%d") % n.id
+            # numbered within the function, not by the DAG's process-wide node ids: the same energy lowers to
+            # the same text in every process (the JIT's disk cache is keyed by the source)
+            name = ("b%d" if n.type == ad.BOOL else "t%d") % (len(self.names) + 1)
             ty = "bool" if n.type == ad.BOOL else "real"
             self.lines.append("const %s %s = %s;" % (ty, name, self.rhs(n)))
             self.names[n.id] = name
@@ -238,19 +240,22 @@ class Generator:
         for g in L.residuals.groups:
             terms = [_Term(L, t) for t in g.terms]
             dom, sparse = _domain_of(L, [t.exp for t in terms])
+            # jtjp schedule of the group (get_schedule, thallo.t:4100-4134): J materialised -> [Jt][[J]p]
+            # (PRECOMPUTE_J); only Jp materialised -> Jt[Jp] (APPLY_SEPARATELY); neither -> JtJp (INLINE)
             self.groups.append(dict(name=g.name, terms=terms, domain=dom, sparse=sparse,
-                                    materialize=g.J.materialize))
+                                    materialize=g.J.materialize,
+                                    storejp=bool(getattr(g, "Jp", None) and g.Jp.materialize) and not g.J.materialize))
         udoms = set(tuple(d.idx for d in im.dims) for im in self.unknowns)
         can_at_output = (len(udoms) == 1 and all((not g["sparse"]) and g["domain"] == next(iter(udoms))
                                                  for g in self.groups)
-                         and not any(g["materialize"] for g in self.groups))
+                         and not any(g["materialize"] or g["storejp"] for g in self.groups))
         self._find_endpoints()
         if schedule == "auto":
             schedule = "at_output" if can_at_output else ("gather" if self.can_gather else "residualwise")
         if schedule == "at_output":
             assert can_at_output, "compute_at_output needs every residual domain to equal the unknown domain"
         if schedule == "residualwise":
-            assert not any(g["materialize"] for g in self.groups), "materialised Jacobians need the gather schedule"
+            assert not any(g["materialize"] or g["storejp"] for g in self.groups), "materialised J / Jp need the gather schedule"
         if schedule == "gather":
             assert self.can_gather, "the gather schedule needs every unknown access to be a sparse index or a dense offset of the residual's own domain"
         self.schedule = schedule
@@ -774,6 +779,20 @@ class Generator:
             if self.hoist_enabled and not g["materialize"]:
                 acc = dict((j, self._hoist_gather(x, hmemo, pmemo)) for j, x in acc.items())
             ep["roots"] = acc
+            if g["storejp"]:        # Jt[Jp]: this endpoint's partials times the stored J p of the residual element
+                tacc = {}
+                for (ti, u, p) in ep["parts"]:
+                    j = sp["slots"][(u.key.image, u.key.channel)]
+                    tacc[j] = tacc.get(j, zero) + p * ad.var(JpVal(ti))
+                if self.hoist_enabled:
+                    tacc = dict((j, self._hoist_gather(x, hmemo, pmemo)) for j, x in tacc.items())
+                ep["jtp_roots"] = tacc
+        for g in self.groups:
+            if g["storejp"]:
+                rows = [t.jp("P") for t in g["terms"]]
+                if self.hoist_enabled:
+                    rows = [self._hoist_gather(x, hmemo, pmemo) for x in rows]
+                g["applyj_roots"] = rows
         from .dsl import Image
         for si, sp in enumerate(self.spaces):       # plan-owned coefficient images (must exist before any function is emitted)
             if self.scoef[si]:
@@ -813,6 +832,13 @@ class Generator:
             src.append(self._fn(
                 "template <class A> __device__ __forceinline__ void matJ_g%d(const A& a, const Params& P, const real* __restrict__ jv, real* __restrict__ jpv)" % gi,
                 rows, lambda r: ["jpv[%d] = %s;" % (i, x) for i, x in enumerate(r)], dom, jq_lines(rows)))
+        # per Jt[Jp] group: J p per residual row, matrix-free (applyJ, thallo.t:3754-3790)
+        for gi, g in enumerate(self.groups):
+            if not g["storejp"]:
+                continue
+            src.append(self._fn(
+                "template <class A> __device__ __forceinline__ void applyJ_g%d(const A& a, const Params& P, real* __restrict__ jpv)" % gi,
+                g["applyj_roots"], lambda r: ["jpv[%d] = %s;" % (i, x) for i, x in enumerate(r)], g["domain"]))
         # per endpoint: contribution of one residual element to the unknowns at that endpoint
         for si, sp in enumerate(self.spaces):
             if self.scoef[si]:
@@ -829,6 +855,12 @@ class Generator:
             src.append(self._fn(
                 "template <class A> __device__ __forceinline__ void jtj_ep%d(const A& a, const Params& P, real* __restrict__ acc)" % ep["id"],
                 [acc[j] for j in js], lambda r, js=js: ["acc[%d] += %s;" % (j, x) for j, x in zip(js, r)], dom))
+            if g["storejp"]:          # applyJt (thallo.t:3808-3841), gathered instead of scattered
+                tacc = ep["jtp_roots"]
+                tjs = sorted(tacc)
+                src.append(self._fn(
+                    "template <class A> __device__ __forceinline__ void jtp_ep%d(const A& a, const Params& P, const real* __restrict__ jpv, real* __restrict__ acc)" % ep["id"],
+                    [tacc[j] for j in tjs], lambda r, tjs=tjs: ["acc[%d] += %s;" % (j, x) for j, x in zip(tjs, r)], dom))
             if g["materialize"]:
                 macc = {}
                 for (ti, u, p) in ep["parts"]:
@@ -866,13 +898,15 @@ class Generator:
                 gi = ep["group"]
                 g = self.groups[gi]
                 mat = bool(g["materialize"])
+                sjp = bool(g["storejp"])
                 call_free = "jtj_ep%d(a, P, acc);" % ep["id"]
+                call_jtp = "jtp_ep%d(a, P, G.jp[%d] + idx.lin * %d, acc);" % (ep["id"], gi, len(g["terms"]))
                 call_mat = ("jt_ep%d(G.jvals[%d] + e * %d, G.jp[%d] + e * %d, acc);" % (ep["id"], gi, g["nnzp"], gi, len(g["terms"])))
                 if ep["kind"] == "sparse":
                     sid = ep["sid"]
                     body.append("{   // endpoint %d: group %s through %s" % (ep["id"], g["name"], ep["sparse"]))
-                    if mat:
-                        body.append("    if (WHICH == 0) {")      # A*delta of the LM reset skips materialised groups (gauss_newton.t:1058-1065)
+                    if mat or sjp:
+                        body.append("    if (WHICH == 0) {")      # A*delta of the LM reset skips groups without an applyJTJ (gauss_newton.t:1058-1065)
                     body.append("    const int lo = __ldg(G.ptr[%d] + t.lin), hi = __ldg(G.ptr[%d] + t.lin + 1);" % (sid, sid))
                     body.append("    const int* __restrict__ perm = G.perm[%d];" % sid)
                     body.append("    for (int i = lo + lane; i < hi; i += LANES) {")
@@ -882,15 +916,15 @@ class Generator:
                     else:
                         body.append("        ThIdx<dom_g%d> idx; idx.from_linear(e);" % gi)
                         body.append("        GAcc<dom_g%d, TH_OWN_ENDPOINT ? %d : -1> a(idx, vec, t.lin);" % (gi, self.ptr_slot[ep["sparse"]]))
-                        body.append("        " + call_free)
+                        body.append("        " + (call_jtp if sjp else call_free))
                     body.append("    }")
-                    if mat:
+                    if mat or sjp:
                         body.append("    }")
                     body.append("}")
                 else:
                     o = ep["off"]
                     body.append("if (lane == 0%s) {   // endpoint %d: group %s at offset (%d, %d, %d)"
-                                % (" && WHICH == 0" if mat else "", ep["id"], g["name"], o[0], o[1], o[2]))
+                                % (" && WHICH == 0" if (mat or sjp) else "", ep["id"], g["name"], o[0], o[1], o[2]))
                     body.append("    const int x = t.c[0] - (%d), y = t.c[1] - (%d), z = t.c[2] - (%d);" % (o[0], o[1], o[2]))
                     body.append("    ThIdx<dom_g%d> idx;" % gi)
                     body.append("    if (x >= 0 && y >= 0 && z >= 0 && idx.from_coords(x, y, z)) {")
@@ -899,7 +933,7 @@ class Generator:
                         body.append("        " + call_mat)
                     else:
                         body.append("        GAcc<dom_g%d> a(idx, vec);" % gi)
-                        body.append("        " + call_free)
+                        body.append("        " + (call_jtp if sjp else call_free))
                     body.append("    }")
                     body.append("}")
             src.append("template <int WHICH, int LANES> __device__ __forceinline__ void gather_s%d(const ThIdx<dom_s%d>& t, int lane, "
@@ -1079,6 +1113,7 @@ class Generator:
             hdr.append("#define TH_NSPACES %d" % len(self.spaces))
             hdr.append("#define TH_SPACE_LIST(X) %s" % " ".join("X(%d)" % i for i in range(len(self.spaces))))
             hdr.append("#define TH_MAT_LIST(X) %s" % " ".join("X(%d)" % gi for gi, g in enumerate(self.groups) if g["materialize"]))
+            hdr.append("#define TH_JP_LIST(X) %s" % " ".join("X(%d)" % gi for gi, g in enumerate(self.groups) if g["storejp"]))
             hdr.append("#define TH_SPACE_TABLE {%s}" % ", ".join("{%d, %d, %dLL}" % (sp["nslots"], sp["lanes"], sp["elements"])
                                                                  for sp in self.spaces))
             mx = max(sp["nslots"] for sp in self.spaces)
@@ -1149,7 +1184,7 @@ class Generator:
             unknowns=[dict(name=im.name, channels=im.channels, offset=self.uoff[im.name], pidx=im.pidx,
                            elements=im.elements, dims=[x.idx for x in im.dims]) for im in self.unknowns],
             groups=[dict(name=g["name"], domain=list(g["domain"]), nterms=len(g["terms"]),
-                         count=_prod(L.dims[x].size for x in g["domain"]), materialize=int(g["materialize"]),
+                         count=_prod(L.dims[x].size for x in g["domain"]), materialize=(1 if g["materialize"] else 2 if g["storejp"] else 0),
                          nnz_per_elem=g["nnz_per_elem"], row_nnz=g["row_nnz"]) for g in self.groups],
         )
         d["computed"] = [dict(elements=ca.elements, ngrad=sum(1 for ch in ca.gchannel if ch >= 0)) for ca in self.computed]

@@ -208,7 +208,7 @@ class _Sched:
 class ResidualGroup:
     def __init__(self, name, terms):
         self.name, self.terms = name, terms
-        self.J, self.JtJ = _Sched(), _Sched()
+        self.J, self.JtJ, self.Jp = _Sched(), _Sched(), _Sched()     # MaterializeInfo of thallo.t:5740-5748
         self.at_output = None
 
     def compute_at_output(self, b):

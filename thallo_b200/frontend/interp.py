@@ -203,6 +203,12 @@ def gather_apply(gen, params, vec, dtype=np.float64, materialised=False):
                 stored[gi] = (jv, [np.array(v) for v in it2.eval(g["matj_roots"])])
             it.jvals, it.jp = stored[gi]
             vals = it.eval([ep["mat_roots"][j] for j in js])
+        elif g.get("storejp"):          # Jt[Jp]: J p per residual row (applyJ_g), then this endpoint's partials times it
+            if gi not in stored:
+                stored[gi] = [np.array(v) for v in Interp(gen, params, g["domain"], vec, dtype).eval(g["applyj_roots"])]
+            it.jp = stored[gi]
+            js = sorted(ep["jtp_roots"])
+            vals = it.eval([ep["jtp_roots"][j] for j in js])
         else:
             vals = it.eval([ep["roots"][j] for j in js])
         if ep["kind"] == "sparse":
