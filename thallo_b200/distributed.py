@@ -100,3 +100,129 @@ class SlabSolver:
 
     def __getattr__(self, name):          # solve / init / step / current_cost / set_parameters / ...
         return getattr(self.solver, name)
+
+
+# ---------------------------------------------------------------------------------------------------
+# Graph domains: contiguous vertex ranges, one per rank.  A residual over the
+# edge domain belongs to the rank that owns the vertex its FIRST index array points at; a rank also holds
+# the foreign edges that touch its vertices through another index array (their J^T J p contributions to
+# its own vertices are gathered locally, so no scatter ever crosses ranks), and copies ("ghosts") of the
+# neighbouring ranks' vertices those edges reach.  With a locality-preserving vertex order (any banded
+# ordering: grid order, RCM) the ghosts of a rank are the tail of the previous rank's range and the head
+# of the next one's, which makes the exchange the 1-D case of the slab exchange: two contiguous blocks.
+def graph_partition(num_vertices, index_arrays, world):
+    """Partition `num_vertices` vertices and the edges described by `index_arrays` (list of int arrays of
+    equal length E; entry e of array k is the vertex edge e reaches through its k-th index) over `world` ranks.
+
+    Returns a list of dicts, one per rank:
+      start, count          owned vertex range [start, start+count)
+      ghost_lo, ghost_hi    ghost vertices held in front of / behind the owned range
+      edges                 global ids of the local edges: owned edges first (ascending), then foreign edges
+      owned_edges           number of owned edges (the first `owned_edges` entries of `edges`)
+    Raises ValueError when an edge reaches beyond the adjacent ranks (vertex order not banded enough)."""
+    N, world = int(num_vertices), int(world)
+    idx = [np.asarray(a).astype(np.int64).reshape(-1) for a in index_arrays]
+    assert idx and all(len(a) == len(idx[0]) for a in idx), "index arrays must have equal length"
+    assert world >= 1 and N >= world, "fewer vertices than ranks"
+    base, rem = divmod(N, world)
+    starts = [r * base + min(r, rem) for r in range(world + 1)]
+    owner = [np.searchsorted(np.asarray(starts[1:]), a, side="right") for a in idx]      # rank owning each endpoint
+    parts = []
+    for r in range(world):
+        s, e = starts[r], starts[r + 1]
+        touches = np.zeros(len(idx[0]), bool)
+        for o in owner:
+            touches |= o == r
+        own = owner[0] == r
+        owned_e = np.nonzero(own)[0]
+        foreign_e = np.nonzero(touches & ~own)[0]
+        edges = np.concatenate([owned_e, foreign_e])
+        lo, hi = s, e
+        for a in idx:
+            if len(edges):
+                lo = min(lo, int(a[edges].min()))
+                hi = max(hi, int(a[edges].max()) + 1)
+        if lo < (starts[r - 1] if r > 0 else 0) or hi > (starts[r + 2] if r + 2 <= world else N):
+            raise ValueError("rank %d: edges reach beyond the adjacent ranks; reorder the vertices (e.g. RCM) "
+                             "so that edges connect nearby vertex ids" % r)
+        parts.append(dict(start=s, count=e - s, ghost_lo=s - lo, ghost_hi=hi - e, edges=edges, owned_edges=len(owned_e)))
+    # a rank's ghosts must not be wider than what the neighbour owns (they are pushed from owned memory)
+    for r in range(world):
+        if r > 0 and parts[r]["ghost_lo"] > parts[r - 1]["count"] or r < world - 1 and parts[r]["ghost_hi"] > parts[r + 1]["count"]:
+            raise ValueError("rank %d: ghost block wider than the neighbouring rank's range" % r)
+    return parts
+
+
+def local_vertex_rows(array, part):
+    """Rows (vertices) of a global per-vertex array a rank holds: ghosts, owned, ghosts."""
+    a = np.asarray(array)
+    return np.ascontiguousarray(a[part["start"] - part["ghost_lo"]:part["start"] + part["count"] + part["ghost_hi"]])
+
+
+def local_index_array(index_array, part):
+    """A global index array restricted to the rank's edges and renumbered to its local vertex ids."""
+    a = np.asarray(index_array).reshape(-1)
+    return np.ascontiguousarray((a[part["edges"]].astype(np.int64) - (part["start"] - part["ghost_lo"])).astype(np.int32))
+
+
+def owned_vertex_rows(local, part):
+    return local[part["ghost_lo"]:part["ghost_lo"] + part["count"]]
+
+
+class GraphSolver:
+    """One rank of a vertex-partitioned graph solve (energies over a vertex domain N and an edge domain E,
+    e.g. arap_mesh_deformation).  `vertex_dim` / `edge_dim` are the positions of N and E in Dims();
+    `index_arrays` the global index arrays in the order the energy declares them (the first one decides
+    which rank owns an edge)."""
+
+    def __init__(self, global_dims, energy, kind, rank, world, index_arrays, vertex_dim=0, edge_dim=1, double=False,
+                 group=None, **kw):
+        import torch.distributed as dist
+        from .api import ThalloSolver, lib
+        self.rank, self.world = rank, world
+        self.parts = graph_partition(global_dims[vertex_dim], index_arrays, world)
+        self.part = p = self.parts[rank]
+        self.local_dims = list(global_dims)
+        self.local_dims[vertex_dim] = p["ghost_lo"] + p["count"] + p["ghost_hi"]
+        self.local_dims[edge_dim] = len(p["edges"])
+        partition = None
+        if world > 1:
+            partition = {vertex_dim: (p["ghost_lo"], p["ghost_hi"]), edge_dim: (0, len(p["edges"]) - p["owned_edges"])}
+        self.solver = ThalloSolver(self.local_dims, energy, kind, double=double, partition=partition, schedule="gather", **kw)
+        if world > 1:
+            L = lib()
+            s = self.solver
+            idbuf = C.create_string_buffer(128)
+            if rank == 0:
+                assert L.ThalloB200_NcclUniqueId(idbuf, 128) == 0, "ncclGetUniqueId failed"
+            box = [bytes(idbuf.raw)]
+            dist.broadcast_object_list(box, src=0, group=group)
+            assert L.ThalloB200_PlanInitComm(s.state, s.plan, box[0], rank, world) == 0, L.ThalloB200_LastError().decode()
+            h = C.create_string_buffer(64)
+            extent = C.c_longlong(0)
+            assert L.ThalloB200_PlanIpcHandle(s.state, s.plan, h, C.byref(extent)) == 0
+            # what a neighbour needs to address this rank's ghost blocks: the handle, the local vertex count
+            # and the width of the ghost block facing it
+            mine = (bytes(h.raw), int(extent.value), p["ghost_lo"], p["ghost_hi"])
+            everyone = [None] * world
+            dist.all_gather_object(everyone, mine, group=group)
+            lo = everyone[rank - 1] if rank > 0 else None
+            hi = everyone[rank + 1] if rank < world - 1 else None
+            rc = L.ThalloB200_PlanConnectGraph(
+                s.state, s.plan,
+                lo[0] if lo else None, lo[1] if lo else 0, lo[3] if lo else 0,       # lower neighbour: its ghost_hi block is filled from here
+                hi[0] if hi else None, hi[1] if hi else 0, hi[2] if hi else 0)       # upper neighbour: its ghost_lo block
+            assert rc == 0, L.ThalloB200_LastError().decode()
+            self._keep = (box, everyone)
+
+    def vertex_rows(self, global_array):
+        return local_vertex_rows(global_array, self.part)
+
+    def index_array(self, global_index_array):
+        return local_index_array(global_index_array, self.part)
+
+    def owned(self, local_array):
+        return owned_vertex_rows(local_array, self.part)
+
+    def __getattr__(self, name):
+        return getattr(self.solver, name)
