@@ -64,6 +64,18 @@ int ThalloB200_PlanIpcHandle(Thallo_State* state, Thallo_Plan* plan, void* handl
 int ThalloB200_PlanConnect(Thallo_State* state, Thallo_Plan* plan, const void* handle_lo, long long extent_lo,
                            const void* handle_hi, long long extent_hi);
 
+/* ---- multi-GPU: vertex partition of a graph domain (energies over a vertex domain and an edge
+ * domain, gather schedule).  Every rank owns a contiguous vertex range and lowers the energy for its LOCAL
+ * vertices (ghost copies of the neighbouring ranks' vertices in front of and behind the owned range) and its
+ * local edges (the edges it owns first, then the foreign edges that touch its vertices); descriptor line
+ * "gpartition", see thallo_b200/distributed.py graph_partition.  Communicator and IPC handle as above
+ * (*slow_extent = number of local vertices); instead of ThalloB200_PlanConnect:
+ *   ThalloB200_PlanConnectGraph   map the neighbours' solver vectors; width_lo / width_hi = how many of THIS rank's
+ *                                 first / last owned vertices the lower / upper neighbour holds as ghosts.  The
+ *                                 ghost values of p / z / delta are stored straight into the neighbours' memory. */
+int ThalloB200_PlanConnectGraph(Thallo_State* state, Thallo_Plan* plan, const void* handle_lo, long long extent_lo,
+                                long long width_lo, const void* handle_hi, long long extent_hi, long long width_hi);
+
 /* Known-answer tests of the warp primitives behind the residualwise scatter path (ballot, peer
  * discovery by key, by-key reduction before the atomic), written after the reference's
  * tests/cuda_unit_tests/{ballot,get_peers,reduce_peers}.t; one warp each on the current device.

@@ -1,0 +1,115 @@
+"""Multi-GPU parity check for graph domains, run under torchrun (one rank per GPU):
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 tests/mgpu_graph_check.py
+Solves the same global arap_mesh_deformation problem (a) vertex-partitioned over all ranks (ghost vertices
+over NVLink peer stores, PCG scalars over NCCL) and (b) on one GPU, and compares every cost of the
+trajectory, the LM inner iteration counts and the unknowns.  Exit code 0 = parity.
+Called by tests/test_gpu_multi.py.  `--bench N` instead times an N x N mesh (PCG iterations / s)."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+VERTEX = ("Position", "Angle", "Original", "Constraints")
+
+
+def trajectory(s, params):
+    s.init(params)
+    costs, lin = [s.current_cost()], []
+    while s.step():
+        costs.append(s.current_cost())
+        lin.append(s.last_linear_iterations())
+    costs.append(s.current_cost())
+    return costs, lin
+
+
+def run(kind, nx, ny, nit, lit, dist, rank, world, torch):
+    from thallo_b200 import workloads as wl
+    from thallo_b200.api import ThalloSolver
+    from thallo_b200.distributed import GraphSolver
+    d = wl.arap_mesh_inputs(nx, ny)
+    N, E = nx * ny, len(d["V0"])
+    scal = [np.array([d["w_fitSqrt"]], np.float32), np.array([d["w_regSqrt"]], np.float32)]
+    s = GraphSolver([N, E], "arap_mesh_deformation", kind, rank, world, [d["V0"], d["V1"]])
+    loc = [torch.from_numpy(s.vertex_rows(d[k])).cuda() for k in VERTEX]
+    idx = [torch.from_numpy(s.index_array(d[k])).cuda() for k in ("V0", "V1")]
+    s.set_parameters(nIterations=nit, lIterations=lit)
+    costs, lin = trajectory(s, scal + loc + idx)
+    torch.cuda.synchronize()
+    own = [s.owned(t.cpu().numpy()) for t in loc[:2]]
+    gathered = [None] * world
+    dist.all_gather_object(gathered, own)
+    ok = True
+    if rank == 0:
+        pos = np.concatenate([g[0] for g in gathered])
+        ang = np.concatenate([g[1] for g in gathered])
+        d1 = wl.arap_mesh_inputs(nx, ny)
+        one = [torch.from_numpy(np.ascontiguousarray(d1[k])).cuda() for k in VERTEX + ("V0", "V1")]
+        r = ThalloSolver([N, E], "arap_mesh_deformation", kind, schedule="gather")
+        r.set_parameters(nIterations=nit, lIterations=lit)
+        c1, l1 = trajectory(r, scal + one)
+        rel = max(abs(a - b) / max(abs(b), 1e-3) for a, b in zip(costs, c1)) if len(costs) == len(c1) else float("inf")
+        dp = float(np.abs(pos - one[0].cpu().numpy()).max())
+        da = float(np.abs(ang - one[1].cpu().numpy()).max())
+        ok = len(costs) == len(c1) and rel <= 1e-5 and lin == l1 and dp < 1e-3 and da < 1e-3
+        print("mgpu graph %s %dx%d world=%d (ghosts %s): max rel cost diff %.3g, lin %s vs %s, max|dPosition| %.3g max|dAngle| %.3g -> %s"
+              % (kind, nx, ny, world, [(p["ghost_lo"], p["ghost_hi"]) for p in s.parts], rel, lin, l1, dp, da, "OK" if ok else "MISMATCH"),
+              flush=True)
+        if not ok:
+            print(costs, c1, flush=True)
+    return ok
+
+
+def bench(n, dist, rank, world, torch):
+    """Weak scaling: n x (n * world) mesh, n*n owned vertices per rank."""
+    from thallo_b200 import workloads as wl
+    from thallo_b200.distributed import GraphSolver
+    d = wl.arap_mesh_inputs(n, n * world)
+    N, E = n * n * world, len(d["V0"])
+    scal = [np.array([d["w_fitSqrt"]], np.float32), np.array([d["w_regSqrt"]], np.float32)]
+    s = GraphSolver([N, E], "arap_mesh_deformation", "gauss_newton", rank, world, [d["V0"], d["V1"]])
+    loc0 = [s.vertex_rows(d[k]) for k in VERTEX]
+    idx = [torch.from_numpy(s.index_array(d[k])).cuda() for k in ("V0", "V1")]
+    nit, lit = 2, 50
+    s.set_parameters(nIterations=nit, lIterations=lit)
+    ms = []
+    for rep in range(4):
+        loc = [torch.from_numpy(a.copy()).cuda() for a in loc0]
+        torch.cuda.synchronize(); dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        s.solve(scal + loc + idx)
+        e1.record(); torch.cuda.synchronize()
+        ms.append(e0.elapsed_time(e1))
+    t = torch.tensor([min(ms[1:])], dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        import json
+        print(json.dumps({"workload": "arap_mesh %dx%d (%d vertices per GPU)" % (n, n * world, n * n), "n_gpus": world,
+                          "pcg_iterations_per_s": nit * lit / (float(t[0]) * 1e-3), "ms_per_solve": float(t[0]),
+                          "slab_pcg_iterations_per_s": world * nit * lit / (float(t[0]) * 1e-3), "final_cost": s.current_cost()}), flush=True)
+    return True
+
+
+def main():
+    import torch
+    import torch.distributed as dist
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("gloo")
+    ok = True
+    if len(sys.argv) > 2 and sys.argv[1] == "--bench":
+        bench(int(sys.argv[2]), dist, rank, world, torch)
+    else:
+        for kind, nx, ny, nit, lit in [("gauss_newton", 40, 36, 3, 25), ("levenberg_marquardt", 48, 50, 4, 30)]:
+            ok = run(kind, nx, ny, nit, lit, dist, rank, world, torch) and ok
+    flag = [ok]
+    dist.broadcast_object_list(flag, src=0)
+    dist.destroy_process_group()
+    sys.exit(0 if flag[0] else 1)
+
+
+if __name__ == "__main__":
+    main()

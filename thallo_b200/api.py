@@ -83,6 +83,8 @@ def lib():
     L.ThalloB200_PlanIpcHandle.argtypes = [vp, vp, vp, C.POINTER(C.c_longlong)]
     L.ThalloB200_PlanConnect.restype = C.c_int
     L.ThalloB200_PlanConnect.argtypes = [vp, vp, vp, C.c_longlong, vp, C.c_longlong]
+    L.ThalloB200_PlanConnectGraph.restype = C.c_int
+    L.ThalloB200_PlanConnectGraph.argtypes = [vp, vp, vp, C.c_longlong, C.c_longlong, vp, C.c_longlong, C.c_longlong]
     L.ThalloB200_WarpSelfTest.restype = C.c_int
     L.ThalloB200_WarpSelfTest.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_double), C.c_int]
     L.ThalloB200_LastError.restype, L.ThalloB200_LastError.argtypes = cp, []

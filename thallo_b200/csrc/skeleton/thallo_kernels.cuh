@@ -24,6 +24,30 @@
 #pragma once
 #include "thallo_access.cuh"
 
+// Does this rank own domain element `i`?  Single GPU: always; slab partition: its slowest coordinate lies in the
+// owned layers; graph partition: every coordinate lies in the owned range of its dimension.
+template <class Dom> __device__ __forceinline__ bool th_owned(const ThIdx<Dom>& i) {
+#if TH_MULTI && defined(TH_PART_TABLE)
+    bool ok = i.c[0] >= TH_PART[Dom::I0].lo && i.c[0] < Dom::D0 - TH_PART[Dom::I0].hi;
+    if (Dom::ND > 1) ok = ok && i.c[1] >= TH_PART[Dom::I1].lo && i.c[1] < Dom::D1 - TH_PART[Dom::I1].hi;
+    if (Dom::ND > 2) ok = ok && i.c[2] >= TH_PART[Dom::I2].lo && i.c[2] < Dom::D2 - TH_PART[Dom::I2].hi;
+    return ok;
+#else
+    return th_owned_slow(i.c[Dom::ND - 1]);
+#endif
+}
+// flat index of an unknown scalar -> owned by this rank?
+__device__ __forceinline__ bool th_flat_owned(long long f) {
+#if TH_MULTI
+    bool ok = false;
+#pragma unroll
+    for (int k = 0; k < TH_NRANGES; ++k) ok = ok || (f >= th_range_lo(k) && f < th_range_hi(k));
+    return ok;
+#else
+    return true;
+#endif
+}
+
 // ================================================================== at-output (unknownwise) kernels
 #if TH_AT_OUTPUT
 extern "C" __global__ void __launch_bounds__(TH_BLOCK)
@@ -314,7 +338,11 @@ th_step2_second(const __grid_constant__ Vecs V, ThScalars* S, double* partials, 
 extern "C" __global__ void __launch_bounds__(TH_BLOCK)
 th_step3(const __grid_constant__ Vecs V, ThScalars* S, real q_tolerance, ThHostFlags* hf, int epoch) {
     if (S->done) return;
+#if TH_MULTI
+    const real beta = th_beta_prev(S);       // th_mg_close has already closed the iteration (after the all-reduce of <z,r>)
+#else
     const real beta = th_beta(S);
+#endif
     const real* __restrict__ vz = V.z;
     real* __restrict__ vp = V.p;
     th_for_owned(0, TH_NUNK,
@@ -325,6 +353,7 @@ th_step3(const __grid_constant__ Vecs V, ThScalars* S, real q_tolerance, ThHostF
             ((real4*)vp)[i] = p;
         },
         [&](long long i) { vp[i] = vz[i] + beta * vp[i]; });
+#if !TH_MULTI
     __shared__ bool last;
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -336,6 +365,7 @@ th_step3(const __grid_constant__ Vecs V, ThScalars* S, real q_tolerance, ThHostF
         S->ticket[3] = 0u;
         th_close_iteration(S, q_tolerance, hf, epoch);
     }
+#endif
 }
 
 // ================================================================== hoisted invariants
@@ -765,6 +795,7 @@ extern "C" __global__ void __launch_bounds__(TH_BLOCK)
 th_init_finish(const __grid_constant__ Params P, const __grid_constant__ Vecs V, ThScalars* S, double* partials, int first_nonlinear) {
     double acc[1] = {0.0};
     for (long long f = (long long)blockIdx.x * blockDim.x + threadIdx.x; f < TH_NUNK; f += (long long)gridDim.x * blockDim.x) {
+        if (!th_flat_owned(f)) continue;       // ghost entries (graph partition) are the owner's to initialise; p arrives by push
         if (th_excluded(f, P)) { th_zero_scalar(V, f); continue; }
         acc[0] += (double)th_init_scalar(P, V, f, -V.r[f], V.pre[f], (real)1, first_nonlinear);   // pre := 1 when off, gauss_newton.t:718-722
     }
@@ -832,7 +863,7 @@ template <int LANES> __device__ __forceinline__ real th_lanes_sum_real(real v) {
         real* __restrict__ out = which ? V.Adelta : V.Ap;                                                           \
         double acc1[1] = {0.0};                                                                                     \
         ThIdx<th::dom_s##SP> t;                                                                                     \
-        const bool valid = t.from_linear(gt / LANES);                                                               \
+        const bool valid = t.from_linear(gt / LANES) && th_owned(t);   /* ghost vertices: the owner computes Ap */  \
         bool ex = true;                                                                                             \
         real acc[NS];                                                                                               \
         _Pragma("unroll") for (int j = 0; j < NS; ++j) acc[j] = (real)0;                                            \
@@ -988,7 +1019,7 @@ TH_COMPUTED_LIST(TH_COMPUTED_KERNEL)
         ThIdx<th::dom_g##G> idx;                                                                                    \
         double acc[1] = {0.0};                                                                                      \
         if (idx.from_linear((long long)blockIdx.x * blockDim.x + threadIdx.x) &&                                    \
-            th_owned_slow(idx.c[th::dom_g##G::ND - 1])) {                                                           \
+            th_owned(idx)) {                                                                                        \
             GAcc<th::dom_g##G> a(idx, nullptr);                                                                     \
             acc[0] = (double)th::cost_g##G(a, P);                                                                   \
         }                                                                                                           \
@@ -1003,7 +1034,7 @@ TH_COMPUTED_LIST(TH_COMPUTED_KERNEL)
         ThIdx<th::dom_g##G> idx;                                                                                    \
         double acc[1] = {0.0};                                                                                      \
         if (idx.from_linear((long long)blockIdx.x * blockDim.x + threadIdx.x) &&                                    \
-            th_owned_slow(idx.c[th::dom_g##G::ND - 1])) {                                                           \
+            th_owned(idx)) {                                                                                        \
             GAcc<th::dom_g##G> a(idx, V.delta);                                                                     \
             acc[0] = (double)th::modelcost_g##G(a, P);                                                              \
         }                                                                                                           \

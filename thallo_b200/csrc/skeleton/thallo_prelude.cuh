@@ -115,7 +115,18 @@ struct ThSlot { int image; int channel; };
 #define TH_GHOST_LO 0
 #define TH_GHOST_HI 0
 #endif
-#if TH_MULTI
+#if TH_MULTI && defined(TH_PART_TABLE)
+// graph partition (gather schedule): per dimension the owned index range [lo, size - hi) -- ghost vertices in
+// front of / behind the owned vertices, foreign edges behind the owned edges -- and per unknown image the flat
+// range of its owned scalars
+struct ThPart { long long lo, hi; };
+__device__ constexpr ThPart TH_PART[TH_NDIMS] = TH_PART_TABLE;
+__device__ constexpr ThPart TH_RANGE[TH_NUM_UIMG] = TH_RANGE_TABLE;
+#define TH_NRANGES TH_NUM_UIMG
+__device__ constexpr long long th_range_lo(int k) { return TH_RANGE[k].lo; }
+__device__ constexpr long long th_range_hi(int k) { return TH_RANGE[k].hi; }
+__device__ __forceinline__ bool th_owned_slow(int) { return true; }
+#elif TH_MULTI
 #define TH_NRANGES TH_NUM_UIMG
 __device__ constexpr long long th_range_lo(int k) {
     return TH_UIMG[k].offset + (long long)TH_GHOST_LO * (TH_UIMG[k].elements / TH_DSLOW) * TH_UIMG[k].channels;

@@ -225,6 +225,10 @@ int ThalloB200_PlanConnect(Thallo_State*, Thallo_Plan* plan, const void* handle_
                            long long extent_hi) {
     return plan ? plan->plan->connect(handle_lo, extent_lo, handle_hi, extent_hi) : 1;
 }
+int ThalloB200_PlanConnectGraph(Thallo_State*, Thallo_Plan* plan, const void* handle_lo, long long extent_lo, long long width_lo,
+                                const void* handle_hi, long long extent_hi, long long width_hi) {
+    return plan ? plan->plan->connect_graph(handle_lo, extent_lo, width_lo, handle_hi, extent_hi, width_hi) : 1;
+}
 int ThalloB200_WarpSelfTest(int which, int nkeys, double* out, int capacity) {
     if (!out || capacity <= 0 || which < 0 || which > 2) return -1;
     if (nkeys < 1 || nkeys > 32) nkeys = 4;

@@ -74,6 +74,7 @@ bool parse_descriptor(const std::string& text, PlanDesc& d, std::string& err) {
         else if (key == "ncoef") ls >> d.ncoef;
         else if (key == "computed") { int k; long long n; int g; ls >> k >> n >> g; d.computed.push_back({n, g}); }
         else if (key == "partition") { ls >> d.ghost_lo >> d.ghost_hi; d.multi = true; }
+        else if (key == "gpartition") { ls >> d.part_dim >> d.part_extent >> d.ghost_lo >> d.ghost_hi; d.multi = d.gmulti = true; }
         else if (key == "tile") {
             ls >> d.tile[0] >> d.tile[1] >> d.tile[2] >> d.halo[0] >> d.halo[1] >> d.halo[2] >> d.smem_bytes;
             if (!(ls >> d.pipe)) d.pipe = 2;
@@ -139,7 +140,7 @@ int Plan::ipc_handle(void* handle64, long long* slow_extent) {
     CD(cudaIpcGetMemHandle(&h, vec_block_));
     static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
     memcpy(handle64, &h, 64);
-    if (slow_extent) *slow_extent = d_.uw_dims.back();
+    if (slow_extent) *slow_extent = d_.gmulti ? d_.part_extent : d_.uw_dims.back();
     return 0;
 }
 int Plan::connect(const void* handle_lo, long long extent_lo, const void* handle_hi, long long extent_hi) {
@@ -154,6 +155,15 @@ int Plan::connect(const void* handle_lo, long long extent_lo, const void* handle
     }
     return 0;
 }
+// graph partition: besides the mapping, the width of each neighbour's ghost block that faces this rank
+int Plan::connect_graph(const void* handle_lo, long long extent_lo, long long width_lo, const void* handle_hi, long long extent_hi,
+                        long long width_hi) {
+    if (!d_.gmulti) { error_ = "plan was not lowered with a graph partition"; return 1; }
+    peer_width_[0] = width_lo; peer_width_[1] = width_hi;
+    const long long owned = d_.part_extent - d_.ghost_lo - d_.ghost_hi;
+    if (width_lo > owned || width_hi > owned) { error_ = "a neighbour's ghost block is wider than this rank's owned range"; return 1; }
+    return connect(handle_lo, extent_lo, handle_hi, extent_hi);
+}
 // sum a few doubles of the device scalar block over all ranks, in place, on the solver stream (NVLink / NVLS)
 void Plan::allreduce(size_t off, int count) {
     if (!comm_) { fprintf(stderr, "thallo_b200: multi-GPU plan used before ThalloB200_PlanInitComm\n"); exit(1); }
@@ -165,14 +175,17 @@ void Plan::allreduce(size_t off, int count) {
 // all-reduce contribution in stream order, and a neighbour reads its ghost layers only after that
 // all-reduce has completed on its side.
 void Plan::halo_push(int vec, int check_done) {
+    // slab: D layers of the slowest axis, h stencil-halo layers per side; graph: D local vertices, per side as many
+    // vertices as the neighbour keeps ghosts of this rank's
     const int nd = (int)d_.uw_dims.size();
-    const long long D = d_.uw_dims[nd - 1];
-    const int h = d_.halo[nd - 1];
-    if (h == 0 || world_ == 1) return;
+    const long long D = d_.gmulti ? d_.part_extent : d_.uw_dims[nd - 1];
+    const long long hs[2] = {d_.gmulti ? peer_width_[0] : (long long)d_.halo[nd - 1], d_.gmulti ? peer_width_[1] : (long long)d_.halo[nd - 1]};
+    if ((hs[0] == 0 && hs[1] == 0) || world_ == 1) return;
     struct Segs { const void* src[8]; void* dst[8]; long long count[8]; } g{};
     int n = 0;
     for (int side = 0; side < 2; ++side) {
-        if (!peer_[side]) continue;
+        if (!peer_[side] || hs[side] == 0) continue;
+        const long long h = hs[side];
         const long long E = peer_extent_[side];
         long long peer_off = 0, peer_nunk = 0;
         for (auto& u : d_.unknowns) peer_nunk += (u.elements / D) * E * u.channels;
@@ -734,6 +747,7 @@ void Plan::linear_iteration(int l) {
         launch_uw(fn("th_step1_uw"), a);
     } else if (d_.gather) {
         launch_gather(0);
+        if (d_.multi) allreduce(offsetof(HScalars, aD), 1);
     } else {
         clear(vecs_[V_AP]);
         for (size_t g = 0; g < d_.groups.size(); ++g) {
@@ -761,6 +775,10 @@ void Plan::linear_iteration(int l) {
             void* a[] = {P, V, &d_scalars_, &d_partials_, &one};
             launch_uw(fn("th_step1_uw"), a);
         } else if (d_.gather) {
+            if (d_.multi) {       // A*delta reads delta at the ghost vertices
+                halo_push(V_DELTA, 1);
+                allreduce(offsetof(HScalars, spare), 1);
+            }
             launch_gather(1);        // materialised groups contribute nothing to A*delta (gauss_newton.t:1058-1065: no applyJTJ exists for them)
         } else {
             clear(vecs_[V_ADELTA]);
@@ -826,6 +844,10 @@ int Plan::step(void** params) {
         }
         void* a[] = {P, V, &d_scalars_, &d_partials_, &first};
         launch_flat(fn("th_init_finish"), a);
+        if (d_.multi) {                       // p0 at the ghost vertices, global <r,p>
+            halo_push(V_P, 0);
+            allreduce(offsetof(HScalars, rz), 1);
+        }
         if (d_.gather)          // precomputeJ (gauss_newton.t:1019-1025, cusparseOuter :1332): store the partial derivatives
             for (size_t g = 0; g < d_.groups.size(); ++g) {
                 if (d_.groups[g].materialize != 1) continue;

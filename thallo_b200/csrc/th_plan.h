@@ -53,6 +53,11 @@ struct PlanDesc {
     // multi-GPU slab partition ("partition" line): ghost layers of the slowest axis included in dims
     bool multi = false;
     int ghost_lo = 0, ghost_hi = 0;
+    // multi-GPU graph partition ("gpartition" line, gather schedule): dimension of the vertex domain every
+    // unknown image lives on, its local extent and the ghost vertices in front of / behind the owned range
+    bool gmulti = false;
+    int part_dim = -1;
+    long long part_extent = 0;
 };
 bool parse_descriptor(const std::string& text, PlanDesc& d, std::string& err);
 int nccl_unique_id(void* out, int capacity);
@@ -106,6 +111,8 @@ public:
     int comm_init(const void* nccl_id, int rank, int world);
     int ipc_handle(void* handle64, long long* slow_extent);
     int connect(const void* handle_lo, long long extent_lo, const void* handle_hi, long long extent_hi);
+    int connect_graph(const void* handle_lo, long long extent_lo, long long width_lo, const void* handle_hi, long long extent_hi,
+                      long long width_hi);
     // per-kernel device times (timingLevel >= 2, like util.t:774-790): "name count total_ms\n" lines
     std::string kernel_times();
 
@@ -157,6 +164,7 @@ private:
     int rank_ = 0, world_ = 1;
     char* peer_[2] = {nullptr, nullptr};            // neighbours' solver-vector blocks (CUDA IPC mappings): lo, hi
     long long peer_extent_[2] = {0, 0};
+    long long peer_width_[2] = {0, 0};              // graph partition: width of the neighbour's ghost block this rank fills
     void allreduce(size_t scalars_offset, int count);
     void halo_push(int vec, int check_done);
     void* dscalar(size_t off) const { return (char*)d_scalars_ + off; }

@@ -208,6 +208,12 @@ class Generator:
                  partition=None):
         self.L, self.name = L, name
         # multi-GPU slab partition: (ghost_lo, ghost_hi) ghost layers of the slowest axis included in `dims`
+        # or, for graph domains in the gather schedule, {dim index: (lo, hi)}: elements [lo, size - hi) of that
+        # dimension are owned by this rank, the others are ghost vertices / foreign edges (distributed.graph_partition)
+        self.gpartition = None
+        if isinstance(partition, dict):
+            self.gpartition = dict((int(k), (int(v[0]), int(v[1]))) for k, v in partition.items())
+            partition = None
         self.partition = tuple(int(x) for x in partition) if partition is not None else None
         self.hoist_enabled = bool(hoist)
         self.tile_request = tile
@@ -1051,6 +1057,20 @@ class Generator:
         hdr.append("#define TH_USEPRE %d" % int(L.usepreconditioner))
         hdr.append("#define TH_AT_OUTPUT %d" % int(self.schedule == "at_output"))
         hdr.append("#define TH_GATHER %d" % int(self.schedule == "gather"))
+        if self.gpartition is not None:
+            assert self.schedule == "gather", "a graph partition needs the gather schedule"
+            assert not self.computed, "computed arrays are not supported by the multi-GPU graph partition yet"
+            vdims = set(tuple(d.idx for d in im.dims) for im in self.unknowns)
+            assert len(vdims) == 1 and len(next(iter(vdims))) == 1, \
+                "a graph partition needs every unknown to live on one 1-D vertex domain"
+            vd = next(iter(vdims))[0]
+            glo, ghi = self.gpartition.get(vd, (0, 0))
+            hdr.append("#define TH_MULTI 1")
+            hdr.append("#define TH_PART_TABLE {%s}" % ", ".join("{%dLL, %dLL}" % self.gpartition.get(d.idx, (0, 0)) for d in L.dims))
+            hdr.append("#define TH_RANGE_TABLE {%s}" % ", ".join(
+                "{%dLL, %dLL}" % (self.uoff[im.name] + glo * im.channels, self.uoff[im.name] + (im.elements - ghi) * im.channels)
+                for im in self.unknowns))
+            self.gpart_line = (vd, L.dims[vd].size, glo, ghi)
         if self.partition is not None:
             assert self.tiled, "multi-GPU partitioning needs the tiled at-output schedule (2-D / 3-D image domain)"
             assert all(tuple(g["domain"]) == tuple(self.udomain) for g in self.groups), \
@@ -1156,8 +1176,10 @@ class Generator:
 
         def dom_struct(nm, dimidx):
             sz = [L.dims[x].size for x in dimidx] + [1] * (MAXD - len(dimidx))
-            return ("struct %s { static constexpr int ND = %d; static constexpr long long D0 = %d, D1 = %d, D2 = %d; };"
-                    % (nm, len(dimidx), sz[0], sz[1], sz[2]))
+            ix = list(dimidx) + [0] * (MAXD - len(dimidx))
+            return ("struct %s { static constexpr int ND = %d; static constexpr long long D0 = %d, D1 = %d, D2 = %d; "
+                    "static constexpr int I0 = %d, I1 = %d, I2 = %d; };"
+                    % (nm, len(dimidx), sz[0], sz[1], sz[2], ix[0], ix[1], ix[2]))
         for k, im in enumerate(self.unknowns):
             doms.append(dom_struct("dom_u%d" % k, [x.idx for x in im.dims]))
         if self.schedule == "at_output":
@@ -1187,6 +1209,8 @@ class Generator:
                          count=_prod(L.dims[x].size for x in g["domain"]), materialize=(1 if g["materialize"] else 2 if g["storejp"] else 0),
                          nnz_per_elem=g["nnz_per_elem"], row_nnz=g["row_nnz"]) for g in self.groups],
         )
+        if self.gpartition is not None:
+            d["gpartition"] = self.gpart_line
         d["computed"] = [dict(elements=ca.elements, ngrad=sum(1 for ch in ca.gchannel if ch >= 0)) for ca in self.computed]
         if self.schedule == "gather":
             d["gather"] = dict(
@@ -1240,6 +1264,8 @@ def descriptor_text(d):
                                                       " ".join(map(str, g["row_nnz"]))))
     for k, c in enumerate(d.get("computed", [])):
         ln.append("computed %d %d %d" % (k, c["elements"], c["ngrad"]))
+    if d.get("gpartition") is not None:
+        ln.append("gpartition %d %d %d %d" % tuple(d["gpartition"]))
     if d["schedule"] == "gather":
         ga = d["gather"]
         for sp in ga["spaces"]:
