@@ -249,3 +249,42 @@ def test_two_rank_gloo_ghost_vertex_exchange():
     for p in ps:
         p.join(60)
     assert res == [(0, True, True), (1, True, True)]
+
+
+# ---------------------------------------------------------------- slab partition of energies with absolute coordinates
+@pytest.mark.parametrize("name", ["shape_from_shading", "optical_flow"])
+def test_slab_local_operators_equal_the_global_ones(name):
+    """Computed arrays (evaluated on owned + ghost layers), index VALUES (offset by the slab origin) and sampled
+    images (row offset of the local slab): the generated at-output operators of every rank's local problem equal
+    the global problem's on the owned rows."""
+    import energies
+    from thallo_b200 import workloads as wl
+    from thallo_b200.frontend import codegen, interp
+    W, H, world = 24, 30, 3
+    if name == "shape_from_shading":
+        params = [np.asarray(p, np.float64) if np.asarray(p).dtype == np.float32 else p for p in wl.sfs_params(wl.sfs_inputs(W, H))]
+        images, uslot, kind = [16, 17, 18, 19, 20], 16, "gauss_newton"
+    else:
+        d = wl.optical_flow_inputs(W, H)
+        d["X"] = (0.4 * np.random.RandomState(2).randn(W * H, 2)).astype(np.float32)        # |flow| < ghost width
+        params = [np.asarray(p, np.float64) for p in wl.optical_flow_params(d)]
+        images, uslot, kind = [2, 3, 4, 5, 6], 2, "gauss_newton"
+    define = energies.load(name)
+    low = codegen.lower(define, [W, H], kind, name, True, "at_output")
+    U = low.generator.U
+    pvec = np.random.RandomState(4).randn(W * H * U)
+    g0, d0, o0 = interp.unknownwise(low.generator, params, pvec)
+    halo = D.stencil_halo(name, [W, H], kind)
+    parts = D.slab_partition(H, world, halo)
+    for part in parts:
+        ext = part["count"] + part["ghost_lo"] + part["ghost_hi"]
+        lp = [D.local_slab(np.asarray(p).reshape(W * H, -1), W, part).reshape((-1,) + np.asarray(p).shape[1:]) if i in images else p
+              for i, p in enumerate(params)]
+        origin = part["start"] - part["ghost_lo"]
+        lowl = codegen.lower(define, [W, ext], kind, name, True, "at_output", partition=(part["ghost_lo"], part["ghost_hi"], origin))
+        pl = D.local_slab(pvec.reshape(W * H, U), W, part).reshape(-1)
+        g, d, o = interp.unknownwise(lowl.generator, lp, pl)
+        a, b = part["ghost_lo"] * W * U, (part["ghost_lo"] + part["count"]) * W * U
+        ga, gb = part["start"] * W * U, (part["start"] + part["count"]) * W * U
+        for got, want in ((g, g0), (d, d0), (o, o0)):
+            assert np.abs(got[a:b] - want[ga:gb]).max() <= 1e-10 * max(1.0, np.abs(want).max()), (name, part)

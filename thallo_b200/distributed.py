@@ -68,7 +68,7 @@ class SlabSolver:
         self.layer = int(np.prod(self.global_dims[:-1]))
         ext = self.part["count"] + self.part["ghost_lo"] + self.part["ghost_hi"]
         self.local_dims = self.global_dims[:-1] + [ext]
-        partition = (self.part["ghost_lo"], self.part["ghost_hi"]) if world > 1 else None
+        partition = (self.part["ghost_lo"], self.part["ghost_hi"], self.part["start"] - self.part["ghost_lo"]) if world > 1 else None
         self.solver = ThalloSolver(self.local_dims, energy, kind, double=double, partition=partition, **kw)
         if world > 1:
             L = lib()

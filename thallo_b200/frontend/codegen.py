@@ -199,7 +199,10 @@ class Emitter:
         if op in cmpops: return "(%s %s %s)" % (a[0], cmpops[op], a[1])
         if op == "sample":
             im = g.image(n.const[0])
-            return "a.template samp<%d>(P, %s, %s)" % (g.ptr_slot[im.name], a[0], a[1])
+            y = a[1]
+            if g.partition is not None and g.slow_origin and len(g.udomain) == 2:
+                y = "(%s - %s)" % (y, g.lit(float(g.slow_origin)))      # absolute row -> row of the rank-local slab
+            return "a.template samp<%d>(P, %s, %s)" % (g.ptr_slot[im.name], a[0], y)
         return "th_%s(%s)" % (op, a[0])
 
 
@@ -214,6 +217,13 @@ class Generator:
         if isinstance(partition, dict):
             self.gpartition = dict((int(k), (int(v[0]), int(v[1]))) for k, v in partition.items())
             partition = None
+        # (ghost_lo, ghost_hi[, origin]): `origin` = global index of the local extent's first layer, added to the
+        # VALUE of the slowest index (x:asvalue() in camera models such as shape_from_shading's) so that
+        # expressions in absolute coordinates see the same numbers on every rank
+        self.slow_origin = 0
+        if partition is not None and len(partition) > 2:
+            self.slow_origin = int(partition[2])
+            partition = tuple(partition[:2])
         self.partition = tuple(int(x) for x in partition) if partition is not None else None
         self.hoist_enabled = bool(hoist)
         self.tile_request = tile
@@ -318,7 +328,8 @@ class Generator:
                 lo[pos], hi[pos] = l, h
             return "a.template inb<%d, %d, %d, %d, %d, %d>()" % (lo[0], hi[0], lo[1], hi[1], lo[2], hi[2])
         if isinstance(k, IndexValue):
-            return "(real)(a.template coord<%d>() + (%d))" % (dom.index(k.dim), k.off)
+            origin = self.slow_origin if (self.partition is not None and self.udomain and k.dim == self.udomain[-1]) else 0
+            return "(real)(a.template coord<%d>() + (%d))" % (dom.index(k.dim), k.off + origin)
         if isinstance(k, Param):
             return "P.sc[%d]" % self.sc_slot[k.name]
         if isinstance(k, _JVal):
@@ -1153,7 +1164,9 @@ class Generator:
         # ComputedArrays: value + gradient channels of one element (createprecomputed, thallo.t:4046-4094)
         hdr.append("#define TH_NCOMPUTED %d" % len(self.computed))
         if self.computed:
-            assert self.partition is None, "computed arrays are not supported by the multi-GPU slab partition yet"
+            # under the slab partition the stored images are evaluated locally on owned AND ghost layers (the unknowns'
+            # ghost layers are kept current); the outermost ghost layer may read past the local extent and hold a
+            # wrong value, which no owned residual reaches (halo = stencil reach of the residuals through the arrays)
             rows = []
             for k, ca in enumerate(self.computed):
                 grads = [g for g, ch in zip(ca.gradients, ca.gchannel) if ch >= 0]

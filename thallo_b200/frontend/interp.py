@@ -99,7 +99,8 @@ class Interp:
                 ok &= (c + lo >= 0) & (c + hi < n)
             return ok
         if isinstance(k, IndexValue):
-            return (self.coord[k.dim] + k.off).astype(self.dt)
+            origin = g.slow_origin if (g.partition is not None and g.udomain and k.dim == g.udomain[-1]) else 0
+            return (self.coord[k.dim] + k.off + origin).astype(self.dt)
         if isinstance(k, Param):
             pd = [p for p in g.L.params if p.name == k.name][0]
             return self.dt(np.asarray(self.params[pd.pidx]).reshape(-1)[0])
@@ -139,7 +140,8 @@ class Interp:
                                  lesseq=np.less_equal, greatereq=np.greater_equal)[op]
                         r = f(a[0], a[1])
                     elif op == "sample":
-                        r = self._sample(n.const[0], a[0], a[1])
+                        yo = self.gen.slow_origin if (self.gen.partition is not None and len(self.gen.udomain) == 2) else 0
+                        r = self._sample(n.const[0], a[0], a[1] - yo)
                     else:
                         r = getattr(np, dict(abs="abs", asin="arcsin", acos="arccos", atan="arctan").get(op, op))(a[0])
                 val[n.id] = r
