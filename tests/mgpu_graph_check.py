@@ -62,6 +62,49 @@ def run(kind, nx, ny, nit, lit, dist, rank, world, torch):
     return ok
 
 
+def run_ba(kind, C_, P_, per_point, nit, lit, dist, rank, world, torch, materialize=True):
+    """bundle_adjustment: points + observations partitioned, cameras replicated (their sums all-reduced)."""
+    from thallo_b200 import workloads as wl
+    from thallo_b200.api import ThalloSolver
+    from thallo_b200.distributed import ReplicatedSolver
+    d = wl.bundle_adjustment_inputs(C_, P_, per_point)
+    O_ = len(d["oToC"])
+    kw = dict(define_kwargs=dict(materialize=materialize))
+    s = ReplicatedSolver([C_, P_, O_], "bundle_adjustment", kind, rank, world, d["oToP"], **kw)
+    cams = torch.from_numpy(np.ascontiguousarray(d["cameras"])).cuda()
+    pts = torch.from_numpy(s.point_rows(d["points"])).cuda()
+    obs = torch.from_numpy(s.observation_rows(d["observations"])).cuda()
+    o2c = torch.from_numpy(s.observation_rows(d["oToC"])).cuda()
+    o2p = torch.from_numpy(s.point_index(d["oToP"])).cuda()
+    s.set_parameters(nIterations=nit, lIterations=lit)
+    costs, lin = trajectory(s, [cams, pts, obs, o2c, o2p])
+    torch.cuda.synchronize()
+    gathered = [None] * world
+    dist.all_gather_object(gathered, (pts.cpu().numpy(), cams.cpu().numpy()))
+    ok = True
+    if rank == 0:
+        allpts = np.concatenate([g[0] for g in gathered])
+        cam_spread = max(float(np.abs(g[1] - gathered[0][1]).max()) for g in gathered)       # replicas must stay bit-identical
+        d1 = wl.bundle_adjustment_inputs(C_, P_, per_point)
+        one = [torch.from_numpy(np.ascontiguousarray(x)).cuda() for x in wl.bundle_adjustment_params(d1)]
+        r = ThalloSolver([C_, P_, O_], "bundle_adjustment", kind, schedule="gather", **kw)
+        r.set_parameters(nIterations=nit, lIterations=lit)
+        c1, l1 = trajectory(r, one)
+        rel = max(abs(a - b) / max(abs(b), 1e-3) for a, b in zip(costs, c1)) if len(costs) == len(c1) else float("inf")
+        dp = float(np.abs(allpts - one[1].cpu().numpy()).max())
+        dc = float(np.abs(gathered[0][1] - one[0].cpu().numpy()).max())
+        # the camera sums are formed in a different order than on one GPU (per-rank partial sums, then NCCL):
+        # float32 rounding differences, amplified like in every truncated-PCG comparison (tests/_parity.py)
+        ok = len(costs) == len(c1) and rel <= 2e-4 and abs(costs[1] - c1[1]) <= 1e-5 * abs(c1[1]) and cam_spread == 0.0
+        print("mgpu bundle_adjustment %s C=%d P=%d O=%d materialize=%s world=%d: max rel cost diff %.3g (first step %.3g), lin %s vs %s, "
+              "max|dpoints| %.3g max|dcameras| %.3g, replica spread %.3g -> %s"
+              % (kind, C_, P_, O_, materialize, world, rel, abs(costs[1] - c1[1]) / abs(c1[1]), lin, l1, dp, dc, cam_spread,
+                 "OK" if ok else "MISMATCH"), flush=True)
+        if not ok:
+            print(costs, c1, flush=True)
+    return ok
+
+
 def bench(n, dist, rank, world, torch):
     """Weak scaling: n x (n * world) mesh, n*n owned vertices per rank."""
     from thallo_b200 import workloads as wl
@@ -105,6 +148,8 @@ def main():
     else:
         for kind, nx, ny, nit, lit in [("gauss_newton", 40, 36, 3, 25), ("levenberg_marquardt", 48, 50, 4, 30)]:
             ok = run(kind, nx, ny, nit, lit, dist, rank, world, torch) and ok
+        ok = run_ba("gauss_newton", 12, 400, 4, 3, 20, dist, rank, world, torch, materialize=False) and ok
+        ok = run_ba("levenberg_marquardt", 12, 400, 4, 3, 20, dist, rank, world, torch, materialize=True) and ok
     flag = [ok]
     dist.broadcast_object_list(flag, src=0)
     dist.destroy_process_group()

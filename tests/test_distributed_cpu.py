@@ -288,3 +288,54 @@ def test_slab_local_operators_equal_the_global_ones(name):
         ga, gb = part["start"] * W * U, (part["start"] + part["count"]) * W * U
         for got, want in ((g, g0), (d, d0), (o, o0)):
             assert np.abs(got[a:b] - want[ga:gb]).max() <= 1e-10 * max(1.0, np.abs(want).max()), (name, part)
+
+
+# ---------------------------------------------------------------- bundle adjustment: points partitioned, cameras replicated
+def test_point_partition_and_replicated_camera_sums():
+    """Every observation belongs to exactly one rank; the ranks' local J^T J p agree with the global product on
+    their own points, and their camera blocks ADD UP to the global camera block (what the all-reduce computes)."""
+    import energies
+    from oracle.npdsl import evaluate
+    from thallo_b200 import workloads as wl
+    from thallo_b200.frontend import codegen, interp
+    Cn, Pn, world = 5, 37, 3
+    d = wl.bundle_adjustment_inputs(Cn, Pn, 3)
+    params = [np.asarray(p, np.float64) if np.asarray(p).dtype == np.float32 else p for p in wl.bundle_adjustment_params(d)]
+    On = len(d["oToC"])
+    define = energies.load("bundle_adjustment")
+    _, F, J = evaluate(define, [Cn, Pn, On], params, np.float64, materialize=False)
+    pvec = np.random.RandomState(2).randn(J.shape[1])
+    want = J.T.tocsr() @ (J @ pvec)
+    parts = D.point_partition(Pn, d["oToP"], world)
+    assert np.array_equal(np.sort(np.concatenate([p["observations"] for p in parts])), np.arange(On))
+    cam = np.zeros(9 * Cn)
+    for r, part in enumerate(parts):
+        obs = part["observations"]
+        assert np.all((d["oToP"][obs] >= part["start"]) & (d["oToP"][obs] < part["start"] + part["count"]))
+        lp = [params[0], params[1][part["start"]:part["start"] + part["count"]], params[2][obs], d["oToC"][obs],
+              (d["oToP"][obs] - part["start"]).astype(np.int32)]
+        dims = [Cn, part["count"], len(obs)]
+        for mat in (False, True):
+            low = codegen.lower(define, dims, "gauss_newton", "bundle_adjustment", True, "gather",
+                                partition=dict(replicated=(0,), owner=(r == 0)), materialize=mat)
+            assert "replicated 0 %d" % (9 * Cn) in codegen.descriptor_text(low.desc)
+            assert ("#define TH_REP_OWNER %d" % int(r == 0)) in low.source
+        ploc = np.concatenate([pvec[:9 * Cn], pvec[9 * Cn + 3 * part["start"]:9 * Cn + 3 * (part["start"] + part["count"])]])
+        out = interp.gather_apply(low.generator, lp, ploc, materialised=True)
+        cam += out[:9 * Cn]
+        pts = want[9 * Cn + 3 * part["start"]:9 * Cn + 3 * (part["start"] + part["count"])]
+        assert np.abs(out[9 * Cn:] - pts).max() <= 1e-10 * np.abs(want).max()
+    assert np.abs(cam - want[:9 * Cn]).max() <= 1e-10 * np.abs(want).max()
+
+
+def test_replicated_plans_compile_for_sm100a():
+    import energies
+    from thallo_b200 import api
+    from thallo_b200.frontend import codegen
+    api.build_library()
+    for owner in (True, False):
+        low = codegen.lower(energies.load("bundle_adjustment"), [6, 40, 150], "levenberg_marquardt", "bundle_adjustment",
+                            schedule="gather", partition=dict(replicated=(0,), owner=owner))
+        ok, log, size = api.compile_only(low.source)
+        assert ok, log[-3000:]
+        assert "th_rep_finish" in open(os.path.join(os.path.dirname(api.LIB_PATH), "..", "csrc", "skeleton", "thallo_kernels.cuh")).read()

@@ -48,6 +48,18 @@ __device__ __forceinline__ bool th_flat_owned(long long f) {
 #endif
 }
 
+// flat index of an unknown scalar -> does this rank count it in the dot products?
+__device__ __forceinline__ bool th_flat_counted(long long f) {
+#if TH_MULTI
+    bool ok = false;
+#pragma unroll
+    for (int k = 0; k < TH_NRANGES; ++k) ok = ok || (th_range_counted(k) && f >= th_range_lo(k) && f < th_range_hi(k));
+    return ok;
+#else
+    return true;
+#endif
+}
+
 // ================================================================== at-output (unknownwise) kernels
 #if TH_AT_OUTPUT
 extern "C" __global__ void __launch_bounds__(TH_BLOCK)
@@ -184,8 +196,8 @@ __device__ __forceinline__ void th_for_owned(long long lo, long long hi, FV&& fv
         const real rn_ = r.c - alpha * ap.c;                                     \
         const real z_ = TH_USEPRE ? pre.c * rn_ : rn_;                           \
         dl.c = dn_; r.c = rn_; zz.c = z_;                                        \
-        acc[0] += (double)(z_ * rn_);                                            \
-        if (TH_LM) acc[1] += (double)((real)0.5 * (dn_ * (rn_ + bb.c)));         \
+        accr[0] += (double)(z_ * rn_);                                           \
+        if (TH_LM) accr[1] += (double)((real)0.5 * (dn_ * (rn_ + bb.c)));        \
     }
 // End of step 2 in the last block: publish the two sums.  Multi-GPU plans publish this rank's
 // partial sums instead; the host all-reduces them over NCCL and th_mg_close finishes the iteration.
@@ -230,7 +242,7 @@ th_pcg_b(const __grid_constant__ Vecs V, ThScalars* S, double* partials, real q_
     const real* __restrict__ vap = V.Ap;
     const real* __restrict__ vpre = V.pre;
     const real* __restrict__ vb = V.b;
-    double acc[2] = {0.0, 0.0};
+    double acc[2] = {0.0, 0.0}, accr[2] = {0.0, 0.0};
     const long long stride = (long long)gridDim.x * blockDim.x;
     const long long gtid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     auto scalar = [&](long long i) {
@@ -239,8 +251,8 @@ th_pcg_b(const __grid_constant__ Vecs V, ThScalars* S, double* partials, real q_
         const real rn = vr[i] - alpha * vap[i];
         const real zv = TH_USEPRE ? vpre[i] * rn : rn;
         vd[i] = dn; vr[i] = rn; vz[i] = zv;
-        acc[0] += (double)(zv * rn);
-        if (TH_LM) acc[1] += (double)((real)0.5 * (dn * (rn + vb[i])));
+        accr[0] += (double)(zv * rn);
+        if (TH_LM) accr[1] += (double)((real)0.5 * (dn * (rn + vb[i])));
     };
 #pragma unroll
     for (int k = 0; k < TH_NRANGES; ++k) {          // owned flat ranges (one range = everything on a single GPU)
@@ -261,6 +273,8 @@ th_pcg_b(const __grid_constant__ Vecs V, ThScalars* S, double* partials, real q_
         }
         for (long long i = lo + gtid; i < (v0 * 4 < hi ? v0 * 4 : hi); i += stride) scalar(i);
         for (long long i = v1 * 4 + gtid; i < hi; i += stride) scalar(i);
+        if (th_range_counted(k)) { acc[0] += accr[0]; acc[1] += accr[1]; }     // a replicated range counts on one rank only
+        accr[0] = accr[1] = 0.0;
     }
     double tot[2];
     if (th_grid_reduce<2>(acc, tot, partials, &S->ticket[2])) {
@@ -298,15 +312,16 @@ th_step2_second(const __grid_constant__ Vecs V, ThScalars* S, double* partials, 
     const real* __restrict__ vpre = V.pre;
     real* __restrict__ vr = V.r;
     real* __restrict__ vz = V.z;
+    double accr[2] = {0.0, 0.0};
     auto lane = [&](real delta, real Ax, real ctc, real b, real pre, real& r, real& z) {
         if (add_ctc) Ax += ctc * delta;
         r = b - Ax;
         z = TH_USEPRE ? pre * r : r;
-        acc[0] += (double)(z * r);
-        acc[1] += (double)((real)0.5 * (delta * (r + b)));
+        accr[0] += (double)(z * r);
+        accr[1] += (double)((real)0.5 * (delta * (r + b)));
     };
 #pragma unroll
-    for (int k = 0; k < TH_NRANGES; ++k)
+    for (int k = 0; k < TH_NRANGES; ++k) {
         th_for_owned(th_range_lo(k), th_range_hi(k),
             [&](long long i) {
                 const real4 dl = ((const real4*)vdl)[i];
@@ -328,6 +343,9 @@ th_step2_second(const __grid_constant__ Vecs V, ThScalars* S, double* partials, 
                 vr[i] = r;
                 vz[i] = z;
             });
+        if (th_range_counted(k)) { acc[0] += accr[0]; acc[1] += accr[1]; }     // a replicated range counts on one rank only
+        accr[0] = accr[1] = 0.0;
+    }
     double tot[2];
     if (th_grid_reduce<2>(acc, tot, partials, &S->ticket[2])) {
         if (threadIdx.x == 0) th_step2_publish(S, tot, q_tolerance, hf, epoch);
@@ -797,7 +815,8 @@ th_init_finish(const __grid_constant__ Params P, const __grid_constant__ Vecs V,
     for (long long f = (long long)blockIdx.x * blockDim.x + threadIdx.x; f < TH_NUNK; f += (long long)gridDim.x * blockDim.x) {
         if (!th_flat_owned(f)) continue;       // ghost entries (graph partition) are the owner's to initialise; p arrives by push
         if (th_excluded(f, P)) { th_zero_scalar(V, f); continue; }
-        acc[0] += (double)th_init_scalar(P, V, f, -V.r[f], V.pre[f], (real)1, first_nonlinear);   // pre := 1 when off, gauss_newton.t:718-722
+        const real rp = th_init_scalar(P, V, f, -V.r[f], V.pre[f], (real)1, first_nonlinear);   // pre := 1 when off, gauss_newton.t:718-722
+        if (th_flat_counted(f)) acc[0] += (double)rp;
     }
     double tot[1];
     if (th_grid_reduce<1>(acc, tot, partials, &S->ticket[0])) {
@@ -835,6 +854,12 @@ __device__ constexpr ThSpace TH_SPACE[TH_NSPACES] = TH_SPACE_TABLE;
 __device__ constexpr ThSlot TH_SLOT[TH_NSPACES][TH_MAXSLOTS] = TH_SLOT_TABLE;
 __device__ constexpr int TH_NNZP[TH_NGROUPS] = TH_GROUP_NNZP;
 
+#if TH_HAS_REP
+__device__ constexpr int TH_SPACE_REP_T[TH_NSPACES] = TH_SPACE_REP;
+#define TH_SPACE_IS_REP(SP) (TH_SPACE_REP_T[SP] != 0)
+#else
+#define TH_SPACE_IS_REP(SP) false
+#endif
 // sum over the LANES adjacent lanes that share one unknown element (LANES a power of two)
 template <int LANES> __device__ __forceinline__ real th_lanes_sum_real(real v) {
 #pragma unroll
@@ -882,6 +907,7 @@ template <int LANES> __device__ __forceinline__ real th_lanes_sum_real(real v) {
                 const int k = TH_SLOT[SP][j].image;                                                                 \
                 const long long off = TH_UIMG[k].offset + t.lin * TH_UIMG[k].channels + TH_SLOT[SP][j].channel;     \
                 if (ex) { out[off] = (real)0; continue; }                                                           \
+                if (TH_SPACE_IS_REP(SP)) { out[off] = acc[j]; continue; }   /* summed over the ranks, then th_rep_finish */ \
                 const real pv = in[off];                                                                            \
                 real val = acc[j];                                                                                  \
                 if (TH_LM) val += V.CtC[off] * pv;                                                                  \
@@ -897,6 +923,37 @@ template <int LANES> __device__ __forceinline__ real th_lanes_sum_real(real v) {
         }                                                                                                           \
     }
 TH_SPACE_LIST(TH_GATHER_KERNEL)
+
+#if TH_HAS_REP
+// Replicated unknowns (the cameras of a point-partitioned bundle adjustment): the gather kernels left this rank's
+// partial sums in Ap / Adelta, NCCL summed them over the ranks; finish like the gather kernel does for
+// partitioned unknowns: + CtC p in LM and, on the one rank that counts them, their part of <p, Ap>.
+extern "C" __global__ void __launch_bounds__(TH_BLOCK)
+th_rep_finish(const __grid_constant__ Params P, const __grid_constant__ Vecs V, ThScalars* S, double* partials, int which) {
+    if (S->done) return;
+    const real* __restrict__ in = which ? V.delta : V.p;
+    real* __restrict__ out = which ? V.Adelta : V.Ap;
+    double acc1[1] = {0.0};
+#pragma unroll
+    for (int k = 0; k < TH_NUM_UIMG; ++k) {
+        if (!TH_REP[k]) continue;
+        const long long lo = TH_UIMG[k].offset, hi = lo + TH_UIMG[k].elements * TH_UIMG[k].channels;
+        for (long long f = lo + (long long)blockIdx.x * blockDim.x + threadIdx.x; f < hi; f += (long long)gridDim.x * blockDim.x) {
+            if (th_excluded(f, P)) { out[f] = (real)0; continue; }
+            const real pv = in[f];
+            real val = out[f];
+            if (TH_LM) val += V.CtC[f] * pv;
+            out[f] = val;
+            if (TH_REP_OWNER) acc1[0] += (double)(pv * val);
+        }
+    }
+    if (which) return;
+    double tot[1];
+    if (th_grid_reduce<1>(acc1, tot, partials, &S->ticket[1])) {
+        if (threadIdx.x == 0) S->aD += tot[0];
+    }
+}
+#endif
 
 // Materialised Jacobian of one residual group (sparse_materialize schedules): the partial
 // derivatives are stored once per nonlinear iteration (precomputeJ, gauss_newton.t:1019-1025; no

@@ -126,6 +126,13 @@ __device__ constexpr ThPart TH_RANGE[TH_NUM_UIMG] = TH_RANGE_TABLE;
 __device__ constexpr long long th_range_lo(int k) { return TH_RANGE[k].lo; }
 __device__ constexpr long long th_range_hi(int k) { return TH_RANGE[k].hi; }
 __device__ __forceinline__ bool th_owned_slow(int) { return true; }
+// replicated unknown images (TH_REP_TABLE): every rank holds and updates them in full (their part of J^T F,
+// diag J^T J and J^T J p is all-reduced), and exactly one rank (TH_REP_OWNER) counts them in the dot products
+#ifdef TH_REP_TABLE
+#define TH_HAS_REP 1
+__device__ constexpr int TH_REP[TH_NUM_UIMG] = TH_REP_TABLE;
+__device__ constexpr bool th_range_counted(int k) { return !TH_REP[k] || TH_REP_OWNER; }
+#endif
 #elif TH_MULTI
 #define TH_NRANGES TH_NUM_UIMG
 __device__ constexpr long long th_range_lo(int k) {
@@ -140,6 +147,11 @@ __device__ __forceinline__ bool th_owned_slow(int c) { return c >= TH_GHOST_LO &
 __device__ constexpr long long th_range_lo(int) { return 0; }
 __device__ constexpr long long th_range_hi(int) { return TH_NUNK; }
 __device__ __forceinline__ bool th_owned_slow(int) { return true; }
+#endif
+
+#ifndef TH_HAS_REP
+#define TH_HAS_REP 0
+__device__ constexpr bool th_range_counted(int) { return true; }
 #endif
 
 #if TH_TILED

@@ -74,6 +74,7 @@ bool parse_descriptor(const std::string& text, PlanDesc& d, std::string& err) {
         else if (key == "ncoef") ls >> d.ncoef;
         else if (key == "computed") { int k; long long n; int g; ls >> k >> n >> g; d.computed.push_back({n, g}); }
         else if (key == "partition") { ls >> d.ghost_lo >> d.ghost_hi; d.multi = true; }
+        else if (key == "replicated") { long long o, n; ls >> o >> n; d.replicated.push_back({o, n}); }
         else if (key == "gpartition") { ls >> d.part_dim >> d.part_extent >> d.ghost_lo >> d.ghost_hi; d.multi = d.gmulti = true; }
         else if (key == "tile") {
             ls >> d.tile[0] >> d.tile[1] >> d.tile[2] >> d.halo[0] >> d.halo[1] >> d.halo[2] >> d.smem_bytes;
@@ -154,6 +155,13 @@ int Plan::connect(const void* handle_lo, long long extent_lo, const void* handle
         peer_extent_[i] = ex[i];
     }
     return 0;
+}
+// sum a segment of a solver vector over all ranks, in place (replicated unknowns: the camera block of bundle adjustment)
+void Plan::allreduce_vec(int vec, long long offset, long long count) {
+    if (!comm_) { fprintf(stderr, "thallo_b200: multi-GPU plan used before ThalloB200_PlanInitComm\n"); exit(1); }
+    void* ptr = (char*)vecs_[vec] + (size_t)offset * real_size_;
+    const int r = nccl().AllReduce(ptr, ptr, (size_t)count, d_.is_double ? /*ncclFloat64*/ 8 : /*ncclFloat32*/ 7, /*ncclSum*/ 0, comm_, stream());
+    if (r != 0) fatal_nccl(r, "ncclAllReduce (vector segment)");
 }
 // graph partition: besides the mapping, the width of each neighbour's ghost block that faces this rank
 int Plan::connect_graph(const void* handle_lo, long long extent_lo, long long width_lo, const void* handle_hi, long long extent_hi,
@@ -561,6 +569,12 @@ void Plan::launch_gather(int which) {
         const long long threads = d_.spaces[s].elements * d_.spaces[s].lanes;
         launch(fn("th_gather_s" + std::to_string(s)), dim3((unsigned)((threads + 255) / 256)), dim3(256), a);
     }
+    if (!d_.replicated.empty()) {      // replicated unknowns: sum the ranks' partial J^T J p, then + CtC p and the dot product
+        long long n = 0;
+        for (auto& r : d_.replicated) { allreduce_vec(which ? V_ADELTA : V_AP, r.first, r.second); n += r.second; }
+        void* a[] = {P, V, &d_scalars_, &d_partials_, &which};
+        launch(fn("th_rep_finish"), dim3((unsigned)std::min<long long>((n + 255) / 256, (long long)sms_ * 8)), dim3(256), a);
+    }
 }
 
 // util.initParameters, util.t:609-643: images / sparse = device pointers, scalars read through host pointers
@@ -841,6 +855,10 @@ int Plan::step(void** params) {
         for (size_t g = 0; g < d_.groups.size(); ++g) {
             void* a[] = {P, V};
             launch_group(fn("th_evaljtf_g" + std::to_string(g)), (int)g, a);
+        }
+        for (auto& r : d_.replicated) {       // replicated unknowns: J^T F and diag(J^T J) summed over the ranks' residuals
+            allreduce_vec(V_R, r.first, r.second);
+            allreduce_vec(V_PRE, r.first, r.second);
         }
         void* a[] = {P, V, &d_scalars_, &d_partials_, &first};
         launch_flat(fn("th_init_finish"), a);

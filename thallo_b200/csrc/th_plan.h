@@ -56,6 +56,7 @@ struct PlanDesc {
     // multi-GPU graph partition ("gpartition" line, gather schedule): dimension of the vertex domain every
     // unknown image lives on, its local extent and the ghost vertices in front of / behind the owned range
     bool gmulti = false;
+    std::vector<std::pair<long long, long long>> replicated;    // flat (offset, count) of the replicated unknown images
     int part_dim = -1;
     long long part_extent = 0;
 };
@@ -111,6 +112,7 @@ public:
     int comm_init(const void* nccl_id, int rank, int world);
     int ipc_handle(void* handle64, long long* slow_extent);
     int connect(const void* handle_lo, long long extent_lo, const void* handle_hi, long long extent_hi);
+    void allreduce_vec(int vec, long long offset, long long count);
     int connect_graph(const void* handle_lo, long long extent_lo, long long width_lo, const void* handle_hi, long long extent_hi,
                       long long width_hi);
     // per-kernel device times (timingLevel >= 2, like util.t:774-790): "name count total_ms\n" lines

@@ -214,7 +214,14 @@ class Generator:
         # or, for graph domains in the gather schedule, {dim index: (lo, hi)}: elements [lo, size - hi) of that
         # dimension are owned by this rank, the others are ghost vertices / foreign edges (distributed.graph_partition)
         self.gpartition = None
+        # Special keys: "replicated" = dimensions whose unknowns every rank holds in full (the cameras of bundle
+        # adjustment: every rank sees observations of every camera, so their part of J^T J p is all-reduced);
+        # "owner" = whether this rank counts the replicated unknowns in the dot products.
+        self.replicated_dims, self.rep_owner = (), True
         if isinstance(partition, dict):
+            partition = dict(partition)
+            self.replicated_dims = tuple(int(x) for x in partition.pop("replicated", ()))
+            self.rep_owner = bool(partition.pop("owner", True))
             self.gpartition = dict((int(k), (int(v[0]), int(v[1]))) for k, v in partition.items())
             partition = None
         # (ghost_lo, ghost_hi[, origin]): `origin` = global index of the local extent's first layer, added to the
@@ -1071,17 +1078,25 @@ class Generator:
         if self.gpartition is not None:
             assert self.schedule == "gather", "a graph partition needs the gather schedule"
             assert not self.computed, "computed arrays are not supported by the multi-GPU graph partition yet"
-            vdims = set(tuple(d.idx for d in im.dims) for im in self.unknowns)
-            assert len(vdims) == 1 and len(next(iter(vdims))) == 1, \
-                "a graph partition needs every unknown to live on one 1-D vertex domain"
-            vd = next(iter(vdims))[0]
-            glo, ghi = self.gpartition.get(vd, (0, 0))
+            assert all(len(im.dims) == 1 for im in self.unknowns), "a graph partition needs 1-D unknown domains"
+            ghosted = sorted(set(im.dims[0].idx for im in self.unknowns if any(self.gpartition.get(im.dims[0].idx, (0, 0)))))
+            assert len(ghosted) <= 1, "at most one unknown domain can carry ghost elements"
+            assert not (ghosted and ghosted[0] in self.replicated_dims)
             hdr.append("#define TH_MULTI 1")
             hdr.append("#define TH_PART_TABLE {%s}" % ", ".join("{%dLL, %dLL}" % self.gpartition.get(d.idx, (0, 0)) for d in L.dims))
-            hdr.append("#define TH_RANGE_TABLE {%s}" % ", ".join(
-                "{%dLL, %dLL}" % (self.uoff[im.name] + glo * im.channels, self.uoff[im.name] + (im.elements - ghi) * im.channels)
-                for im in self.unknowns))
-            self.gpart_line = (vd, L.dims[vd].size, glo, ghi)
+            rng = []
+            for im in self.unknowns:
+                glo, ghi = self.gpartition.get(im.dims[0].idx, (0, 0))
+                rng.append("{%dLL, %dLL}" % (self.uoff[im.name] + glo * im.channels, self.uoff[im.name] + (im.elements - ghi) * im.channels))
+            hdr.append("#define TH_RANGE_TABLE {%s}" % ", ".join(rng))
+            vd = ghosted[0] if ghosted else -1
+            self.gpart_line = (vd, L.dims[vd].size if ghosted else 0) + (self.gpartition[vd] if ghosted else (0, 0))
+            self.rep_images = [k for k, im in enumerate(self.unknowns) if im.dims[0].idx in self.replicated_dims]
+            if self.rep_images:
+                hdr.append("#define TH_REP_TABLE {%s}" % ", ".join("1" if k in self.rep_images else "0" for k in range(len(self.unknowns))))
+                hdr.append("#define TH_REP_OWNER %d" % int(self.rep_owner))
+                hdr.append("#define TH_SPACE_REP {%s}" % ", ".join(
+                    "1" if sp["dims"][0] in self.replicated_dims else "0" for sp in self.spaces))
         if self.partition is not None:
             assert self.tiled, "multi-GPU partitioning needs the tiled at-output schedule (2-D / 3-D image domain)"
             assert all(tuple(g["domain"]) == tuple(self.udomain) for g in self.groups), \
@@ -1224,6 +1239,7 @@ class Generator:
         )
         if self.gpartition is not None:
             d["gpartition"] = self.gpart_line
+            d["replicated"] = [(self.uoff[self.unknowns[k].name], self.unknowns[k].cardinality) for k in self.rep_images]
         d["computed"] = [dict(elements=ca.elements, ngrad=sum(1 for ch in ca.gchannel if ch >= 0)) for ca in self.computed]
         if self.schedule == "gather":
             d["gather"] = dict(
@@ -1279,6 +1295,8 @@ def descriptor_text(d):
         ln.append("computed %d %d %d" % (k, c["elements"], c["ngrad"]))
     if d.get("gpartition") is not None:
         ln.append("gpartition %d %d %d %d" % tuple(d["gpartition"]))
+        for off, n in d.get("replicated", []):
+            ln.append("replicated %d %d" % (off, n))
     if d["schedule"] == "gather":
         ga = d["gather"]
         for sp in ga["spaces"]:
