@@ -87,6 +87,12 @@ def _check_gather(name, dims, params, kw=None):
     for mat in (False, True):       # matrix-free endpoint functions, then the stored-value (materialised J) functions
         out = interp.gather_apply(gen, params, p, materialised=mat)
         assert np.abs(out - o0).max() <= 1e-10 * max(1.0, np.abs(o0).max()), mat
+    # gathered PCGInit1: -J^T F and diag(J^T J)
+    r, dg = interp.gather_jtf(gen, params)
+    g0 = -(J.T.tocsr() @ F)
+    d0 = np.asarray(J.multiply(J).sum(axis=0)).reshape(-1)
+    assert np.abs(r - g0).max() <= 1e-10 * max(1.0, np.abs(g0).max())
+    assert np.abs(dg - d0).max() <= 1e-10 * max(1.0, d0.max())
     return low
 
 

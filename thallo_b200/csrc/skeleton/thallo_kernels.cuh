@@ -924,6 +924,38 @@ template <int LANES> __device__ __forceinline__ real th_lanes_sum_real(real v) {
     }
 TH_SPACE_LIST(TH_GATHER_KERNEL)
 
+// PCGInit1 of the gather schedule: r = -J^T F and the raw diagonal of J^T J, gathered per unknown element over the
+// same adjacency lists (replaces the clears of r and the preconditioner + the scattering residualwise PCGInit1,
+// gauss_newton.t:998-1004; no atomics, deterministic).  th_init_finish then proceeds as after the scatter form.
+#define TH_GATHERJTF_KERNEL(SP)                                                                                     \
+    extern "C" __global__ void __launch_bounds__(TH_BLOCK)                                                          \
+    th_gatherjtf_s##SP(const __grid_constant__ Params P, const __grid_constant__ Vecs V,                            \
+                       const __grid_constant__ ThGather G) {                                                        \
+        constexpr int LANES = TH_SPACE[SP].lanes;                                                                   \
+        constexpr int NS = TH_SPACE[SP].nslots;                                                                     \
+        const long long gt = (long long)blockIdx.x * blockDim.x + threadIdx.x;                                      \
+        const int lane = (int)(threadIdx.x % LANES);                                                                \
+        ThIdx<th::dom_s##SP> t;                                                                                     \
+        const bool valid = t.from_linear(gt / LANES) && th_owned(t);                                                \
+        real accg[NS], accd[NS];                                                                                    \
+        _Pragma("unroll") for (int j = 0; j < NS; ++j) { accg[j] = (real)0; accd[j] = (real)0; }                    \
+        if (valid) th::gatherjtf_s##SP<LANES>(t, lane, P, G, accg, accd);                                           \
+        if (LANES > 1) {                                                                                            \
+            _Pragma("unroll") for (int j = 0; j < NS; ++j) {                                                        \
+                accg[j] = th_lanes_sum_real<LANES>(accg[j]); accd[j] = th_lanes_sum_real<LANES>(accd[j]);           \
+            }                                                                                                       \
+        }                                                                                                           \
+        if (valid && lane == 0) {                                                                                   \
+            _Pragma("unroll") for (int j = 0; j < NS; ++j) {                                                        \
+                const int k = TH_SLOT[SP][j].image;                                                                 \
+                const long long off = TH_UIMG[k].offset + t.lin * TH_UIMG[k].channels + TH_SLOT[SP][j].channel;     \
+                V.r[off] = accg[j];                                                                                 \
+                V.pre[off] = accd[j];                                                                               \
+            }                                                                                                       \
+        }                                                                                                           \
+    }
+TH_SPACE_LIST(TH_GATHERJTF_KERNEL)
+
 #if TH_HAS_REP
 // Replicated unknowns (the cameras of a point-partitioned bundle adjustment): the gather kernels left this rank's
 // partial sums in Ap / Adelta, NCCL summed them over the ranks; finish like the gather kernel does for

@@ -300,6 +300,7 @@ Plan::Plan(const StateOptions* opts, const PlanDesc& desc, const std::string& so
     for (auto& sp : d_.spaces) maxblocks = std::max(maxblocks, (sp.elements * sp.lanes + 255) / 256);
     CD(cudaMalloc((void**)&d_partials_, sizeof(double) * 2 * (size_t)maxblocks));
     if (d_.gather) {
+        if (const char* e = getenv("THALLO_B200_SCATTER_JTF")) gather_jtf_ = atoi(e) == 0;
         adj_.resize(d_.seps.size());
         jvals_.assign(d_.groups.size(), nullptr);
         jp_.assign(d_.groups.size(), nullptr);
@@ -850,11 +851,19 @@ int Plan::step(void** params) {
             allreduce(offsetof(HScalars, rz), 1);
         }
     } else {
-        clear(vecs_[V_R]);
-        clear(vecs_[V_PRE]);
-        for (size_t g = 0; g < d_.groups.size(); ++g) {
-            void* a[] = {P, V};
-            launch_group(fn("th_evaljtf_g" + std::to_string(g)), (int)g, a);
+        if (d_.gather && gather_jtf_) {       // gathered over the adjacency lists: no clears, no atomics
+            for (size_t s = 0; s < d_.spaces.size(); ++s) {
+                void* a[] = {P, V, gather_buf_.data()};
+                const long long threads = d_.spaces[s].elements * d_.spaces[s].lanes;
+                launch(fn("th_gatherjtf_s" + std::to_string(s)), dim3((unsigned)((threads + 255) / 256)), dim3(256), a);
+            }
+        } else {
+            clear(vecs_[V_R]);
+            clear(vecs_[V_PRE]);
+            for (size_t g = 0; g < d_.groups.size(); ++g) {
+                void* a[] = {P, V};
+                launch_group(fn("th_evaljtf_g" + std::to_string(g)), (int)g, a);
+            }
         }
         for (auto& r : d_.replicated) {       // replicated unknowns: J^T F and diag(J^T J) summed over the ranks' residuals
             allreduce_vec(V_R, r.first, r.second);

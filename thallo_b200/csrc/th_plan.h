@@ -175,6 +175,7 @@ private:
     struct Adjacency { const void* src = nullptr; unsigned long long checksum = 0; bool valid = false; int* ptr = nullptr; int* perm = nullptr; };
     std::vector<Adjacency> adj_;
     std::vector<void*> jvals_, jp_, scoef_;
+    bool gather_jtf_ = true;          // PCGInit1 gathered over the adjacency lists (THALLO_B200_SCATTER_JTF=1: the atomic scatter form)
     std::vector<void*> computed_;  // value image, gradient image per ComputedArray (2 entries each)
     void run_precompute();         // gpu.precompute, gauss_newton.t:979-986
     std::vector<char> gather_buf_;          // host image of the device struct ThGather

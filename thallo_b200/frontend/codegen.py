@@ -289,6 +289,7 @@ class Generator:
         self.tile_pad = os.environ.get("THALLO_B200_TILE_PAD", "1") != "0"      # tuning switch
         gl = os.environ.get("THALLO_B200_GATHER_LANES")                          # tuning switch: lanes per unknown element (1..16)
         self.gather_lanes = int(gl) if gl else None
+        self.gather_unroll = int(os.environ.get("THALLO_B200_GATHER_UNROLL", "1"))   # tuning switch: unroll of the adjacency walk
         self.coef_exprs = []          # hoisted PCG-invariant per-element expressions (channels of the __coef image)
         self._coef_index = {}
 
@@ -803,6 +804,16 @@ class Generator:
             if self.hoist_enabled and not g["materialize"]:
                 acc = dict((j, self._hoist_gather(x, hmemo, pmemo)) for j, x in acc.items())
             ep["roots"] = acc
+            # gathered PCGInit1: -J^T F and diag(J^T J) of this endpoint's unknowns
+            gacc, dacc = {}, {}
+            for (ti, u, p) in ep["parts"]:
+                j = sp["slots"][(u.key.image, u.key.channel)]
+                gacc[j] = gacc.get(j, zero) + (-1.0) * p * g["terms"][ti].exp
+                dacc[j] = dacc.get(j, zero) + p * p
+            if self.hoist_enabled:
+                gacc = dict((j, self._hoist_gather(x, hmemo, pmemo)) for j, x in gacc.items())
+                dacc = dict((j, self._hoist_gather(x, hmemo, pmemo)) for j, x in dacc.items())
+            ep["jtf_roots"] = (gacc, dacc)
             if g["storejp"]:        # Jt[Jp]: this endpoint's partials times the stored J p of the residual element
                 tacc = {}
                 for (ti, u, p) in ep["parts"]:
@@ -879,6 +890,13 @@ class Generator:
             src.append(self._fn(
                 "template <class A> __device__ __forceinline__ void jtj_ep%d(const A& a, const Params& P, real* __restrict__ acc)" % ep["id"],
                 [acc[j] for j in js], lambda r, js=js: ["acc[%d] += %s;" % (j, x) for j, x in zip(js, r)], dom))
+            gacc, dacc = ep["jtf_roots"]
+            gjs = sorted(gacc)
+            src.append(self._fn(
+                "template <class A> __device__ __forceinline__ void jtf_ep%d(const A& a, const Params& P, real* __restrict__ accg, real* __restrict__ accd)" % ep["id"],
+                [gacc[j] for j in gjs] + [dacc[j] for j in gjs],
+                lambda r, gjs=gjs: ["accg[%d] += %s;" % (j, x) for j, x in zip(gjs, r[:len(gjs)])] +
+                                   ["accd[%d] += %s;" % (j, x) for j, x in zip(gjs, r[len(gjs):])], dom))
             if g["storejp"]:          # applyJt (thallo.t:3808-3841), gathered instead of scattered
                 tacc = ep["jtp_roots"]
                 tjs = sorted(tacc)
@@ -917,7 +935,35 @@ class Generator:
             else:
                 lanes = 1
             sp["lanes"] = lanes
-            body = []
+            body, jbody = [], []
+            for ep in sp["endpoints"]:      # the same walk for PCGInit1 (J^T F, diag J^T J): always matrix-free
+                gi = ep["group"]
+                call = "jtf_ep%d(a, P, accg, accd);" % ep["id"]
+                if ep["kind"] == "sparse":
+                    sid = ep["sid"]
+                    jbody.append("{")
+                    jbody.append("    const int lo = __ldg(G.ptr[%d] + t.lin), hi = __ldg(G.ptr[%d] + t.lin + 1);" % (sid, sid))
+                    jbody.append("    const int* __restrict__ perm = G.perm[%d];" % sid)
+                    jbody.append("    for (int i = lo + lane; i < hi; i += LANES) {")
+                    jbody.append("        const long long e = perm ? (long long)__ldg(perm + i) : (long long)i;")
+                    jbody.append("        ThIdx<dom_g%d> idx; idx.from_linear(e);" % gi)
+                    jbody.append("        GAcc<dom_g%d, TH_OWN_ENDPOINT ? %d : -1> a(idx, nullptr, t.lin);" % (gi, self.ptr_slot[ep["sparse"]]))
+                    jbody.append("        " + call)
+                    jbody.append("    }")
+                    jbody.append("}")
+                else:
+                    o = ep["off"]
+                    jbody.append("if (lane == 0) {")
+                    jbody.append("    const int x = t.c[0] - (%d), y = t.c[1] - (%d), z = t.c[2] - (%d);" % (o[0], o[1], o[2]))
+                    jbody.append("    ThIdx<dom_g%d> idx;" % gi)
+                    jbody.append("    if (x >= 0 && y >= 0 && z >= 0 && idx.from_coords(x, y, z)) {")
+                    jbody.append("        GAcc<dom_g%d> a(idx, nullptr);" % gi)
+                    jbody.append("        " + call)
+                    jbody.append("    }")
+                    jbody.append("}")
+            src.append("template <int LANES> __device__ __forceinline__ void gatherjtf_s%d(const ThIdx<dom_s%d>& t, int lane, "
+                       "const Params& P, const ThGather& G, real* __restrict__ accg, real* __restrict__ accd) {\n    %s\n}\n"
+                       % (si, si, "\n    ".join(jbody)))
             for ep in sp["endpoints"]:
                 gi = ep["group"]
                 g = self.groups[gi]
@@ -933,6 +979,8 @@ class Generator:
                         body.append("    if (WHICH == 0) {")      # A*delta of the LM reset skips groups without an applyJTJ (gauss_newton.t:1058-1065)
                     body.append("    const int lo = __ldg(G.ptr[%d] + t.lin), hi = __ldg(G.ptr[%d] + t.lin + 1);" % (sid, sid))
                     body.append("    const int* __restrict__ perm = G.perm[%d];" % sid)
+                    if self.gather_unroll > 1:      # lets the compiler overlap the dependent index -> neighbour loads of consecutive edges
+                        body.append("    #pragma unroll %d" % self.gather_unroll)
                     body.append("    for (int i = lo + lane; i < hi; i += LANES) {")
                     body.append("        const long long e = perm ? (long long)__ldg(perm + i) : (long long)i;")
                     if mat:

@@ -237,3 +237,42 @@ def gather_apply(gen, params, vec, dtype=np.float64, materialised=False):
             base, C, ch = slot_to[j]
             np.add.at(out, base + tgt * C + ch, np.asarray(v, dtype).reshape(-1))
     return out
+
+
+def gather_jtf(gen, params, dtype=np.float64):
+    """Evaluate the gather schedule's PCGInit1 endpoint functions (jtf_ep<k>) summed per unknown element the way
+    th_gatherjtf_s<i> does.  Returns (r, d) = (-J^T F, diag J^T J) as flat vectors in the solver's unknown layout."""
+    r = np.zeros(gen.nunk, dtype)
+    dg = np.zeros(gen.nunk, dtype)
+    Interp.shared = {}
+    for ep in gen.endpoints:
+        g = gen.groups[ep["group"]]
+        sp = gen.spaces[ep["space"]]
+        it = Interp(gen, params, g["domain"], None, dtype)
+        gacc, dacc = ep["jtf_roots"]
+        js = sorted(gacc)
+        vals = it.eval([gacc[j] for j in js] + [dacc[j] for j in js])
+        if ep["kind"] == "sparse":
+            tgt = it._sparse(ep["sparse"])
+            ok = None
+        else:
+            ok = np.ones(it.shape, bool)
+            lin = np.zeros(it.shape, np.int64)
+            stride = 1
+            for i, d in enumerate(g["domain"]):
+                c = it.coord[d] + ep["off"][i]
+                n = gen.L.dims[d].size
+                ok &= (c >= 0) & (c < n)
+                lin += np.clip(c, 0, n - 1) * stride
+                stride *= n
+            tgt = lin.reshape(-1)
+            vals = [np.where(ok, v, 0.0) for v in vals]
+        slot_to = {}
+        for im in sp["images"]:
+            for ch in range(im.channels):
+                slot_to[sp["slots"][(im.name, ch)]] = (gen.uoff[im.name], im.channels, ch)
+        for n_, j in enumerate(js):
+            base, C, ch = slot_to[j]
+            np.add.at(r, base + tgt * C + ch, np.asarray(vals[n_], dtype).reshape(-1))
+            np.add.at(dg, base + tgt * C + ch, np.asarray(vals[len(js) + n_], dtype).reshape(-1))
+    return r, dg
