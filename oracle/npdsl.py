@@ -227,6 +227,15 @@ class Vec:
     def __call__(self, i):
         return self.c[i]
 
+    def get(self, *idx):
+        return Vec([c.get(*idx) for c in self.c])
+
+    def dot(self, o):
+        r = self.c[0] * o.c[0]
+        for a, b in zip(self.c[1:], o.c[1:]):
+            r = r + a * b
+        return r
+
     def slice(self, a, b):
         return Vec(self.c[a:b])
 
@@ -397,6 +406,9 @@ class _Residuals:
         self.groups = groups
         for g in groups:
             setattr(self, g.name, g)
+
+    def merge(self, *groups):            # scheduling hint only
+        return groups[0] if groups else None
 
 
 class NumpyL:
@@ -646,8 +658,16 @@ class NumpyL:
         if rows:
             J = sp.csr_matrix((np.concatenate(vals), (np.concatenate(rows), np.concatenate(cols))),
                               shape=(row0, nunk), dtype=self.dtype)
+            # squares of the partials PER UNKNOWN ACCESS, which is what the reference's PCGInit1 accumulates into the
+            # preconditioner (createjtfResidualwise, thallo.t:3897-3901: one `partial*partial` scatter per access).  It
+            # differs from diag(J^T J) only where two accesses of one residual hit the same unknown (self loops,
+            # coincident index arrays): there J holds the sum of the partials and its square is not the sum of squares.
+            v2 = np.concatenate(vals)
+            self.diag_sq = np.asarray(sp.csr_matrix((v2 * v2, (np.concatenate(rows), np.concatenate(cols))),
+                                                    shape=(row0, nunk), dtype=self.dtype).sum(axis=0)).reshape(-1)
         else:
             J = sp.csr_matrix((row0, nunk), dtype=self.dtype)
+            self.diag_sq = np.zeros(nunk, self.dtype)
         return F, J, ranges
 
 

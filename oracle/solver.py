@@ -121,7 +121,7 @@ class OracleSolver:
         Jk = J.multiply(keep[None, :]).tocsr().astype(dt)      # excluded unknowns: columns drop out
         JT = Jk.T.tocsr()
         g = (JT @ F).astype(dt)
-        dtrue = np.asarray(Jk.multiply(Jk).sum(axis=0)).reshape(-1).astype(dt)
+        dtrue = (L.diag_sq * keep).astype(dt)            # sum of squared partials per unknown access (thallo.t:3897-3901)
         r = (-g).astype(dt)
         if self.mode == "at_output":
             d = dtrue if usepre else np.ones_like(dtrue)

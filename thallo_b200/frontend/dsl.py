@@ -77,6 +77,9 @@ class Vector:
     def __truediv__(self, o): return self._bin(o, lambda x, y: x / y)
     def __neg__(self): return Vector([-x for x in self.c])
 
+    def get(self, *idx):                 # ExpVector:get: every component stored / fetched on its own (ad.t ExpVector)
+        return Vector([c.get(*idx) for c in self.c])
+
     def dot(self, o):
         r = self.c[0] * o.c[0]
         for a, b in zip(self.c[1:], o.c[1:]):
@@ -221,6 +224,11 @@ class Residuals:
         self.groups = groups
         for g in groups:
             setattr(self, g.name, g)
+
+    def merge(self, *groups):
+        """`r:merge(a, b)` asks the reference to evaluate two residual groups in one kernel (thallo.t:5173); it does
+        not change the energy.  The schedules here fuse per unknown element already, so this is accepted and ignored."""
+        return groups[0] if groups else None
 
 
 class _NS:

@@ -582,6 +582,10 @@ class Interpreter:
             f = self.eval(e[1], sc)
             args = self.eval_list(e[2], sc)
             line = e[3]
+            if f is None:
+                self.line = line
+                what = ("global '%s'" % e[1][1]) if e[1][0] == "name" else ("field '%s'" % e[1][2][1]) if e[1][0] == "index" and e[1][2][0] == "const" else "expression"
+                self.error("attempt to call a nil value (%s)" % what)
             try:
                 return self.call(f, args)
             except (LuaError, _Return, _Break):
