@@ -1176,3 +1176,38 @@ TH_COMPUTED_LIST(TH_COMPUTED_KERNEL)
         }                                                                                                           \
     }
 TH_GROUP_LIST(TH_GROUP_KERNELS)
+
+#if TH_AT_OUTPUT
+// At-output plans: every residual group lives on the unknown domain, so the cost and the model cost of ALL groups
+// are formed in one pass (the unknowns, delta and the auxiliary images are read once instead of once per group;
+// image_warping: 5 + 5 launches per nonlinear iteration -> 1 + 1).  Per element the groups' values are the same
+// numbers as in th_cost_g<i> / th_modelcost_g<i>, added up in double.
+#define TH_COST_TERM(G) + (double)th::cost_g##G(a, P)
+#define TH_MODELCOST_TERM(G) + (double)th::modelcost_g##G(a, P)
+extern "C" __global__ void __launch_bounds__(TH_BLOCK)
+th_cost_uw(const __grid_constant__ Params P, ThScalars* S, double* partials) {
+    ThIdx<th::dom_uw> idx;
+    double acc[1] = {0.0};
+    if (th_uw_index(idx) && th_owned(idx)) {
+        GAcc<th::dom_uw> a(idx, nullptr);
+        acc[0] = 0.0 TH_GROUP_LIST(TH_COST_TERM);
+    }
+    double tot[1];
+    if (th_grid_reduce<1>(acc, tot, partials, &S->ticket[4])) {
+        if (threadIdx.x == 0 && threadIdx.y == 0 && threadIdx.z == 0) S->cost = tot[0];
+    }
+}
+extern "C" __global__ void __launch_bounds__(TH_BLOCK)
+th_modelcost_uw(const __grid_constant__ Params P, const __grid_constant__ Vecs V, ThScalars* S, double* partials) {
+    ThIdx<th::dom_uw> idx;
+    double acc[1] = {0.0};
+    if (th_uw_index(idx) && th_owned(idx)) {
+        GAcc<th::dom_uw> a(idx, V.delta);
+        acc[0] = 0.0 TH_GROUP_LIST(TH_MODELCOST_TERM);
+    }
+    double tot[1];
+    if (th_grid_reduce<1>(acc, tot, partials, &S->ticket[4])) {
+        if (threadIdx.x == 0 && threadIdx.y == 0 && threadIdx.z == 0) S->modelcost = tot[0];
+    }
+}
+#endif

@@ -645,11 +645,15 @@ void Plan::run_precompute() {
 // computeCost, gauss_newton.t:1128-1136
 double Plan::compute_cost() {
     void* P = params_buf_.data();
-    for (size_t g = 0; g < d_.groups.size(); ++g) {
-        int first = g == 0;
-        void* args[] = {P, &d_scalars_, &d_partials_, &first};
-        launch_group(fn("th_cost_g" + std::to_string(g)), (int)g, args);
-    }
+    if (d_.at_output) {            // every group lives on the unknown domain: one pass for all of them
+        void* args[] = {P, &d_scalars_, &d_partials_};
+        launch_uw(fn("th_cost_uw"), args);
+    } else
+        for (size_t g = 0; g < d_.groups.size(); ++g) {
+            int first = g == 0;
+            void* args[] = {P, &d_scalars_, &d_partials_, &first};
+            launch_group(fn("th_cost_g" + std::to_string(g)), (int)g, args);
+        }
     if (d_.multi) allreduce(offsetof(HScalars, cost), 1);
     read_scalars();
     return round_real(h_scalars_->cost);
@@ -919,11 +923,15 @@ int Plan::step(void** params) {
         allreduce(offsetof(HScalars, spare), 1);
     }
     if (d_.lm) {   // computeModelCostChange + savePreviousUnknowns, gauss_newton.t:1694-1697
-        for (size_t g = 0; g < d_.groups.size(); ++g) {
-            int f = g == 0;
-            void* a[] = {P, V, &d_scalars_, &d_partials_, &f};
-            launch_group(fn("th_modelcost_g" + std::to_string(g)), (int)g, a);
-        }
+        if (d_.at_output) {
+            void* a[] = {P, V, &d_scalars_, &d_partials_};
+            launch_uw(fn("th_modelcost_uw"), a);
+        } else
+            for (size_t g = 0; g < d_.groups.size(); ++g) {
+                int f = g == 0;
+                void* a[] = {P, V, &d_scalars_, &d_partials_, &f};
+                launch_group(fn("th_modelcost_g" + std::to_string(g)), (int)g, a);
+            }
         if (d_.multi) allreduce(offsetof(HScalars, modelcost), 1);
         void* a[] = {P, &vecs_[V_PREVX], &zero};
         launch_flat(fn("th_copy_x"), a);
