@@ -429,6 +429,13 @@ class NumpyL:
         self.dims = [Dim(n, i, int(self.dim_sizes[i]), self) for i, n in enumerate(names)]
         return self.dims if len(names) > 1 else self.dims[0]
 
+    def Dim(self, name, idx):            # thallo.Dim(name, idx): one dimension at a time (older energy files)
+        if not hasattr(self, "dims"):
+            self.dims = []
+        assert idx == len(self.dims), "Dim() indices must be declared in order"
+        self.dims.append(Dim(name, idx, int(self.dim_sizes[idx]), self))
+        return self.dims[-1]
+
     def Unknown(self, t, dims, pidx):
         return ("Unknown", t, dims, pidx)
 

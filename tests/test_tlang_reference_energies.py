@@ -41,6 +41,7 @@ def random_params(define, dims, seed=0):
 CASES = [
     ("examples/cotangent_mesh_smoothing/cotangent_mesh_smoothing.t", [30, 70], "gather"),
     ("examples/robust_nonrigid_alignment/robust_nonrigid_alignment.t", [30, 70], "gather"),
+    ("examples/embedded_mesh_deformation/embedded_mesh_deformation.t", [30, 70], "gather"),
     ("examples/poisson_image_editing/poisson_image_editing.t", [14, 11], "at_output"),
     ("tests/minimal_exclude/minimal_exclude.t", [14, 11], "at_output"),
     ("tests/minimal_materialize/minimal_materialize.t", [14, 11], "at_output"),

@@ -264,6 +264,12 @@ class SymbolicL:
         self.dims = [Dim(n, i, self.dim_sizes[i]) for i, n in enumerate(names)]
         return self.dims if len(names) > 1 else self.dims[0]
 
+    def Dim(self, name, idx):            # thallo.Dim(name, idx): one dimension at a time (older energy files)
+        assert idx == len(self.dims), "Dim() indices must be declared in order"
+        assert idx < len(self.dim_sizes), "energy needs more dimensions than were given"
+        self.dims.append(Dim(name, idx, self.dim_sizes[idx]))
+        return self.dims[-1]
+
     def Unknown(self, t, dims, pidx): return ("Unknown", t, dims, pidx)
     def Array(self, t, dims, pidx): return ("Array", t, dims, pidx)
     def Sparse(self, frm, to, pidx): return ("Sparse", frm, to, pidx)

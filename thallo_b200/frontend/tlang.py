@@ -1036,6 +1036,7 @@ def _dsl_globals(L, G):
         return lambda x: mf(x) if _isnum(x) else f(x)
 
     env = {
+        "Dim": lambda name, idx: L.Dim(name, int(idx)),
         "Dims": Dims, "Inputs": Inputs, "Residuals": Residuals, "Stencil": Stencil,
         "Unknown": decl("Unknown"), "Array": decl("Array"), "Image": decl("Array"), "Sparse": decl("Sparse"),
         "Param": decl("Param"),
@@ -1061,6 +1062,8 @@ def _dsl_globals(L, G):
         t = getattr(L, attr, None)
         if t is not None:
             env["float" + n] = env["thallo_float" + n] = env["double" + n] = t
+    if getattr(L, "float9", None) is not None:
+        env["thallo_mat3f"] = env["mat3f"] = L.float9               # 3x3 matrix unknowns are nine packed scalars
     for n in ("uint8", "int"):
         if hasattr(L, n):
             env[n] = getattr(L, n)
