@@ -770,7 +770,7 @@ void Plan::linear_iteration(int l) {
     } else {
         clear(vecs_[V_AP]);
         for (size_t g = 0; g < d_.groups.size(); ++g) {
-            if (d_.groups[g].materialize) continue;   // TODO(next): CSR path for materialized groups
+            if (d_.groups[g].materialize) continue;   // (the front end lowers materialised J / J p groups to the gather schedule only)
             void* a[] = {P, V, &d_scalars_, &zero};
             launch_group(fn("th_applyjtj_g" + std::to_string(g)), (int)g, a);
         }
