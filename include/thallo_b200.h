@@ -42,6 +42,15 @@ unsigned long long ThalloB200_PlanTotalLinearIterations(Thallo_State* state, Tha
  * (count reals of the plan's precision).  Test hook. Returns number of reals copied. */
 long long ThalloB200_PlanReadVector(Thallo_State* state, Thallo_Plan* plan, const char* name, void* host_dst, long long count);
 
+/* Materialise the Jacobian of residual group `group` at the current unknowns (after Thallo_ProblemInit), in the
+ * reference's CSR order (precomputeJ / generateDumpJ, gauss_newton.t:325-487,1019-1025): element-major, within an
+ * element row by row, row k holding the descriptor's row_nnz[k] entries; host_vals receives reals of the plan's
+ * precision, host_cols the flat index of the unknown scalar each partial derivative belongs to (imageOffset +
+ * channels*idx + channel) or -1 where the access falls outside the domain.  Returns the number of entries
+ * (count * nnz per element) or -1.  Test / export hook: the solver itself never forms this copy. */
+long long ThalloB200_PlanExportJacobian(Thallo_State* state, Thallo_Plan* plan, int group, void* host_vals,
+                                        long long* host_cols, long long capacity);
+
 /* Per-kernel device times accumulated since plan creation when the state was created with
  * timingLevel >= 2 (the reference wraps every launch in an event pair at that level,
  * util.t:774-790).  Writes "kernel_name launches total_ms\n" lines; returns bytes written. */

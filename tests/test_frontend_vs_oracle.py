@@ -170,3 +170,29 @@ def test_graph_laplacian_jtjp_schedule_matches_oracle():
     X, A, v0, v1 = wl.minimal_graph_inputs(48)
     low = _check_gather("graph_laplacian", [48, 47], [X.astype(np.float64) * 0.9, A.astype(np.float64), v0, v1], dict(jp=True))
     assert [g["materialize"] for g in low.desc["groups"]] == [0, 2]
+
+
+# ---- Jacobian export (ThalloB200_PlanExportJacobian): layout + assembly against the oracle's J
+@pytest.mark.parametrize("case", ["image_warping", "arap_mesh", "bundle_adjustment"])
+def test_exported_jacobian_layout_assembles_to_the_oracle_jacobian(case):
+    from thallo_b200 import api
+    if case == "image_warping":
+        W, H = 20, 14
+        d = wl.image_warping_inputs(W, H)
+        rng = np.random.RandomState(1)
+        d["Offset"] = d["Offset"] + rng.randn(*d["Offset"].shape).astype(np.float32)
+        d["Angle"] = d["Angle"] + 0.3 * rng.randn(*d["Angle"].shape).astype(np.float32)
+        name, dims, params = "image_warping", [W, H], [np.asarray(p, np.float64) for p in wl.image_warping_params(d)]
+    elif case == "arap_mesh":
+        d = wl.arap_mesh_inputs(7, 6)
+        name, dims = "arap_mesh_deformation", [42, len(d["V0"])]
+        params = [np.asarray(p, np.float64) if np.asarray(p).dtype == np.float32 else p for p in wl.arap_mesh_params(d)]
+    else:
+        d = wl.bundle_adjustment_inputs(5, 30, 3)
+        name, dims = "bundle_adjustment", [5, 30, len(d["oToC"])]
+        params = [np.asarray(p, np.float64) if np.asarray(p).dtype == np.float32 else p for p in wl.bundle_adjustment_params(d)]
+    low = codegen.lower(energies.load(name), dims, "gauss_newton", name, True)
+    _, F, J = evaluate(energies.load(name), dims, params, np.float64)
+    Jx = api.assemble_jacobian(low.desc, lambda gi, n: interp.jacobian_entries(low.generator, params, gi))
+    assert Jx.shape == J.shape
+    assert abs(Jx - J).max() <= 1e-12 * max(1.0, abs(J).max())

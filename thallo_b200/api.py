@@ -75,6 +75,8 @@ def lib():
     L.ThalloB200_PlanTotalLinearIterations.restype, L.ThalloB200_PlanTotalLinearIterations.argtypes = C.c_ulonglong, [vp, vp]
     L.ThalloB200_PlanReadVector.restype = C.c_longlong
     L.ThalloB200_PlanReadVector.argtypes = [vp, vp, cp, vp, C.c_longlong]
+    L.ThalloB200_PlanExportJacobian.restype = C.c_longlong
+    L.ThalloB200_PlanExportJacobian.argtypes = [vp, vp, C.c_int, vp, vp, C.c_longlong]
     L.ThalloB200_PlanKernelTimes.restype = C.c_longlong
     L.ThalloB200_PlanKernelTimes.argtypes = [vp, vp, C.c_char_p, C.c_longlong]
     L.ThalloB200_NcclUniqueId.restype, L.ThalloB200_NcclUniqueId.argtypes = C.c_int, [vp, C.c_int]
@@ -110,6 +112,25 @@ def compile_only(source):
     sz = C.c_ulong(0)
     rc = L.ThalloB200_CompileOnly(source.encode(), buf, len(buf), C.byref(sz))
     return rc == 0, buf.value.decode(errors="replace"), sz.value
+
+
+def assemble_jacobian(desc, fetch):
+    """CSR J from per-group (value, column) entry lists in the export layout of ThalloB200_PlanExportJacobian:
+    `fetch(group, n)` returns the n = count * nnz_per_elem entries of a group, element-major, within an element row
+    by row with row_nnz[k] entries in row k; column -1 marks an access outside the domain.  Rows are numbered like the
+    reference's (gauss_newton.t:401-402): group base + element * terms + term."""
+    import numpy as np
+    import scipy.sparse as sp
+    rows, cols, vals, base = [], [], [], 0
+    for gi, g in enumerate(desc["groups"]):
+        n = g["count"] * g["nnz_per_elem"]
+        v, c = fetch(gi, n)
+        term_of = np.repeat(np.arange(g["nterms"]), g["row_nnz"])                  # entry within an element -> row
+        r = base + (np.arange(g["count"])[:, None] * g["nterms"] + term_of[None, :]).reshape(-1)
+        ok = np.asarray(c) >= 0
+        rows.append(r[ok]); cols.append(np.asarray(c)[ok]); vals.append(np.asarray(v)[ok])
+        base += g["count"] * g["nterms"]
+    return sp.csr_matrix((np.concatenate(vals), (np.concatenate(rows), np.concatenate(cols))), shape=(base, desc["nunk"]))
 
 
 class ThalloSolver:
@@ -229,6 +250,21 @@ class ThalloSolver:
             name, cnt, ms = ln.split()
             out[name] = (int(cnt), float(ms))
         return out
+
+    def export_jacobian(self):
+        """J at the current unknowns (after init) as a SciPy CSR matrix in the reference's row order
+        (group base + element * terms + term), assembled from ThalloB200_PlanExportJacobian of every group."""
+        import numpy as np
+        rt = np.float64 if self.double else np.float32
+
+        def fetch(gi, n):
+            v = np.zeros(max(n, 1), rt)
+            c = np.zeros(max(n, 1), np.int64)
+            got = self.L.ThalloB200_PlanExportJacobian(self.state, self.plan, gi, v.ctypes.data, c.ctypes.data, n)
+            if got != n:
+                raise RuntimeError("ThalloB200_PlanExportJacobian failed for group %d" % gi)
+            return v[:n], c[:n]
+        return assemble_jacobian(self.lowered.desc, fetch)
 
     def read_vector(self, name, count):
         import numpy as np

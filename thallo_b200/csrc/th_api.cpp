@@ -200,6 +200,10 @@ int ThalloB200_PlanLastLinearIterations(Thallo_State*, Thallo_Plan* plan) { retu
 unsigned long long ThalloB200_PlanTotalLinearIterations(Thallo_State*, Thallo_Plan* plan) {
     return plan ? plan->plan->total_linear_iterations : 0;
 }
+long long ThalloB200_PlanExportJacobian(Thallo_State*, Thallo_Plan* plan, int group, void* host_vals, long long* host_cols,
+                                        long long capacity) {
+    return plan && host_vals && host_cols ? plan->plan->export_jacobian(group, host_vals, host_cols, capacity) : -1;
+}
 long long ThalloB200_PlanReadVector(Thallo_State*, Thallo_Plan* plan, const char* name, void* host_dst, long long count) {
     return plan ? plan->plan->read_vector(name, host_dst, count) : 0;
 }

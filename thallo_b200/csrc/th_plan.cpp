@@ -1040,4 +1040,24 @@ long long Plan::read_vector(const char* name, void* dst, long long count) {
     return 0;
 }
 
+// The Jacobian of one residual group at the current unknowns, as the reference materialises it (generateDumpJ,
+// gauss_newton.t:325-487): per residual element its rows term by term, row k holding row_nnz[k] (value, column)
+// pairs; column = flat index of the unknown scalar (imageOffset + channels*idx + ch) or -1 outside the domain.
+long long Plan::export_jacobian(int g, void* host_vals, long long* host_cols, long long capacity) {
+    if (g < 0 || g >= (int)d_.groups.size() || params_buf_.empty()) return -1;
+    const long long n = d_.groups[g].count * (long long)d_.groups[g].nnz;
+    if (n > capacity) return -1;
+    if (n == 0) return 0;
+    void* dv = nullptr; long long* dc = nullptr;
+    CD(cudaMalloc(&dv, (size_t)n * real_size_));
+    CD(cudaMalloc((void**)&dc, (size_t)n * sizeof(long long)));
+    void* a[] = {params_buf_.data(), &dv, &dc};
+    launch_group(fn("th_computej_g" + std::to_string(g)), g, a);
+    CD(cudaMemcpyAsync(host_vals, dv, (size_t)n * real_size_, cudaMemcpyDeviceToHost, stream()));
+    CD(cudaMemcpyAsync(host_cols, dc, (size_t)n * sizeof(long long), cudaMemcpyDeviceToHost, stream()));
+    CD(cudaStreamSynchronize(stream()));
+    cudaFree(dv); cudaFree(dc);
+    return n;
+}
+
 }  // namespace thallo

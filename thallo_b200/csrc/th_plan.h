@@ -108,6 +108,7 @@ public:
     void get_parameter(const char* name, void* value);
     void summary(Thallo_PerformanceSummary* s) const { *s = perf_; }
     long long read_vector(const char* name, void* dst, long long count);
+    long long export_jacobian(int group, void* host_vals, long long* host_cols, long long capacity);
     // multi-GPU (include/thallo_b200.h "slab partition")
     int comm_init(const void* nccl_id, int rank, int world);
     int ipc_handle(void* handle64, long long* slow_extent);

@@ -276,3 +276,39 @@ def gather_jtf(gen, params, dtype=np.float64):
             np.add.at(r, base + tgt * C + ch, np.asarray(vals[n_], dtype).reshape(-1))
             np.add.at(dg, base + tgt * C + ch, np.asarray(vals[len(js) + n_], dtype).reshape(-1))
     return r, dg
+
+
+def jacobian_entries(gen, params, gi, dtype=np.float64):
+    """What th_computej_g<gi> writes: (values, columns) of group gi in the export layout (element-major, per element
+    the partials term-major / unknown-minor; column = flat unknown index or -1 outside the domain)."""
+    g = gen.groups[gi]
+    it = Interp(gen, params, g["domain"], None, dtype)
+    exprs, keys = [], []
+    for t in g["terms"]:
+        for u, p in zip(t.unknowns, t.partials):
+            exprs.append(p)
+            keys.append(u.key)
+    count = int(np.prod(it.shape)) if it.shape else 1
+    if not exprs:
+        return np.zeros(0, dtype), np.zeros(0, np.int64)
+    vals = np.stack([np.asarray(v, dtype).reshape(-1) for v in it.eval(exprs)], axis=1)            # (count, nnz)
+    cols = np.zeros((count, len(keys)), np.int64)
+    for j, k in enumerate(keys):
+        im = gen.images[k.image]
+        if k.index[0][0] == "s":
+            lin = it._sparse(k.index[0][1])
+            ok = np.ones(count, bool)
+        else:
+            lin = np.zeros(it.shape, np.int64)
+            ok = np.ones(it.shape, bool)
+            stride = 1
+            offs = it._offs(k.index)
+            for i, d in enumerate(g["domain"]):
+                c = it.coord[d] + offs[i]
+                n = gen.L.dims[d].size
+                ok &= (c >= 0) & (c < n)
+                lin += c * stride
+                stride *= n
+            lin, ok = lin.reshape(-1), ok.reshape(-1)
+        cols[:, j] = np.where(ok, gen.uoff[im.name] + lin * im.channels + k.channel, -1)
+    return vals.reshape(-1), cols.reshape(-1)
