@@ -142,3 +142,27 @@ def test_solver_parameter_roundtrip_and_summary():
     assert sm.total.count == 1 and sm.nonlinearIteration.count == 3 and sm.linearSolve.count == 3
     assert sm.total.meanMS > 0
     assert s.launches() >= 3 * (1 + 5 * 2)      # per nonlinear iteration: init + lIterations x (th_pcg_a, th_pcg_b)
+
+
+def test_lm_as_committed_switch_runs_gauss_newton(monkeypatch):
+    """THALLO_LM_AS_COMMITTED=1: a "levenberg_marquardt" problem defined by file name behaves like the reference
+    snapshot, where that kind silently runs Gauss-Newton (thallo.t:463)."""
+    W, H = 64, 40
+
+    def run(kind):
+        p = wl.image_warping_params(wl.image_warping_inputs(W, H))
+        dp = [dev(x) if i < 5 else x for i, x in enumerate(p)]
+        s = make_solver([W, H], "image_warping.t", kind, via_file=True)
+        s.set_parameters(nIterations=3, lIterations=15)
+        s.init(dp)
+        c = [s.current_cost()]
+        while s.step():
+            c.append(s.current_cost())
+        c.append(s.current_cost())
+        s.close()
+        return c
+    gn = run("gauss_newton")
+    lm = run("levenberg_marquardt")
+    monkeypatch.setenv("THALLO_LM_AS_COMMITTED", "1")
+    compat = run("levenberg_marquardt")
+    assert compat == gn and lm != gn

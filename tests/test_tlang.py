@@ -336,3 +336,15 @@ def test_reference_energy_files_lower_like_their_transcriptions(path, mod, dims,
     b = codegen.lower(energies.load(mod), dims, kind, mod, **kw)
     assert codegen.descriptor_text(a.desc) == codegen.descriptor_text(b.desc)
     assert a.source == b.source
+
+
+def test_lm_as_committed_lowers_levenberg_marquardt_to_gauss_newton():
+    """in the reference snapshot `"levenberg_marquardt"` silently runs Gauss-Newton (thallo.t:463).
+    THALLO_LM_AS_COMMITTED=1 (front end flag --lm-as-committed) reproduces that: same plan as a GN lowering."""
+    lm = codegen.lower(energies.load("image_warping"), [40, 24], "levenberg_marquardt", "image_warping")
+    compat = codegen.lower(energies.load("image_warping"), [40, 24], "levenberg_marquardt", "image_warping", lm_as_committed=True)
+    gn = codegen.lower(energies.load("image_warping"), [40, 24], "gauss_newton", "image_warping")
+    assert lm.desc["lm"] == 1 and compat.desc["lm"] == 0 and gn.desc["lm"] == 0
+    strip = lambda low: [l for l in low.source.splitlines() if not l.startswith("// generated by")]
+    assert strip(compat) == strip(gn) and strip(lm) != strip(gn)
+    assert "#define TH_LM 0" in compat.source and "#define TH_LM 1" in lm.source
