@@ -228,7 +228,8 @@ class Vec:
         return self.c[i]
 
     def get(self, *idx):
-        return Vec([c.get(*idx) for c in self.c])
+        return Vec([c.get(*idx) if (hasattr(c, "get") and (not isinstance(c, Dual) or c.d or np.ndim(c.val) > 0)) else c
+                    for c in self.c])
 
     def dot(self, o):
         r = self.c[0] * o.c[0]
@@ -344,6 +345,9 @@ def _shift(data, offs):
 class NSparse:
     def __init__(self, L, name, frm, to, pidx):
         self.L, self.name, self.frm, self.to, self.pidx = L, name, frm, to, pidx
+
+    def set_coherent(self, b):           # scheduling hint (warp-aggregated atomics); no effect on the energy
+        self.coherent = bool(b)
 
     def __call__(self, iv):
         assert isinstance(iv, IdxVar) and iv.dim is self.frm[0]

@@ -48,6 +48,7 @@ CASES = [
     ("tests/create_delete_cycle/laplacian.t", [9, 13], "at_output"),
     ("tests/energy_unit_tests/laplacian.t", [9, 13], "at_output"),
     ("tests/dense/curveFitting.t", [20, 3, 40], "gather"),
+    ("examples/sparse_bundle_fusion/bundle_fusion_solve.t", [8, 8, 12, 60], "gather"),     # SE(3) poses stored per frame, fetched per correspondence
 ]
 
 

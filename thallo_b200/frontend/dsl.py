@@ -250,6 +250,8 @@ class SymbolicL:
         self.computed = {}                   # expression id -> ComputedArray (ComputedArrayCache, thallo.t:69,1879-1885)
 
     def computed_get(self, exp, idx):
+        if exp.kind == "const":              # a constant needs no storage
+            return exp
         ca = self.computed.get(exp.id)
         if ca is None:
             ca = ComputedArray(self, len(self.computed), exp)

@@ -17,7 +17,8 @@ Library names bound (reference lib.t line in brackets): Dims [43], Inputs [578],
 Sparse/Param/Image [568-576], Residuals [18], UsePreconditioner [76], Stencil [559], All [55],
 And/Or/Not [72-74], Select [192], dot [92], Sqrt [96], normalize [100], length [104], gemv [78],
 Rotate2D [138], Rotate3D [123], cross [242], AngleAxisRotatePoint [514], SampledImage [144],
-Vector, InBounds/InBoundsExpanded (thallo.t:2091-2112), the comparison constructors and unary math
+Vector, the rigid-transform helpers [196-512: SelectOnAll, Max, matmul, transpose, PoseToMatrix, rigid_trans, ...],
+InBounds/InBoundsExpanded (thallo.t:2091-2112), the comparison constructors and unary math
 of ad.t:698-836, the scalar type names (thallo.t / precision.t:3-7), plus Lua's own `ipairs pairs
 unpack print assert error type tostring tonumber select math table string.format`.
 """
@@ -1047,6 +1048,21 @@ def _dsl_globals(L, G):
         "Rotate3D": lambda a, v: _lib.Rotate3D(L, vec(a), vec(v)),
         "cross": lambda a, b: _lib.cross(L, vec(a), vec(b)),
         "AngleAxisRotatePoint": lambda a, p: _lib.AngleAxisRotatePoint(L, vec(a), vec(p)),
+        "SelectOnAll": lambda ps, v, d: _lib.SelectOnAll(L, ps.array() if isinstance(ps, LuaTable) else list(ps), v, d),
+        "Max": lambda a, b: _lib.Max(L, a, b),
+        "matmul": lambda a, b: _lib.matmul(L, vec(a), vec(b)),
+        "transpose": lambda m: _lib.transpose(L, vec(m)),
+        "Matrix4": lambda *c: Vector(*c), "Vec4": lambda *c: Vector(*c), "Vec3": lambda v: Vector(v[0], v[1], v[2]),
+        "rotationFromMat4": lambda t: _lib.rotationFromMat4(L, vec(t)),
+        "translationFromMat4": lambda t: _lib.translationFromMat4(L, vec(t)),
+        "RotationMatrixAndTranslationToMat4": lambda r, t: _lib.RotationMatrixAndTranslationToMat4(L, vec(r), vec(t)),
+        "Mat4ToRigidTransform": lambda m: _lib.Mat4ToRigidTransform(L, vec(m)),
+        "RigidTransformToMat4": lambda m: _lib.RigidTransformToMat4(L, vec(m)),
+        "InvertRigidTransform": lambda m: _lib.InvertRigidTransform(L, vec(m)),
+        "CameraToDepth": lambda fx, fy, cx, cy, pos: _lib.CameraToDepth(L, fx, fy, cx, cy, vec(pos)),
+        "RodriguesSO3Exp": lambda w, A, B: _lib.RodriguesSO3Exp(L, vec(w), A, B),
+        "PoseToMatrix": lambda r, t: _lib.PoseToMatrix(L, vec(r), vec(t)),
+        "rigid_trans": lambda M, v: _lib.rigid_trans(L, vec(M), vec(v)),
         "Select": L.Select, "InBounds": L.InBounds, "InBoundsExpanded": L.InBoundsExpanded,
         "And": L.And, "Or": L.Or, "Not": L.Not,
         "inf": math.inf,
@@ -1067,6 +1083,8 @@ def _dsl_globals(L, G):
     for n in ("uint8", "int"):
         if hasattr(L, n):
             env[n] = getattr(L, n)
+    env["ad"] = table_of(Vector=Vector, select=L.Select, less=L.less, greater=L.greater, lesseq=L.lesseq, greatereq=L.greatereq,
+                         eq=L.eq, sqrt=env["sqrt"], sin=env["sin"], cos=env["cos"], toexp=lambda x: x)
     env["uchar"] = env.get("uint8")
     env["int32"] = env.get("int")
     return env
