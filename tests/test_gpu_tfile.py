@@ -113,3 +113,50 @@ def test_graph_energy_with_computed_array_from_t_file(tmp_path, dtype, tol):
     for a, b in zip(c, cref):
         assert abs(a - b) <= tol * max(abs(b), 1e-6), (c, cref)
     assert np.abs(dX.cpu().numpy() - Xo).max() <= (1e-9 if dtype == np.float64 else 2e-4)
+
+
+POSES_T = """
+-- frame-to-frame alignment of point correspondences: one se(3) pose per frame, stored as a 4x4 matrix per frame
+-- (computed array with 12 non-constant entries) and fetched per correspondence through the index arrays
+local T,C = Dims("T","C")
+Inputs {
+    Rot   = Unknown(thallo_float3,{T},0),
+    Trans = Unknown(thallo_float3,{T},1),
+    Pa    = Array(thallo_float3,{C},2),
+    Pb    = Array(thallo_float3,{C},3),
+    fa    = Sparse({C},{T},4),
+    fb    = Sparse({C},{T},5),
+    w     = Param(float,6)
+}
+UsePreconditioner(true)
+local t,c = T(),C()
+local pose = PoseToMatrix(Rot(t), Trans(t))
+local Ma, Mb = pose:get(fa(c)), pose:get(fb(c))
+r = Residuals {
+    align = Sqrt(w) * (rigid_trans(Ma, Pa(c)) - rigid_trans(Mb, Pb(c))),
+    prior = { 0.3*Rot(t), 0.3*Trans(t) }
+}
+"""
+
+
+@pytest.mark.parametrize("dtype,tol", [(np.float64, 1e-10), (np.float32, 1e-5)])
+def test_pose_energy_with_stored_matrices_from_t_file(tmp_path, dtype, tol):
+    rs = np.random.RandomState(9)
+    T, C = 12, 300
+    fa = rs.randint(0, T, C).astype(np.int32)
+    fb = ((fa + 1 + rs.randint(0, T - 1, C)) % T).astype(np.int32)          # never the same frame twice
+    Pa = rs.randn(C, 3).astype(dtype)
+    Pb = (Pa + 0.05 * rs.randn(C, 3)).astype(dtype)
+    Rot = (0.2 * rs.randn(T, 3)).astype(dtype)
+    Trans = (0.3 * rs.randn(T, 3)).astype(dtype)
+    w = np.float32(2.0)
+    p = tmp_path / "poses.t"
+    p.write_text(POSES_T)
+    Ro, To = Rot.copy(), Trans.copy()
+    o, cref = _trajectory_oracle(tlang.load(str(p)), [T, C], "gauss_newton", dtype, "residualwise", [Ro, To, Pa, Pb, fa, fb, w], 4, 12)
+    dR, dT = dev(Rot), dev(Trans)
+    c, _ = _trajectory_gpu(str(p), [T, C], "gauss_newton", dtype, [dR, dT, dev(Pa), dev(Pb), dev(fa), dev(fb), w], 4, 12)
+    assert len(c) == len(cref), (c, cref)
+    for a, b in zip(c, cref):
+        assert abs(a - b) <= tol * max(abs(b), 1e-6), (c, cref)
+    assert np.abs(dR.cpu().numpy() - Ro).max() <= (1e-8 if dtype == np.float64 else 2e-4)
