@@ -348,3 +348,11 @@ def test_lm_as_committed_lowers_levenberg_marquardt_to_gauss_newton():
     strip = lambda low: [l for l in low.source.splitlines() if not l.startswith("// generated by")]
     assert strip(compat) == strip(gn) and strip(lm) != strip(gn)
     assert "#define TH_LM 0" in compat.source and "#define TH_LM 1" in lm.source
+
+
+def test_type_and_tostring_of_host_values():
+    r, _, _ = run("""
+        local function f() end
+        return type(nil), type(true), type(1.5), type("s"), type({}), type(f), type(print), type(obj), tostring(3.0), tostring(nil)
+    """, obj=object())
+    assert r == ["nil", "boolean", "number", "string", "table", "function", "function", "userdata", "3", "nil"]

@@ -738,9 +738,10 @@ class Interpreter:
             return "string"
         if isinstance(v, LuaTable):
             return "table"
-        if isinstance(v, LuaFunction) or callable(v) and not hasattr(v, "__dict__"):
+        import types
+        if isinstance(v, (LuaFunction, types.FunctionType, types.BuiltinFunctionType, types.MethodType)):
             return "function"
-        return "userdata"
+        return "userdata"                    # DSL objects: images, index variables, expressions, vectors
 
     @staticmethod
     def tostring(v):
