@@ -71,3 +71,32 @@ def test_warp_primitive_known_answer_kernels_compile():
     ok, log, size = api.compile_only('#define TH_WARP_KAT 1\n#include "thallo_warp.cuh"\n')
     assert ok, log[-2000:]
     assert size > 1000
+
+
+# ---- error behaviour of the reference-facing entry points, as far as it can be exercised without a GPU
+def test_problem_define_rejects_unknown_solver_kinds_and_plan_fails_loudly_without_a_gpu(tmp_path):
+    import ctypes as C
+    import torch
+    from thallo_b200 import api
+    L = api.lib()
+    st = L.Thallo_NewState(api.InitializationParameters(0, 0, 0, 0, 1, 0))
+    assert st
+    # thallo.t:74 asserts the kind is exactly one of the two names ("LMGPU" is Opt's, not Thallo's)
+    assert not L.Thallo_ProblemDefine(st, b"image_warping.t", b"LMGPU")
+    assert b"unknown solver kind" in L.ThalloB200_LastError()
+    p = L.Thallo_ProblemDefine(st, b"image_warping.t", b"levenberg_marquardt")
+    assert p                                           # only records (file name, kind), like the reference (thallo.t:5954-5958)
+    dims = (C.c_uint * 2)(64, 64)
+    missing = L.Thallo_ProblemDefine(st, b"no_such_energy.t", b"gauss_newton")
+    assert missing and not L.Thallo_ProblemPlan(st, missing, dims)         # the file is read at plan time
+    assert b"does not exist" in L.ThalloB200_LastError()
+    broken = tmp_path / "broken.t"
+    broken.write_text("local W,H = Dims('W','H')\nInputs { X = Unknown(float,{W,H},0) }\nr = Residuals { fit = X(W(),H()) + }\n")
+    bp = L.Thallo_ProblemDefine(st, str(broken).encode(), b"gauss_newton")
+    assert bp and not L.Thallo_ProblemPlan(st, bp, dims)
+    assert b"broken.t:3" in L.ThalloB200_LastError()                        # syntax error reported with file and line
+    if not torch.cuda.is_available():
+        assert not L.Thallo_ProblemPlan(st, p, dims)                          # no CPU fallback: NULL + message, never a silent CPU path
+        assert b"no CUDA device" in L.ThalloB200_LastError() and b"no CPU fallback" in L.ThalloB200_LastError()
+    L.Thallo_ProblemDelete(st, p)
+    assert L.ThalloB200_Version().startswith(b"thallo_b200")
