@@ -36,3 +36,15 @@ def test_product_arm_fails_loudly_without_a_gpu():
     r = _run(["--size", "64", "--steps", "1", "--warmup", "0", "--no-cpu-baseline"])
     assert r.returncode != 0
     assert "\"value\"" not in r.stdout            # no bench line from a fallback path
+
+
+def test_reference_arm_under_torchrun_prints_one_line_from_rank_0():
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29534", os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--size", "64",
+           "--steps", "1", "--warmup", "0"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=300, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    line = json.loads(lines[0])
+    assert line["impl"] == "reference" and line["n_gpus"] == 2 and line["value"] > 0
