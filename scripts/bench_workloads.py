@@ -32,6 +32,9 @@ def main():
     ap.add_argument("--steps", type=int, default=2)
     ap.add_argument("--no-materialize", action="store_true")
     ap.add_argument("--jp", action="store_true", help="arap_mesh: schedule Jt[Jp] for the edge term (J p stored per edge)")
+    ap.add_argument("--jp-all", action="store_true",
+                    help="any workload: gather schedule with every residual group in the Jt[Jp] form (two-pass operator: J p per "
+                         "residual stored, transposed partials gathered per unknown); not verified on a GPU in round 1")
     a = ap.parse_args()
     import numpy as np
     import torch
@@ -97,6 +100,10 @@ def main():
            "input_generation_s": round(gen_s, 1)}
     for timing in (1, 2):
         t1 = time.time()
+        if a.jp_all:
+            kw = dict(kw)
+            kw["define_kwargs"] = dict(kw.get("define_kwargs") or {}, jp_all=True)
+            a.schedule = "gather"
         s = ThalloSolver(dims, energy, kind, timing=timing, schedule=a.schedule, **kw)
         out["schedule"] = s.lowered.desc["schedule"]
         s.set_parameters(nIterations=a.nit, lIterations=a.lit)

@@ -196,3 +196,26 @@ def test_exported_jacobian_layout_assembles_to_the_oracle_jacobian(case):
     Jx = api.assemble_jacobian(low.desc, lambda gi, n: interp.jacobian_entries(low.generator, params, gi))
     assert Jx.shape == J.shape
     assert abs(Jx - J).max() <= 1e-12 * max(1.0, abs(J).max())
+
+
+# ---- two-pass operator on image domains: gather schedule with every group in the Jt[Jp] form (lower(..., jp_all=True))
+@pytest.mark.parametrize("name", ["shape_from_shading", "volumetric_mesh_deformation", "image_warping"])
+def test_two_pass_operator_on_image_domains_matches_oracle(name):
+    if name == "shape_from_shading":
+        dims = [40, 32]
+        params = _sfs_params64(wl.sfs_inputs(*dims))
+    elif name == "volumetric_mesh_deformation":
+        dims = [6, 5, 4]
+        params = [np.asarray(p, np.float64) if np.asarray(p).dtype == np.float32 else p for p in wl.volumetric_params(wl.volumetric_inputs(*dims))]
+    else:
+        dims = [24, 20]
+        d = wl.image_warping_inputs(*dims)
+        d["Angle"] = d["Angle"] + 0.3 * np.random.RandomState(1).randn(*d["Angle"].shape).astype(np.float32)
+        params = [np.asarray(p, np.float64) for p in wl.image_warping_params(d)]
+    low = codegen.lower(energies.load(name), dims, "gauss_newton", name, True, "gather", jp_all=True)
+    assert all(g["materialize"] == 2 for g in low.desc["groups"])
+    _, F, J = evaluate(energies.load(name), dims, params, np.float64)
+    p = np.random.RandomState(5).randn(J.shape[1])
+    want = J.T.tocsr() @ (J @ p)
+    got = interp.gather_apply(low.generator, params, p)
+    assert np.abs(got - want).max() <= 1e-10 * max(1.0, np.abs(want).max())

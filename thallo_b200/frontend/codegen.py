@@ -1374,9 +1374,15 @@ def descriptor_text(d):
 
 
 def lower(define, dims, kind="gauss_newton", name="energy", double=False, schedule="auto",
-          lm_as_committed=False, hoist=True, tile=None, partition=None, **define_kwargs):
+          lm_as_committed=False, hoist=True, tile=None, partition=None, jp_all=False, **define_kwargs):
+    """jp_all: give every residual group the Jt[Jp] schedule (as if the energy said `r.<g>.Jp:set_materialize(true)` for
+    each) -- with schedule="gather" on an image domain this is the two-pass operator: J p per residual stored once,
+    then every unknown applies its transposed partials to the stored values of the residuals around it."""
     from .dsl import build_spec
     L = build_spec(define, dims, **define_kwargs)
+    if jp_all:
+        for g in L.residuals.groups:
+            g.Jp.set_materialize(True)
     gen = Generator(L, name, kind, double, schedule, lm_as_committed, hoist, tile, partition)
     out = gen.generate()
     out.generator = gen
