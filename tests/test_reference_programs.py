@@ -1,0 +1,98 @@
+"""The reference's own C++ test programs (tests/minimal/main.cpp, tests/minimal_graph/main.cpp), UNMODIFIED, compiled
+where they lie against this repository's include/Thallo.h and linked with libThallo.so (`make -C oracle ref`): the
+drop-in check of the C ABI at the source and the link level.  Running them needs a GPU; that part is below, marked
+`gpu`.  Nothing from the reference is copied: the energy files the programs ask for by name (`laplacian.t`) are
+written into the working directory from the texts below, which restate the two energies."""
+import ctypes
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = "/root/reference"
+BIN = os.path.join(ROOT, "oracle", "_ref")
+
+IMAGE_LAPLACIAN_T = """
+-- fit to A plus forward differences in x and y (the revision of the energy that produced tests/minimal/gold.png)
+local W,H = Dims("W","H")
+Inputs { X = Unknown(float,{W,H},0), A = Array(float,{W,H},1) }
+local x,y = W(),H()
+local w_fit = .2
+r = Residuals {
+    fit = w_fit*(X(x,y) - A(x,y)),
+    reg = { Select(InBounds(x+1,y), X(x,y) - X(x+1,y), 0), Select(InBounds(x,y+1), X(x,y) - X(x,y+1), 0) }
+}
+"""
+
+GRAPH_LAPLACIAN_T = """
+-- fit to A plus differences along the edges (v0, v1) of a graph
+local N,E = Dims("N","E")
+Inputs { X = Unknown(float,{N},0), A = Array(float,{N},1), v0 = Sparse({E},{N},2), v1 = Sparse({E},{N},3) }
+local n,e = N(),E()
+r = Residuals { fit = .5*(X(n) - A(n)), reg = X(v0(e)) - X(v1(e)) }
+"""
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference checkout not present (GPU box)")
+def test_reference_callers_compile_and_link_unmodified():
+    from thallo_b200 import api
+    api.build_library()
+    subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "ref"], stdout=subprocess.DEVNULL)
+    for name in ("ref_minimal", "ref_minimal_graph"):
+        path = os.path.join(BIN, name)
+        assert os.path.isfile(path) and os.access(path, os.X_OK)
+        undefined = subprocess.run(["nm", "-D", "--undefined-only", path], capture_output=True, text=True).stdout
+        used = set(re.findall(r"\bThallo_\w+", undefined))
+        assert {"Thallo_NewState", "Thallo_ProblemDefine", "Thallo_ProblemPlan", "Thallo_ProblemSolve",
+                "Thallo_ProblemCurrentCost", "Thallo_PlanFree", "Thallo_ProblemDelete"} <= used
+        ldd = subprocess.run(["ldd", path], capture_output=True, text=True).stdout
+        assert "libThallo.so" in ldd and "not found" not in ldd.split("libThallo.so")[1].splitlines()[0]
+
+
+def _libc_uniform(n):
+    """What the programs fill their input with: glibc rand() / RAND_MAX from the default seed."""
+    libc = ctypes.CDLL("libc.so.6")
+    libc.srand(1)
+    return np.array([libc.rand() / 2147483647.0 for _ in range(n)], np.float64).astype(np.float32)
+
+
+def _run(binary, tmp_path, energy_text):
+    (tmp_path / "laplacian.t").write_text(energy_text)
+    r = subprocess.run([os.path.join(BIN, binary)], cwd=str(tmp_path), capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    m = re.search(r"minimal\w* ([-+0-9.eE]+|nan|inf)", r.stdout)
+    assert m, r.stdout[-2000:]
+    assert (tmp_path / "result.png").exists()
+    return float(m.group(1))
+
+
+@pytest.mark.gpu
+@pytest.mark.xfail(strict=False, reason="written after the GPU budget of round 1 was spent: not yet run on a GPU")
+@pytest.mark.skipif(not os.path.isfile(os.path.join(BIN, "ref_minimal")), reason="oracle/_ref not built")
+def test_reference_minimal_program_runs_against_this_library(tmp_path):
+    import torch
+    from thallo_b200.api import ThalloSolver
+    cost = _run("ref_minimal", tmp_path, IMAGE_LAPLACIAN_T)
+    A = _libc_uniform(512 * 512)
+    dX, dA = torch.from_numpy(A.copy()).cuda(), torch.from_numpy(A.copy()).cuda()
+    s = ThalloSolver([512, 512], "laplacian", "gauss_newton")
+    want = s.solve([dX, dA])                      # the library's defaults, like the program: GN 10 x 10
+    assert abs(cost - want) <= 1e-5 * abs(want)
+
+
+@pytest.mark.gpu
+@pytest.mark.xfail(strict=False, reason="written after the GPU budget of round 1 was spent: not yet run on a GPU")
+@pytest.mark.skipif(not os.path.isfile(os.path.join(BIN, "ref_minimal_graph")), reason="oracle/_ref not built")
+def test_reference_minimal_graph_program_runs_against_this_library(tmp_path):
+    import torch
+    from thallo_b200.api import ThalloSolver
+    cost = _run("ref_minimal_graph", tmp_path, GRAPH_LAPLACIAN_T)
+    A = _libc_uniform(512)
+    v0 = np.arange(511, dtype=np.int32)
+    dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    s = ThalloSolver([512, 511], "graph_laplacian", "gauss_newton")
+    want = s.solve([dev(A.copy()), dev(A.copy()), dev(v0), dev(v0 + 1)])
+    assert abs(cost - want) <= 1e-5 * abs(want)
