@@ -96,3 +96,15 @@ def test_reference_minimal_graph_program_runs_against_this_library(tmp_path):
     s = ThalloSolver([512, 511], "graph_laplacian", "gauss_newton")
     want = s.solve([dev(A.copy()), dev(A.copy()), dev(v0), dev(v0 + 1)])
     assert abs(cost - want) <= 1e-5 * abs(want)
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference checkout not present (GPU box)")
+def test_reference_example_harness_compiles_against_this_header(tmp_path):
+    """examples/shared/ThalloSolver.h -- the wrapper every reference example drives the C ABI through (NewState ->
+    ProblemDefine -> ProblemPlan, SetSolverParameter*, Solve or Init / Step / CurrentCost, GetPerformanceSummary) --
+    compiled as the examples compile it (nvcc) with this repository's Thallo.h in place of the reference's."""
+    tu = tmp_path / "harness.cu"
+    tu.write_text('extern "C" {\n#include "Thallo.h"\n}\n#include "ThalloSolver.h"\nint main() { return 0; }\n')
+    r = subprocess.run(["nvcc", "-std=c++14", "-w", "-c", "-o", str(tmp_path / "harness.o"), "-I", os.path.join(ROOT, "include"),
+                        "-I", os.path.join(REF, "examples", "shared"), str(tu)], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-3000:]
