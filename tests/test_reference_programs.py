@@ -110,3 +110,17 @@ def test_reference_example_harness_compiles_against_this_header(tmp_path):
     r = subprocess.run(["nvcc", "-std=c++14", "-w", "-c", "-o", str(tmp_path / "harness.o"), "-I", os.path.join(ROOT, "include"),
                         "-I", os.path.join(REF, "examples", "shared"), str(tu)], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stderr[-3000:]
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference checkout not present (GPU box)")
+def test_reference_minimal_links_statically_against_libthallo_a(tmp_path):
+    """The reference ships a static libThallo.a (API/Makefile:8-12); so does this repository."""
+    from thallo_b200 import api
+    api.build_library()
+    lib_a = os.path.join(os.path.dirname(api.LIB_PATH), "libThallo.a")
+    out = tmp_path / "ref_minimal_static"
+    r = subprocess.run(["g++", "-std=c++14", "-w", "-I", os.path.join(ROOT, "include"), "-I", "/usr/local/cuda/include",
+                        os.path.join(REF, "tests", "minimal", "main.cpp"), "-o", str(out), lib_a, "-L/usr/local/cuda/lib64",
+                        "-lnvrtc", "-lcudart", "-ldl", "-lrt", "-lpthread"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-3000:]
+    assert "libThallo" not in subprocess.run(["ldd", str(out)], capture_output=True, text=True).stdout
