@@ -1,0 +1,70 @@
+"""Pins the oracle's operator math on the headline energy against code the reference's authors wrote by hand: the
+CUDA device functions of examples/image_warping/src/WarpingSolverEquations.h (cost, -J^T F, J^T J p of the 2-D ARAP
+energy, hand-derived), compiled for the host from the reference tree where it lies (`make -C oracle hand` ->
+oracle/_ref/libiw_hand.so; SURVEY 8c "secondary oracle").  The oracle differentiates the energy as Thallo defines it
+with dual numbers; the hand solver minimises sum w e^2 where Thallo minimises 1/2 sum (sqrt(w) e)^2, hence the factor 2."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+import energies
+from oracle.npdsl import evaluate
+from thallo_b200 import workloads as wl
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LIB = os.path.join(ROOT, "oracle", "_ref", "libiw_hand.so")
+
+
+def _lib():
+    if os.path.isdir("/root/reference"):
+        import subprocess
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "hand"], stdout=subprocess.DEVNULL)
+    if not os.path.exists(LIB):
+        pytest.skip("oracle/_ref/libiw_hand.so not built (needs the reference checkout)")
+    lib = C.CDLL(LIB)
+    fp = C.POINTER(C.c_float)
+    common = [C.c_int, C.c_int, fp, fp, fp, fp, fp, C.c_float, C.c_float]
+    lib.iw_hand_cost.restype, lib.iw_hand_cost.argtypes = C.c_double, common
+    lib.iw_hand_minus_jtf.argtypes = common + [fp, fp]
+    lib.iw_hand_apply_jtj.argtypes = common + [fp, fp, fp, fp]
+    return lib, fp
+
+
+@pytest.mark.parametrize("W,H,seed", [(23, 17, 1), (8, 31, 2), (40, 5, 3)])
+def test_oracle_cost_gradient_and_jtj_match_the_reference_hand_derived_equations(W, H, seed):
+    lib, fp = _lib()
+    rs = np.random.RandomState(seed)
+    d = wl.image_warping_inputs(W, H)
+    d["Offset"] = (d["Offset"] + rs.randn(*d["Offset"].shape)).astype(np.float32)
+    d["Angle"] = (0.4 * rs.randn(*d["Angle"].shape)).astype(np.float32)
+    d["Mask"] = np.zeros_like(d["Mask"])                       # every pixel valid: the two formulations then agree term by term
+    cons = -np.ones_like(d["Constraints"])
+    sel = rs.rand(W * H) < 0.3
+    cons[sel] = (d["UrShape"][sel] + 1.0 + rs.rand(int(sel.sum()), 2)).astype(np.float32)
+    d["Constraints"] = cons
+    wfit, wreg = 3.0, 0.7
+    d["w_fitSqrt"], d["w_regSqrt"] = np.float32(np.sqrt(wfit)), np.float32(np.sqrt(wreg))
+    _, F, J = evaluate(energies.load("image_warping"), [W, H], [np.asarray(p, np.float64) for p in wl.image_warping_params(d)], np.float64)
+    n = W * H
+    ptr = lambda a: a.ctypes.data_as(fp)
+    x, A, ur, cn, mk = (np.ascontiguousarray(d[k], np.float32) for k in ("Offset", "Angle", "UrShape", "Constraints", "Mask"))
+    args = (W, H, ptr(x), ptr(A), ptr(ur), ptr(cn), ptr(mk), wfit, wreg)
+    # cost
+    cost_thallo = 0.5 * float(F @ F)
+    assert abs(lib.iw_hand_cost(*args) - 2 * cost_thallo) <= 1e-6 * 2 * cost_thallo
+    # -J^T F
+    b, bA = np.zeros((n, 2), np.float32), np.zeros(n, np.float32)
+    lib.iw_hand_minus_jtf(*args, ptr(b), ptr(bA))
+    g = -(J.T @ F)
+    assert np.abs(b.reshape(-1) - 2 * g[:2 * n]).max() <= 2e-6 * np.abs(g).max()
+    assert np.abs(bA - 2 * g[2 * n:]).max() <= 2e-6 * np.abs(g).max()
+    # J^T J p
+    pv = rs.randn(3 * n).astype(np.float32)
+    pp, pa = np.ascontiguousarray(pv[:2 * n]), np.ascontiguousarray(pv[2 * n:])
+    out, outA = np.zeros((n, 2), np.float32), np.zeros(n, np.float32)
+    lib.iw_hand_apply_jtj(*args, ptr(pp), ptr(pa), ptr(out), ptr(outA))
+    o = J.T @ (J @ pv.astype(np.float64))
+    assert np.abs(out.reshape(-1) - 2 * o[:2 * n]).max() <= 2e-6 * np.abs(o).max()
+    assert np.abs(outA - 2 * o[2 * n:]).max() <= 2e-6 * np.abs(o).max()
