@@ -6,23 +6,7 @@
 // -J^T F and J^T J p (dual-number AD of the energy as Thallo defines it) can be checked on the CPU against derivatives
 // the reference's authors wrote by hand (SURVEY 8c "secondary oracle").  Scaling between the two: the hand solver
 // minimises sum w e^2, Thallo 1/2 sum (sqrt(w) e)^2, so cost, gradient and J^T J of the former are twice the latter's.
-#include <cuda_runtime.h>
-#include <cmath>
-#include <cstring>
-#include <limits>
-#include <vector>
-
-// device-only constructs used by the included utility headers (never executed here)
-static inline float __shfl_down(float v, int, int) { return v; }
-static inline void __syncthreads() {}
-static inline int __float_as_int(float f) { int i; std::memcpy(&i, &f, 4); return i; }
-static inline float __int_as_float(int i) { float f; std::memcpy(&f, &i, 4); return f; }
-static inline float atomicAdd(float* a, float v) { float o = *a; *a += v; return o; }
-struct ThUint3 { unsigned x, y, z; };
-static ThUint3 threadIdx = {0, 0, 0}, blockIdx = {0, 0, 0}, blockDim = {1, 1, 1}, gridDim = {1, 1, 1};
-#undef __shared__
-#define __shared__
-float bucket[2048];
+#include "hand_shims.h"
 
 #include REF_STATE_HEADER          // WarpingSolverState.h first, as WarpingSolver.cu includes it (the utility header needs SolverInput)
 #include REF_EQUATIONS_HEADER

@@ -68,3 +68,57 @@ def test_oracle_cost_gradient_and_jtj_match_the_reference_hand_derived_equations
     o = J.T @ (J @ pv.astype(np.float64))
     assert np.abs(out.reshape(-1) - 2 * o[:2 * n]).max() <= 2e-6 * np.abs(o).max()
     assert np.abs(outA - 2 * o[2 * n:]).max() <= 2e-6 * np.abs(o).max()
+
+
+def _arap_lib():
+    lib_path = os.path.join(ROOT, "oracle", "_ref", "libarap_hand.so")
+    if os.path.isdir("/root/reference"):
+        import subprocess
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "hand"], stdout=subprocess.DEVNULL)
+    if not os.path.exists(lib_path):
+        pytest.skip("oracle/_ref/libarap_hand.so not built (needs the reference checkout)")
+    lib = C.CDLL(lib_path)
+    fp, ip = C.POINTER(C.c_float), C.POINTER(C.c_int)
+    common = [C.c_int, fp, fp, fp, fp, ip, ip, ip, C.c_float, C.c_float]
+    lib.arap_hand_cost.restype, lib.arap_hand_cost.argtypes = C.c_double, common
+    lib.arap_hand_minus_jtf.argtypes = common + [fp, fp]
+    lib.arap_hand_apply_jtj.argtypes = common + [fp, fp, fp, fp]
+    return lib, fp, ip
+
+
+@pytest.mark.parametrize("nx,ny,seed", [(9, 7, 2), (5, 12, 3)])
+def test_oracle_matches_the_reference_hand_derived_arap_mesh_equations(nx, ny, seed):
+    """examples/arap_mesh_deformation/src/WarpingSolverEquations.h (+ RotationHelper.h): graph domain, 3-D rotations by
+    three Euler angles per vertex; the hand solver walks per-vertex neighbour lists, Thallo's energy directed edges."""
+    lib, fp, ip = _arap_lib()
+    rs = np.random.RandomState(seed)
+    d = wl.arap_mesh_inputs(nx, ny)
+    N = nx * ny
+    d["Position"] = (d["Position"] + 0.3 * rs.randn(N, 3)).astype(np.float32)
+    d["Angle"] = (0.4 * rs.randn(N, 3)).astype(np.float32)
+    wfit, wreg = 4.0, 1.3
+    d["w_fitSqrt"], d["w_regSqrt"] = np.float32(np.sqrt(wfit)), np.float32(np.sqrt(wreg))
+    p64 = [np.asarray(p, np.float64) if np.asarray(p).dtype == np.float32 else p for p in wl.arap_mesh_params(d)]
+    _, F, J = evaluate(energies.load("arap_mesh_deformation"), [N, len(d["V0"])], p64, np.float64)
+    V0, V1 = d["V0"].astype(np.int64), d["V1"].astype(np.int64)
+    numN = np.bincount(V0, minlength=N).astype(np.int32)
+    nOff = np.concatenate([[0], np.cumsum(numN)[:-1]]).astype(np.int32)
+    nIdx = V1[np.argsort(V0, kind="stable")].astype(np.int32)
+    target = d["Constraints"].astype(np.float32).copy()
+    target[target[:, 0] < -999999.9] = -np.inf              # the hand solver marks "no target" with MINF
+    ptr, iptr = (lambda a: a.ctypes.data_as(fp)), (lambda a: a.ctypes.data_as(ip))
+    x, a, ur = (np.ascontiguousarray(d[k], np.float32) for k in ("Position", "Angle", "Original"))
+    args = (N, ptr(x), ptr(a), ptr(target), ptr(ur), iptr(numN), iptr(nIdx), iptr(nOff), wfit, wreg)
+    assert abs(lib.arap_hand_cost(*args) - float(F @ F)) <= 2e-6 * float(F @ F)
+    b, bA = np.zeros((N, 3), np.float32), np.zeros((N, 3), np.float32)
+    lib.arap_hand_minus_jtf(*args, ptr(b), ptr(bA))
+    g = -(J.T @ F)
+    assert np.abs(b.reshape(-1) - 2 * g[:3 * N]).max() <= 3e-6 * np.abs(g).max()
+    assert np.abs(bA.reshape(-1) - 2 * g[3 * N:]).max() <= 3e-6 * np.abs(g).max()
+    pv = rs.randn(6 * N).astype(np.float32)
+    pp, pa = np.ascontiguousarray(pv[:3 * N]), np.ascontiguousarray(pv[3 * N:])
+    out, outA = np.zeros((N, 3), np.float32), np.zeros((N, 3), np.float32)
+    lib.arap_hand_apply_jtj(*args, ptr(pp), ptr(pa), ptr(out), ptr(outA))
+    o = J.T @ (J @ pv.astype(np.float64))
+    assert np.abs(out.reshape(-1) - 2 * o[:3 * N]).max() <= 3e-6 * np.abs(o).max()
+    assert np.abs(outA.reshape(-1) - 2 * o[3 * N:]).max() <= 3e-6 * np.abs(o).max()
