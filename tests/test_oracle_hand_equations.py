@@ -122,3 +122,50 @@ def test_oracle_matches_the_reference_hand_derived_arap_mesh_equations(nx, ny, s
     o = J.T @ (J @ pv.astype(np.float64))
     assert np.abs(out.reshape(-1) - 2 * o[:3 * N]).max() <= 3e-6 * np.abs(o).max()
     assert np.abs(outA.reshape(-1) - 2 * o[3 * N:]).max() <= 3e-6 * np.abs(o).max()
+
+
+@pytest.mark.parametrize("dims,seed", [((5, 4, 6), 2), ((3, 7, 4), 5)])
+def test_oracle_matches_the_reference_hand_derived_volumetric_equations(dims, seed):
+    """examples/volumetric_mesh_deformation/src/WarpingSolverEquations.h: 3-D lattice, six neighbours, 3-D rotations.
+    The hand solver's x is its slowest axis; the stencil is symmetric, so its (x, y, z) = this energy's (D, H, W)."""
+    lib_path = os.path.join(ROOT, "oracle", "_ref", "libvol_hand.so")
+    if os.path.isdir("/root/reference"):
+        import subprocess
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "hand"], stdout=subprocess.DEVNULL)
+    if not os.path.exists(lib_path):
+        pytest.skip("oracle/_ref/libvol_hand.so not built (needs the reference checkout)")
+    lib = C.CDLL(lib_path)
+    fp, ip = C.POINTER(C.c_float), C.POINTER(C.c_int)
+    common = [C.c_int, fp, fp, fp, fp, ip, C.c_float, C.c_float]
+    lib.vol_hand_cost.restype, lib.vol_hand_cost.argtypes = C.c_double, common
+    lib.vol_hand_minus_jtf.argtypes = common + [fp, fp]
+    lib.vol_hand_apply_jtj.argtypes = common + [fp, fp, fp, fp]
+    W, H, D = dims
+    N = W * H * D
+    rs = np.random.RandomState(seed)
+    d = wl.volumetric_inputs(W, H, D)
+    d["Offset"] = (d["Offset"] + 0.3 * rs.randn(N, 3)).astype(np.float32)
+    d["Angle"] = (0.4 * rs.randn(N, 3)).astype(np.float32)
+    wfit, wreg = 2.0, 0.6
+    d["w_fitSqrt"], d["w_regSqrt"] = np.float32(np.sqrt(wfit)), np.float32(np.sqrt(wreg))
+    p64 = [np.asarray(p, np.float64) if np.asarray(p).dtype == np.float32 else p for p in wl.volumetric_params(d)]
+    _, F, J = evaluate(energies.load("volumetric_mesh_deformation"), [W, H, D], p64, np.float64)
+    target = d["Constraints"].astype(np.float32).copy()
+    target[target[:, 0] < -999999.9] = -np.inf
+    nodes = np.array([D, H, W], np.int32)
+    ptr = lambda a: a.ctypes.data_as(fp)
+    x, a, ur = (np.ascontiguousarray(d[k], np.float32) for k in ("Offset", "Angle", "UrShape"))
+    args = (N, ptr(x), ptr(a), ptr(target), ptr(ur), nodes.ctypes.data_as(ip), wfit, wreg)
+    assert abs(lib.vol_hand_cost(*args) - float(F @ F)) <= 2e-6 * float(F @ F)
+    b, bA = np.zeros((N, 3), np.float32), np.zeros((N, 3), np.float32)
+    lib.vol_hand_minus_jtf(*args, ptr(b), ptr(bA))
+    g = -(J.T @ F)
+    assert np.abs(b.reshape(-1) - 2 * g[:3 * N]).max() <= 3e-6 * np.abs(g).max()
+    assert np.abs(bA.reshape(-1) - 2 * g[3 * N:]).max() <= 3e-6 * np.abs(g).max()
+    pv = rs.randn(6 * N).astype(np.float32)
+    pp, pa = np.ascontiguousarray(pv[:3 * N]), np.ascontiguousarray(pv[3 * N:])
+    out, outA = np.zeros((N, 3), np.float32), np.zeros((N, 3), np.float32)
+    lib.vol_hand_apply_jtj(*args, ptr(pp), ptr(pa), ptr(out), ptr(outA))
+    o = J.T @ (J @ pv.astype(np.float64))
+    assert np.abs(out.reshape(-1) - 2 * o[:3 * N]).max() <= 3e-6 * np.abs(o).max()
+    assert np.abs(outA.reshape(-1) - 2 * o[3 * N:]).max() <= 3e-6 * np.abs(o).max()
