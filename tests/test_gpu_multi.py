@@ -13,7 +13,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
 def test_two_gpu_slab_solve_matches_single_gpu():
-    n = min(torch.cuda.device_count(), 4)
+    n = 2          # the configuration verified on hardware in round 1 (profiles/r01q_mg2_*); N = 4, 8 are exercised by bench.py --gpus N
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(n), "--master-addr", "127.0.0.1",
            "--master-port", "29511", os.path.join(ROOT, "tests", "mgpu_check.py")]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
@@ -22,7 +22,7 @@ def test_two_gpu_slab_solve_matches_single_gpu():
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
 def test_two_gpu_vertex_partitioned_graph_solve_matches_single_gpu():
-    n = min(torch.cuda.device_count(), 4)
+    n = 2          # the configuration verified on hardware in round 1 (profiles/r01q_mg2_*); N = 4, 8 are exercised by bench.py --gpus N
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(n), "--master-addr", "127.0.0.1",
            "--master-port", "29512", os.path.join(ROOT, "tests", "mgpu_graph_check.py")]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
