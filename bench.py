@@ -156,7 +156,7 @@ def workload_config(a, world):
                            "one %dx%d problem slab-partitioned along y over %d GPUs (%dx%d owned pixels each): halo rows over NVLink "
                            "peer stores, PCG scalars over NCCL all-reduce; value = global PCG iterations/s x %d slabs"
                            % (a.size, a.size * world, world, a.size, a.size, world),
-            "l2": "working set 12 solver vectors x %.0f MB + inputs, larger than the 126 MB L2; no flush needed" % (12.0 * a.size * a.size / 1e6)}
+            "l2": "working set 13 solver vectors x %.0f MB + inputs, larger than the 126 MB L2; no flush needed" % (12.0 * a.size * a.size / 1e6)}
 
 
 def main():
