@@ -124,3 +124,39 @@ def test_reference_minimal_links_statically_against_libthallo_a(tmp_path):
                         "-lnvrtc", "-lcudart", "-ldl", "-lrt", "-lpthread"], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stderr[-3000:]
     assert "libThallo" not in subprocess.run(["ldd", str(out)], capture_output=True, text=True).stdout
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference checkout not present (GPU box)")
+def test_struct_layouts_equal_the_reference_header(tmp_path):
+    """Thallo_NewState takes its parameters BY VALUE and Thallo_GetPerformanceSummary fills a caller-owned struct: sizes
+    and field offsets of include/Thallo.h must equal those of the reference's API/release/include/Thallo.h."""
+    probe = tmp_path / "probe.c"
+    probe.write_text(r'''
+#include <stdio.h>
+#include <stddef.h>
+#include HEADER
+int main(void) {
+    printf("init %zu %zu %zu %zu %zu %zu %zu\n", sizeof(Thallo_InitializationParameters),
+           offsetof(Thallo_InitializationParameters, doublePrecision), offsetof(Thallo_InitializationParameters, verbosityLevel),
+           offsetof(Thallo_InitializationParameters, timingLevel), offsetof(Thallo_InitializationParameters, threadsPerBlock),
+           offsetof(Thallo_InitializationParameters, useAutoscheduler), offsetof(Thallo_InitializationParameters, cpuOnly));
+    printf("entry %zu %zu %zu %zu %zu %zu\n", sizeof(Thallo_PerformanceEntry), offsetof(Thallo_PerformanceEntry, count),
+           offsetof(Thallo_PerformanceEntry, minMS), offsetof(Thallo_PerformanceEntry, maxMS),
+           offsetof(Thallo_PerformanceEntry, meanMS), offsetof(Thallo_PerformanceEntry, stddevMS));
+    printf("summary %zu %zu %zu %zu %zu %zu\n", sizeof(Thallo_PerformanceSummary), offsetof(Thallo_PerformanceSummary, total),
+           offsetof(Thallo_PerformanceSummary, nonlinearIteration), offsetof(Thallo_PerformanceSummary, nonlinearSetup),
+           offsetof(Thallo_PerformanceSummary, linearSolve), offsetof(Thallo_PerformanceSummary, nonlinearResolve));
+    return 0;
+}
+''')
+    outs = []
+    for tag, header in (("ours", os.path.join(ROOT, "include", "Thallo.h")), ("ref", os.path.join(REF, "API", "release", "include", "Thallo.h"))):
+        exe = tmp_path / ("probe_" + tag)
+        subprocess.check_call(["gcc", "-w", "-DHEADER=\"%s\"" % header, str(probe), "-o", str(exe)])
+        outs.append(subprocess.run([str(exe)], capture_output=True, text=True).stdout)
+    assert outs[0] == outs[1] and outs[0].startswith("init 24 0 4 8 12 16 20")
+    # and the ctypes mirror used by the Python host side agrees with both
+    import ctypes as C
+    from thallo_b200 import api
+    assert C.sizeof(api.InitializationParameters) == 24
+    assert ("summary %d" % C.sizeof(api.PerformanceSummary)) in outs[0] and ("entry %d" % C.sizeof(api.PerformanceEntry)) in outs[0]
