@@ -356,3 +356,8 @@ def test_type_and_tostring_of_host_values():
         return type(nil), type(true), type(1.5), type("s"), type({}), type(f), type(print), type(obj), tostring(3.0), tostring(nil)
     """, obj=object())
     assert r == ["nil", "boolean", "number", "string", "table", "function", "function", "userdata", "3", "nil"]
+
+
+def test_string_methods():
+    r, _, _ = run("""local s = "ab"; return s:rep(3), ("%d/%s"):format(7, "x"), s:upper(), s:len()""")
+    assert r == ["ababab", "7/x", "AB", 2]

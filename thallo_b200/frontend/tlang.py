@@ -601,6 +601,11 @@ class Interpreter:
             if isinstance(obj, LuaTable):
                 f = obj.get(e[2])
                 args = [obj] + args
+            elif isinstance(obj, str):                      # s:format(...), s:rep(n): methods of the string library
+                f = self.G["string"].get(e[2]) if isinstance(self.G.get("string"), LuaTable) else None
+                if f is None:
+                    self.error("string has no method '%s'" % e[2])
+                args = [obj] + args
             else:
                 if obj is None:
                     self.error("attempt to call method '%s' of a nil value" % e[2])
