@@ -3,7 +3,8 @@
 Solves the same global arap_mesh_deformation problem (a) vertex-partitioned over all ranks (ghost vertices
 over NVLink peer stores, PCG scalars over NCCL) and (b) on one GPU, and compares every cost of the
 trajectory, the LM inner iteration counts and the unknowns.  Exit code 0 = parity.
-Called by tests/test_gpu_multi.py.  `--bench N` instead times an N x N mesh (PCG iterations / s)."""
+Called by tests/test_gpu_multi.py.  `--bench N` instead times an N x (N * world) mesh (PCG iterations / s);
+`--bench-ba C P` bundle adjustment with C cameras and P points per GPU."""
 import os
 import sys
 
@@ -136,6 +137,40 @@ def bench(n, dist, rank, world, torch):
     return True
 
 
+def bench_ba(cameras, points_per_rank, dist, rank, world, torch):
+    """Weak scaling of bundle adjustment: `points_per_rank` points (x 5 observations) per GPU, all cameras replicated.
+    (Added after the GPU budget of round 1 was spent; not yet run.)"""
+    from thallo_b200 import workloads as wl
+    from thallo_b200.distributed import ReplicatedSolver
+    P_ = points_per_rank * world
+    d = wl.bundle_adjustment_inputs(cameras, P_, 5)
+    O_ = len(d["oToC"])
+    s = ReplicatedSolver([cameras, P_, O_], "bundle_adjustment", "levenberg_marquardt", rank, world, d["oToP"])
+    host = [np.ascontiguousarray(d["cameras"]), s.point_rows(d["points"]), s.observation_rows(d["observations"]),
+            s.observation_rows(d["oToC"]), s.point_index(d["oToP"])]
+    nit, lit = 2, 50
+    s.set_parameters(nIterations=nit, lIterations=lit)
+    ms, iters = [], 0
+    for rep in range(4):
+        dev = [torch.from_numpy(a.copy()).cuda() for a in host]
+        torch.cuda.synchronize(); dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        before = s.total_linear_iterations()
+        e0.record()
+        s.solve(dev)
+        e1.record(); torch.cuda.synchronize()
+        ms.append(e0.elapsed_time(e1))
+        iters = s.total_linear_iterations() - before
+    t = torch.tensor([min(ms[1:])], dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        import json
+        print(json.dumps({"workload": "bundle_adjustment %d cameras, %d points per GPU" % (cameras, points_per_rank), "n_gpus": world,
+                          "pcg_iterations_per_solve": iters, "ms_per_solve": float(t[0]),
+                          "pcg_iterations_per_s": iters / (float(t[0]) * 1e-3), "final_cost": s.current_cost()}), flush=True)
+    return True
+
+
 def main():
     import torch
     import torch.distributed as dist
@@ -145,6 +180,8 @@ def main():
     ok = True
     if len(sys.argv) > 2 and sys.argv[1] == "--bench":
         bench(int(sys.argv[2]), dist, rank, world, torch)
+    elif len(sys.argv) > 3 and sys.argv[1] == "--bench-ba":
+        bench_ba(int(sys.argv[2]), int(sys.argv[3]), dist, rank, world, torch)
     else:
         for kind, nx, ny, nit, lit in [("gauss_newton", 40, 36, 3, 25), ("levenberg_marquardt", 48, 50, 4, 30)]:
             ok = run(kind, nx, ny, nit, lit, dist, rank, world, torch) and ok
