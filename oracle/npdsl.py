@@ -20,8 +20,9 @@ Reference semantics restated here:
 Pinned (parity pinned): with oracle/solver.py on the reference's two golden images (tests/test_oracle_golden.py),
 and -- cost, -J^T F and J^T J p of image_warping, arap_mesh_deformation and volumetric_mesh_deformation -- on the
 reference authors' hand-derived CUDA equations compiled for the host from the reference tree
-(oracle/*_hand_host.cpp, tests/test_oracle_hand_equations.py).  Energies with neither (optical_flow,
-shape_from_shading, bundle_adjustment) are checked only against the product's independent symbolic AD.
+(oracle/*_hand_host.cpp, tests/test_oracle_hand_equations.py), as is the stored shading term of shape_from_shading
+with its gradient image.  optical_flow and bundle_adjustment have neither and are checked only against the product's
+independent symbolic AD.
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / reference arm may import this.
 """
 import numpy as np

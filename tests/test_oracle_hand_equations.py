@@ -169,3 +169,53 @@ def test_oracle_matches_the_reference_hand_derived_volumetric_equations(dims, se
     o = J.T @ (J @ pv.astype(np.float64))
     assert np.abs(out.reshape(-1) - 2 * o[:3 * N]).max() <= 3e-6 * np.abs(o).max()
     assert np.abs(outA.reshape(-1) - 2 * o[3 * N:]).max() <= 3e-6 * np.abs(o).max()
+
+
+@pytest.mark.parametrize("W,H,seed", [(36, 28, 4), (17, 40, 6)])
+def test_oracle_shading_term_and_its_gradient_match_the_reference_hand_derived_helper(W, H, seed):
+    """shape_from_shading: the per-pixel shading error B - I (normal from three depth samples, nine spherical-harmonics
+    lighting coefficients) and its derivatives with respect to those samples, hand-derived in
+    examples/shape_from_shading/src/SFSSolverUtil.h:59-195, against the value and gradient image of the ComputedArray
+    `B_I_comp` the oracle derives from the energy by dual-number AD (captured at its first :get)."""
+    from oracle import npdsl
+    lib_path = os.path.join(ROOT, "oracle", "_ref", "libsfs_hand.so")
+    if os.path.isdir("/root/reference"):
+        import subprocess
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "hand"], stdout=subprocess.DEVNULL)
+    if not os.path.exists(lib_path):
+        pytest.skip("oracle/_ref/libsfs_hand.so not built (needs the reference checkout)")
+    lib = C.CDLL(lib_path)
+    fp = C.POINTER(C.c_float)
+    lib.sfs_hand_shading.argtypes = [C.c_int, C.c_int, fp, fp, fp, C.c_float, C.c_float, C.c_float, C.c_float, fp]
+    d = wl.sfs_inputs(W, H)
+    rs = np.random.RandomState(seed)
+    depth = (0.5 + 0.05 * rs.rand(H, W)).astype(np.float32)       # every depth valid and positive: the hand code tests the refined
+    d["X"] = depth.reshape(-1).copy()                              # depth for validity, the energy the input depth
+    d["D_i"] = depth.reshape(-1).copy()
+    p64 = [np.asarray(p, np.float64) if np.asarray(p).dtype == np.float32 else p for p in wl.sfs_params(d)]
+    captured = []
+    orig = npdsl.Dual.get
+
+    def spy(self, *idx):
+        captured.append(self)
+        return orig(self, *idx)
+    npdsl.Dual.get = spy
+    try:
+        npdsl.evaluate(energies.load("shape_from_shading"), [W, H], p64, np.float64)
+    finally:
+        npdsl.Dual.get = orig
+    bi = captured[0]                                               # B_I_comp, shape_from_shading.t:79
+    assert sorted(k[1][1] for k in bi.d) == [(-1, 0), (0, -1), (0, 0)]
+    out = np.zeros((H, W, 4), np.float32)
+    X, Im = np.ascontiguousarray(d["X"], np.float32), np.ascontiguousarray(d["Im"], np.float32)
+    light = np.ascontiguousarray(np.array(d["light"], np.float32))
+    ptr = lambda a: a.ctypes.data_as(fp)
+    lib.sfs_hand_shading(W, H, ptr(X), ptr(Im), ptr(light), d["f_x"], d["f_y"], d["u_x"], d["u_y"], ptr(out))
+    inner = (slice(1, H), slice(1, W))
+    val = np.asarray(bi.val).reshape(H, W)
+    assert np.abs(out[..., 3][inner] - val[inner]).max() <= 3e-6 * np.abs(val[inner]).max()
+    channel = {(-1, 0): 0, (0, 0): 1, (0, -1): 2}                  # the helper's d0 = X(x-1, y), d1 = X(x, y), d2 = X(x, y-1)
+    for key, dv in bi.d.items():
+        dv = np.broadcast_to(np.asarray(dv), (H, W))
+        got = out[..., channel[tuple(key[1][1])]]
+        assert np.abs(got[inner] - dv[inner]).max() <= 3e-6 * np.abs(dv[inner]).max()
