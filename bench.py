@@ -212,12 +212,14 @@ def main():
 
     def step_resident(s):
         work[0].copy_(pristine[0]); work[1].copy_(pristine[1])       # reset the unknowns (device to device, timed)
-        return s.solve(work + scal)
+        # ... and the trust-region radius, which a solve leaves behind in the solver parameters like the reference does
+        # (gauss_newton.t:1751): every step is then the same solve, with the same PCG iteration counts
+        return s.solve(work + scal, trust_region_radius=1e4)
 
     def step_e2e(s):
         for w, h in zip(work, host):
             w.copy_(h, non_blocking=True)                           # every input from pinned host memory
-        c = s.solve(work + scal)
+        c = s.solve(work + scal, trust_region_radius=1e4)
         out_host[0].copy_(work[0], non_blocking=True); out_host[1].copy_(work[1], non_blocking=True)
         torch.cuda.synchronize()
         return c

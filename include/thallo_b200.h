@@ -85,6 +85,21 @@ int ThalloB200_PlanConnect(Thallo_State* state, Thallo_Plan* plan, const void* h
 int ThalloB200_PlanConnectGraph(Thallo_State* state, Thallo_Plan* plan, const void* handle_lo, long long extent_lo,
                                 long long width_lo, const void* handle_hi, long long extent_hi, long long width_hi);
 
+/* ---- multi-GPU: all-to-all peer mapping (replaces ThalloB200_PlanConnect / ThalloB200_PlanConnectGraph).
+ * Every rank maps EVERY other rank's solver-vector block.  After this call the PCG iteration of a partitioned plan
+ * issues no collective and no helper kernel: the kernel that produces a dot product all-reduces it itself -- its last
+ * CTA stores the rank's partial sums into a mailbox in every peer's memory over NVLink, waits for the peers' values
+ * in its own mailbox and adds them up in rank order (bit-identical on all ranks) -- and the kernel that computes z
+ * stores its boundary layers straight into the neighbours' ghost layers, ordered before its mailbox flag.  NCCL
+ * remains for the once-per-nonlinear-iteration scalars (cost, model cost) and for vector all-reduces (the replicated
+ * camera block of bundle adjustment).  THALLO_B200_MG_NCCL=1 keeps the NCCL sequence for comparison.
+ *   ThalloB200_PlanPeerInfo     info4 = {local extent of the partitioned axis, bytes between consecutive solver
+ *                               vectors, ghost_lo, ghost_hi} of this rank's plan
+ *   ThalloB200_PlanConnectAll   handles64 = world x 64-byte IPC handles (ThalloB200_PlanIpcHandle) in rank order,
+ *                               infos4 = world x 4 values of ThalloB200_PlanPeerInfo; call after ThalloB200_PlanInitComm */
+int ThalloB200_PlanPeerInfo(Thallo_State* state, Thallo_Plan* plan, long long* info4);
+int ThalloB200_PlanConnectAll(Thallo_State* state, Thallo_Plan* plan, int world, const void* handles64, const long long* infos4);
+
 /* Known-answer tests of the warp primitives behind the residualwise scatter path (ballot, peer
  * discovery by key, by-key reduction before the atomic), written after the reference's
  * tests/cuda_unit_tests/{ballot,get_peers,reduce_peers}.t; one warp each on the current device.

@@ -120,6 +120,36 @@ def more_cases(dist, rank, world, torch):
     return ok
 
 
+def determinism(dist, rank, world, torch, repeats=4):
+    """The same LM solve repeated: every cost, every PCG iteration count and the unknowns must come out bit-identical
+    (dot products are summed in a fixed order, also across ranks: rank-ordered sums of the mailbox values)."""
+    from thallo_b200 import workloads as wl
+    from thallo_b200.distributed import SlabSolver
+    W, H, kind = 128, 96, "levenberg_marquardt"
+    d = wl.image_warping_inputs(W, H)
+    names = ("Offset", "Angle", "UrShape", "Constraints", "Mask")
+    scal = [np.array([d["w_fitSqrt"]], np.float32), np.array([d["w_regSqrt"]], np.float32)]
+    s = SlabSolver([W, H], "image_warping", kind, rank, world)
+    runs = []
+    for _ in range(repeats):
+        loc = [torch.from_numpy(s.slab(d[k])).cuda() for k in names]
+        s.set_parameters(nIterations=4, lIterations=40, trust_region_radius=1e4)     # the radius persists across solves (gauss_newton.t:1751)
+        s.init(loc + scal)
+        costs, lin = [s.current_cost()], []
+        while s.step():
+            costs.append(s.current_cost())
+            lin.append(s.last_linear_iterations())
+        torch.cuda.synchronize()
+        runs.append((costs, lin, loc[0].cpu().numpy().tobytes(), loc[1].cpu().numpy().tobytes()))
+    same = all(r == runs[0] for r in runs[1:])
+    flags = [None] * world
+    dist.all_gather_object(flags, same)
+    ok = all(flags)
+    if rank == 0:
+        print("mgpu determinism world=%d: %d repeated LM solves %s (lin %s)" % (world, repeats, "deterministic" if ok else "DIFFER", runs[0][1]), flush=True)
+    return ok
+
+
 def main():
     import torch
     import torch.distributed as dist
@@ -130,6 +160,7 @@ def main():
     for kind, W, H, nit, lit in [("gauss_newton", 96, 64, 3, 20), ("levenberg_marquardt", 128, 90, 5, 40)]:
         ok = run(kind, W, H, nit, lit, dist, rank, world, torch) and ok
     ok = more_cases(dist, rank, world, torch) and ok
+    ok = determinism(dist, rank, world, torch) and ok
     flag = [ok]
     dist.broadcast_object_list(flag, src=0)
     dist.destroy_process_group()

@@ -87,6 +87,9 @@ def lib():
     L.ThalloB200_PlanConnect.argtypes = [vp, vp, vp, C.c_longlong, vp, C.c_longlong]
     L.ThalloB200_PlanConnectGraph.restype = C.c_int
     L.ThalloB200_PlanConnectGraph.argtypes = [vp, vp, vp, C.c_longlong, C.c_longlong, vp, C.c_longlong, C.c_longlong]
+    L.ThalloB200_PlanPeerInfo.restype, L.ThalloB200_PlanPeerInfo.argtypes = C.c_int, [vp, vp, C.POINTER(C.c_longlong)]
+    L.ThalloB200_PlanConnectAll.restype = C.c_int
+    L.ThalloB200_PlanConnectAll.argtypes = [vp, vp, C.c_int, vp, C.POINTER(C.c_longlong)]
     L.ThalloB200_WarpSelfTest.restype = C.c_int
     L.ThalloB200_WarpSelfTest.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_double), C.c_int]
     L.ThalloB200_LastError.restype, L.ThalloB200_LastError.argtypes = cp, []

@@ -187,7 +187,11 @@ template <int K> __device__ __forceinline__ bool th_grid_reduce(double (&val)[K]
         }
     }
     if (tid == 0) {
+#if TH_MULTI
+        __threadfence_system();      // this CTA's stores into peer memory (ThPush) precede the mailbox flag of the last CTA
+#else
         __threadfence();
+#endif
         const unsigned int t = atomicAdd(ticket, 1u);
         last = (t == nblocks - 1);
     }
@@ -209,6 +213,78 @@ template <int K> __device__ __forceinline__ bool th_grid_reduce(double (&val)[K]
     if (tid == 0) *ticket = 0u;
     return true;
 }
+
+// ------------------------------------------------------------------ multi-GPU: peer stores and the in-kernel all-reduce
+#if TH_MULTI
+__device__ __forceinline__ unsigned long long th_ld_acquire_sys(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void th_st_release_sys(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long th_globaltimer() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ ThMail* th_mail(ThMail* base, int kind, int parity, int src) {
+    return base + (kind * 2 + parity) * TH_MAXRANKS + src;
+}
+// Sum K (<= 2) doubles over all ranks.  Called by every thread of warp 0 of ONE CTA per rank (the last CTA of the
+// grid reduction) with this rank's partial sums in v[]; returns the totals in v[] (all lanes), added in rank order so
+// that every rank holds the same bits.  Lane r serves peer r: values, system fence, flag (release) into the peer's
+// mailbox; then it polls this rank's own mailbox entry of rank r (acquire).  `seq` is unique per use of the
+// (kind, parity) slot and identical on all ranks.  A peer that never answers (crashed process) traps after 20 s
+// instead of hanging the GPU.
+template <int K> __device__ __forceinline__ void th_mail_allreduce(const ThPeers& R, int kind, unsigned long long seq, double (&v)[K]) {
+    const int lane = (int)((threadIdx.x + blockDim.x * (threadIdx.y + blockDim.y * threadIdx.z)) & 31u);
+    const int par = (int)(seq & 1ull);
+    double got[2] = {0.0, 0.0};
+    if (lane < R.world) {
+        ThMail* out = th_mail(R.box[lane], kind, par, R.rank);
+#pragma unroll
+        for (int k = 0; k < K; ++k) *(volatile double*)&out->v[k] = v[k];
+        __threadfence_system();
+        th_st_release_sys(&out->seq, seq);
+        ThMail* in = th_mail(R.box[R.rank], kind, par, lane);
+        const unsigned long long t0 = th_globaltimer();
+        while (th_ld_acquire_sys(&in->seq) != seq) {
+            if (th_globaltimer() - t0 > 20000000000ull) {
+                printf("thallo_b200: rank %d waited 20 s for rank %d (mailbox kind %d, seq %llu): peer lost\n", R.rank, lane, kind, seq);
+                __trap();
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < K; ++k) got[k] = *(volatile double*)&in->v[k];
+    }
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        double tot = 0.0;
+        for (int r = 0; r < R.world; ++r) tot += __shfl_sync(0xffffffffu, got[k], r);
+        v[k] = tot;
+    }
+}
+// forward a scalar / a real4 chunk just written at flat index f / chunk i of the pushed vector to the neighbours
+__device__ __forceinline__ void th_push_scalar(const ThPush& H, long long f, real val) {
+#pragma unroll
+    for (int s = 0; s < 2 * TH_NUM_UIMG; ++s)
+        if (s < H.n && f >= H.lo[s] && f < H.hi[s]) H.dst[s][f - H.lo[s]] = val;
+}
+__device__ __forceinline__ void th_push_vec4(const ThPush& H, long long i, const real4& val) {
+#pragma unroll
+    for (int s = 0; s < 2 * TH_NUM_UIMG; ++s) {
+        if (s >= H.n || 4 * i + 3 < H.lo[s] || 4 * i >= H.hi[s]) continue;
+        if (H.vec4[s]) ((real4*)H.dst[s])[i - H.lo[s] / 4] = val;
+        else {
+            th_push_scalar(H, 4 * i, val.x); th_push_scalar(H, 4 * i + 1, val.y);
+            th_push_scalar(H, 4 * i + 2, val.z); th_push_scalar(H, 4 * i + 3, val.w);
+            return;
+        }
+    }
+}
+#endif
 
 __device__ __forceinline__ real th_guarded_invert(real d) {     // GuardedInvertType.CERES, gauss_newton.t:641-648
     const real s = (real)1 + th_sqrt(d);
@@ -246,7 +322,7 @@ __device__ __forceinline__ real th_beta_prev(const ThScalars* S) {
 // Shared tail of both PCGInit forms: given the gradient entry g (=J^T F) and the true
 // diagonal d (=diag J^T J) of one unknown scalar, produce r, preconditioner, p (and in LM
 // CtC, b, SSq) and return r*p.
-__device__ __forceinline__ real th_init_scalar(const Params& P, const Vecs& V, long long off, real g, real d,
+__device__ __forceinline__ real th_init_scalar(const Params& P, const Vecs& V, const ThPush& H, long long off, real g, real d,
                                                real pre_if_off, int first_nonlinear) {
     const real r = -g;
     real pre = TH_USEPRE ? th_guarded_invert(d) : pre_if_off;
@@ -270,9 +346,15 @@ __device__ __forceinline__ real th_init_scalar(const Params& P, const Vecs& V, l
 #else
     V.p[off] = p;
 #endif
+#if TH_MULTI
+    th_push_scalar(H, off, p);      // boundary elements: also into the neighbours' ghost copies
+#endif
     return r * p;
 }
-__device__ __forceinline__ void th_zero_scalar(const Vecs& V, long long off) {
+__device__ __forceinline__ void th_zero_scalar(const Vecs& V, const ThPush& H, long long off) {
+#if TH_MULTI
+    th_push_scalar(H, off, (real)0);
+#endif
     V.delta[off] = (real)0; V.r[off] = (real)0; V.pre[off] = (real)0; V.p[off] = (real)0;
     V.z[off] = (real)0; V.Ap[off] = (real)0;
 #if TH_TILED
@@ -281,6 +363,10 @@ __device__ __forceinline__ void th_zero_scalar(const Vecs& V, long long off) {
 #if TH_LM
     V.CtC[off] = (real)0; V.b[off] = (real)0; V.Adelta[off] = (real)0;
 #endif
+}
+// sequence number of a mailbox use: (epoch of the nonlinear step, PCG iteration + 1); identical on all ranks
+__device__ __forceinline__ unsigned long long th_seq(int epoch, int it1) {
+    return ((unsigned long long)(unsigned int)epoch << 32) | (unsigned long long)(unsigned int)it1;
 }
 __device__ __forceinline__ void th_begin_linear(ThScalars* S, double rz0) {
     S->rz[0] = rz0; S->rz[1] = 0.0; S->aD = 0.0; S->q = 0.0; S->Q0 = 0.0;

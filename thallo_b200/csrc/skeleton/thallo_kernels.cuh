@@ -60,13 +60,47 @@ __device__ __forceinline__ bool th_flat_counted(long long f) {
 #endif
 }
 
+// linear thread id within the block (blocks are 1-D, 2-D or 3-D)
+__device__ __forceinline__ int th_tid() { return (int)(threadIdx.x + blockDim.x * (threadIdx.y + blockDim.y * threadIdx.z)); }
+
+// End of PCGInit in the last block: <r, p> (all ranks' parts) opens the linear solve.  Non-fused multi-GPU plans
+// publish the rank's part; the host all-reduces S->rz[0] over NCCL.
+__device__ __forceinline__ void th_init_publish(ThScalars* S, double (&tot)[1], const ThPeers& R) {
+#if TH_MULTI
+    if (R.fused && th_tid() < 32) th_mail_allreduce<1>(R, TH_MAIL_INIT, th_seq(R.epoch, 1), tot);
+#endif
+    if (th_tid() == 0) th_begin_linear(S, tot[0]);
+}
+// <p, Ap> at the end of the operator kernels, same scheme (sequence number = PCG iteration + 1)
+__device__ __forceinline__ void th_ad_publish(ThScalars* S, double (&tot)[1], const ThPeers& R, bool accumulate, bool reduce_now) {
+    if (th_tid() >= 32) return;
+    if (accumulate) tot[0] += S->aD;
+    __syncwarp();
+#if TH_MULTI
+    if (R.fused && reduce_now) th_mail_allreduce<1>(R, TH_MAIL_A, th_seq(R.epoch, S->it + 1), tot);
+#endif
+    if (th_tid() == 0) S->aD = tot[0];
+}
+
 // ================================================================== at-output (unknownwise) kernels
 #if TH_AT_OUTPUT
 extern "C" __global__ void __launch_bounds__(TH_BLOCK)
-th_init_uw(const __grid_constant__ Params P, const __grid_constant__ Vecs V, ThScalars* S, double* partials, int first_nonlinear) {
+th_init_uw(const __grid_constant__ Params P, const __grid_constant__ Vecs V, ThScalars* S, double* partials, int first_nonlinear,
+           const __grid_constant__ ThPeers R, const __grid_constant__ ThPush H) {
     ThIdx<th::dom_uw> idx;
     double acc[1] = {0.0};
-    if (th_uw_index(idx) && th_owned_slow(idx.c[th::dom_uw::ND - 1])) {     // ghost layers are the neighbours' to initialise
+    const bool inside = th_uw_index(idx);
+#if TH_MULTI
+    if (inside && !th_owned_slow(idx.c[th::dom_uw::ND - 1])) {
+        // ghost layers: r, z, the preconditioner are the neighbours' to initialise (z arrives by their pushes); delta
+        // is kept current locally (delta += alpha p with the ghost copy of p, th_pcg_b), so it restarts from zero here
+#pragma unroll
+        for (int k = 0; k < TH_NUM_UIMG; ++k)
+#pragma unroll
+            for (int ch = 0; ch < TH_UIMG[k].channels; ++ch) V.delta[TH_UIMG[k].offset + idx.lin * TH_UIMG[k].channels + ch] = (real)0;
+    }
+#endif
+    if (inside && th_owned_slow(idx.c[th::dom_uw::ND - 1])) {
         GAcc<th::dom_uw> a(idx, nullptr);
         const bool ex = th::exclude_u0(a, P);
         real g[TH_U], d[TH_U];
@@ -78,16 +112,14 @@ th_init_uw(const __grid_constant__ Params P, const __grid_constant__ Vecs V, ThS
 #pragma unroll
             for (int ch = 0; ch < TH_UIMG[k].channels; ++ch, ++j) {
                 const long long off = TH_UIMG[k].offset + idx.lin * TH_UIMG[k].channels + ch;
-                if (ex) th_zero_scalar(V, off);
-                else dot += th_init_scalar(P, V, off, g[j], d[j], (real)0.25, first_nonlinear);   // d:=1 -> G(1)=0.25, gauss_newton.t:693-696
+                if (ex) th_zero_scalar(V, H, off);
+                else dot += th_init_scalar(P, V, H, off, g[j], d[j], (real)0.25, first_nonlinear);   // d:=1 -> G(1)=0.25, gauss_newton.t:693-696
             }
         }
         acc[0] = (double)dot;
     }
     double tot[1];
-    if (th_grid_reduce<1>(acc, tot, partials, &S->ticket[0])) {
-        if (threadIdx.x + threadIdx.y + threadIdx.z == 0) th_begin_linear(S, tot[0]);
-    }
+    if (th_grid_reduce<1>(acc, tot, partials, &S->ticket[0])) th_init_publish(S, tot, R);
 }
 
 // which = 0: Ap = (JtJ [+CtC]) p with alphaDenominator = <p,Ap>;  which = 1: Adelta = (JtJ [+CtC]) delta
@@ -167,8 +199,7 @@ __device__ __forceinline__ void th_close_iteration(ThScalars* S, real q_toleranc
         // progress >= n also sees every exit taken at an iteration <= n (all ranks of a multi-GPU
         // solve must stop issuing iterations at the same point)
         if (S->done) {
-            *(volatile int*)&hf->done_at = it + 1;
-            *(volatile int*)&hf->done_epoch = epoch;
+            *(volatile long long*)&hf->exit_word = ((long long)epoch << 32) | (long long)(it + 1);
             __threadfence_system();
         }
         *(volatile long long*)&hf->progress = ((long long)epoch << 32) | (long long)(it + 1);
@@ -201,15 +232,25 @@ __device__ __forceinline__ void th_for_owned(long long lo, long long hi, FV&& fv
     }
 // End of step 2 in the last block: publish the two sums.  Multi-GPU plans publish this rank's
 // partial sums instead; the host all-reduces them over NCCL and th_mg_close finishes the iteration.
-__device__ __forceinline__ void th_step2_publish(ThScalars* S, const double (&tot)[2], real q_tolerance, ThHostFlags* hf, int epoch) {
+// Called by every thread of the last block.  Fused multi-GPU plans all-reduce the two sums right here over the
+// peers' mailboxes (the z boundary layers this rank pushed are ordered before its flag, so a rank that has the
+// totals also has its ghost copies of z) and close the iteration like the tiled single-GPU schedule does.
+__device__ __forceinline__ void th_step2_publish(ThScalars* S, double (&tot)[2], real q_tolerance, ThHostFlags* hf, int epoch,
+                                                 const ThPeers& R) {
+    if (th_tid() >= 32) return;
 #if TH_MULTI
-    S->red[0] = tot[0]; S->red[1] = tot[1];
-#else
-    S->rz[(S->it + 1) & 1] = tot[0]; S->q = tot[1];
-#if TH_TILED
-    th_close_iteration(S, q_tolerance, hf, epoch);
+    if (!R.fused) {
+        if (th_tid() == 0) { S->red[0] = tot[0]; S->red[1] = tot[1]; }
+        return;
+    }
+    th_mail_allreduce<2>(R, TH_MAIL_B, th_seq(epoch, S->it + 1), tot);
 #endif
+    if (th_tid() == 0) {
+        S->rz[(S->it + 1) & 1] = tot[0]; S->q = tot[1];
+#if TH_TILED || TH_MULTI
+        th_close_iteration(S, q_tolerance, hf, epoch);
 #endif
+    }
 }
 #if TH_MULTI
 extern "C" __global__ void th_mg_close(ThScalars* S, real q_tolerance, ThHostFlags* hf, int epoch) {
@@ -232,7 +273,8 @@ th_halo_push(const __grid_constant__ ThSegs G, int nseg, const ThScalars* S, int
 #endif
 
 extern "C" __global__ void __launch_bounds__(TH_BLOCK)
-th_pcg_b(const __grid_constant__ Vecs V, ThScalars* S, double* partials, real q_tolerance, ThHostFlags* hf, int epoch) {
+th_pcg_b(const __grid_constant__ Vecs V, ThScalars* S, double* partials, real q_tolerance, ThHostFlags* hf, int epoch,
+         const __grid_constant__ ThPeers R, const __grid_constant__ ThPush H) {
     if (S->done) return;
     const real alpha = th_alpha(S);
     const real* __restrict__ pp = th_pcur(V, S);
@@ -251,9 +293,22 @@ th_pcg_b(const __grid_constant__ Vecs V, ThScalars* S, double* partials, real q_
         const real rn = vr[i] - alpha * vap[i];
         const real zv = TH_USEPRE ? vpre[i] * rn : rn;
         vd[i] = dn; vr[i] = rn; vz[i] = zv;
+#if TH_MULTI
+        th_push_scalar(H, i, zv);
+#endif
         accr[0] += (double)(zv * rn);
         if (TH_LM) accr[1] += (double)((real)0.5 * (dn * (rn + vb[i])));
     };
+#if TH_MULTI
+    // ghost copies of delta: delta += alpha p with the locally maintained ghost copy of p (the same bits as the
+    // owner's), so A*delta, the model cost and the update never need an exchange of delta
+#pragma unroll
+    for (int k = 0; k < TH_NUM_UIMG; ++k) {
+        const long long ilo = TH_UIMG[k].offset, ihi = ilo + TH_UIMG[k].elements * TH_UIMG[k].channels;
+        for (long long i = ilo + gtid; i < th_range_lo(k); i += stride) vd[i] = vd[i] + alpha * pp[i];
+        for (long long i = th_range_hi(k) + gtid; i < ihi; i += stride) vd[i] = vd[i] + alpha * pp[i];
+    }
+#endif
 #pragma unroll
     for (int k = 0; k < TH_NRANGES; ++k) {          // owned flat ranges (one range = everything on a single GPU)
         const long long lo = th_range_lo(k), hi = th_range_hi(k);
@@ -270,6 +325,9 @@ th_pcg_b(const __grid_constant__ Vecs V, ThScalars* S, double* partials, real q_
             ((real4*)vd)[i] = dl;
             ((real4*)vr)[i] = r;
             ((real4*)vz)[i] = zz;
+#if TH_MULTI
+            th_push_vec4(H, i, zz);
+#endif
         }
         for (long long i = lo + gtid; i < (v0 * 4 < hi ? v0 * 4 : hi); i += stride) scalar(i);
         for (long long i = v1 * 4 + gtid; i < hi; i += stride) scalar(i);
@@ -277,9 +335,7 @@ th_pcg_b(const __grid_constant__ Vecs V, ThScalars* S, double* partials, real q_
         accr[0] = accr[1] = 0.0;
     }
     double tot[2];
-    if (th_grid_reduce<2>(acc, tot, partials, &S->ticket[2])) {
-        if (threadIdx.x == 0) th_step2_publish(S, tot, q_tolerance, hf, epoch);
-    }
+    if (th_grid_reduce<2>(acc, tot, partials, &S->ticket[2])) th_step2_publish(S, tot, q_tolerance, hf, epoch, R);
 }
 
 extern "C" __global__ void __launch_bounds__(TH_BLOCK)
@@ -288,9 +344,9 @@ th_step2_first(const __grid_constant__ Vecs V, ThScalars* S) {
     const real alpha = th_alpha(S);
     const real* __restrict__ pp = th_pcur(V, S);
     real* __restrict__ vd = V.delta;
-#pragma unroll
-    for (int k = 0; k < TH_NRANGES; ++k)
-        th_for_owned(th_range_lo(k), th_range_hi(k),
+    // (ghost copies of delta included: they are maintained locally, see th_pcg_b)
+    {
+        th_for_owned(0, TH_NUNK,
             [&](long long i) {
                 const real4 p = ((const real4*)pp)[i];
                 real4 d = ((const real4*)vd)[i];
@@ -298,11 +354,13 @@ th_step2_first(const __grid_constant__ Vecs V, ThScalars* S) {
                 ((real4*)vd)[i] = d;
             },
             [&](long long i) { vd[i] = vd[i] + alpha * pp[i]; });
+    }
 }
 
 // r = b - A delta; add_ctc: A delta still lacks the CtC*delta term (residualwise / materialized schedules)
 extern "C" __global__ void __launch_bounds__(TH_BLOCK)
-th_step2_second(const __grid_constant__ Vecs V, ThScalars* S, double* partials, int add_ctc, real q_tolerance, ThHostFlags* hf, int epoch) {
+th_step2_second(const __grid_constant__ Vecs V, ThScalars* S, double* partials, int add_ctc, real q_tolerance, ThHostFlags* hf, int epoch,
+                const __grid_constant__ ThPeers R, const __grid_constant__ ThPush H) {
     if (S->done) return;
     double acc[2] = {0.0, 0.0};
     const real* __restrict__ vdl = V.delta;
@@ -336,20 +394,24 @@ th_step2_second(const __grid_constant__ Vecs V, ThScalars* S, double* partials, 
                 lane(dl.w, ad.w, ct.w, bb.w, pr.w, r.w, z.w);
                 ((real4*)vr)[i] = r;
                 ((real4*)vz)[i] = z;
+#if TH_MULTI
+                th_push_vec4(H, i, z);
+#endif
             },
             [&](long long i) {
                 real r, z;
                 lane(vdl[i], vad[i], add_ctc ? vctc[i] : (real)0, vb[i], TH_USEPRE ? vpre[i] : (real)1, r, z);
                 vr[i] = r;
                 vz[i] = z;
+#if TH_MULTI
+                th_push_scalar(H, i, z);
+#endif
             });
         if (th_range_counted(k)) { acc[0] += accr[0]; acc[1] += accr[1]; }     // a replicated range counts on one rank only
         accr[0] = accr[1] = 0.0;
     }
     double tot[2];
-    if (th_grid_reduce<2>(acc, tot, partials, &S->ticket[2])) {
-        if (threadIdx.x == 0) th_step2_publish(S, tot, q_tolerance, hf, epoch);
-    }
+    if (th_grid_reduce<2>(acc, tot, partials, &S->ticket[2])) th_step2_publish(S, tot, q_tolerance, hf, epoch, R);
 }
 
 // PCGStep3 of the untiled schedules: beta = rz_new/rz_old; p = z + beta p; closes the iteration.
@@ -357,7 +419,7 @@ extern "C" __global__ void __launch_bounds__(TH_BLOCK)
 th_step3(const __grid_constant__ Vecs V, ThScalars* S, real q_tolerance, ThHostFlags* hf, int epoch) {
     if (S->done) return;
 #if TH_MULTI
-    const real beta = th_beta_prev(S);       // th_mg_close has already closed the iteration (after the all-reduce of <z,r>)
+    const real beta = th_beta_prev(S);       // th_pcg_b (fused) / th_mg_close has already closed the iteration (after the all-reduce of <z,r>)
 #else
     const real beta = th_beta(S);
 #endif
@@ -674,7 +736,8 @@ __device__ __forceinline__ real th_tile_apply(const unsigned char* sm, const Par
 }
 
 template <bool TMA>
-__device__ __forceinline__ void th_pcg_a_impl(const Params& P, const Vecs& V, const ThMaps& M, ThScalars* S, double* partials, int mode) {
+__device__ __forceinline__ void th_pcg_a_impl(const Params& P, const Vecs& V, const ThMaps& M, ThScalars* S, double* partials, int mode,
+                                              const ThPeers& R) {
     extern __shared__ __align__(128) unsigned char th_sm[];      // TMA: TH_PIPE stages of TH_SMEM_BYTES; otherwise one
     __shared__ __align__(8) unsigned long long full[TH_PIPE], empty[TH_PIPE];
     if (S->done) return;
@@ -741,17 +804,17 @@ __device__ __forceinline__ void th_pcg_a_impl(const Params& P, const Vecs& V, co
     }
     if (mode) return;
     double tot[1];
-    if (th_grid_reduce<1>(acc, tot, partials, &S->ticket[1])) {
-        if (tid == 0) S->aD = tot[0];
-    }
+    if (th_grid_reduce<1>(acc, tot, partials, &S->ticket[1])) th_ad_publish(S, tot, R, false, true);
 }
 extern "C" __global__ void __launch_bounds__(TH_TILE_THREADS, TH_PCG_A_MINB)
-th_pcg_a(const __grid_constant__ Params P, const __grid_constant__ Vecs V, const __grid_constant__ ThMaps M, ThScalars* S, double* partials, int mode) {
-    th_pcg_a_impl<true>(P, V, M, S, partials, mode);
+th_pcg_a(const __grid_constant__ Params P, const __grid_constant__ Vecs V, const __grid_constant__ ThMaps M, ThScalars* S, double* partials, int mode,
+         const __grid_constant__ ThPeers R) {
+    th_pcg_a_impl<true>(P, V, M, S, partials, mode, R);
 }
 extern "C" __global__ void __launch_bounds__(TH_TILE_THREADS, TH_PCG_A_MINB)
-th_pcg_a_ld(const __grid_constant__ Params P, const __grid_constant__ Vecs V, const __grid_constant__ ThMaps M, ThScalars* S, double* partials, int mode) {
-    th_pcg_a_impl<false>(P, V, M, S, partials, mode);
+th_pcg_a_ld(const __grid_constant__ Params P, const __grid_constant__ Vecs V, const __grid_constant__ ThMaps M, ThScalars* S, double* partials, int mode,
+            const __grid_constant__ ThPeers R) {
+    th_pcg_a_impl<false>(P, V, M, S, partials, mode, R);
 }
 #endif  // TH_TILED
 
@@ -810,18 +873,19 @@ th_copy_x(const __grid_constant__ Params P, real* buf, int dir) {
 // ================================================================== residualwise-schedule unknown passes
 // After the scatter kernels: V.r holds -J^T F, V.pre holds diag(J^T J) (raw).
 extern "C" __global__ void __launch_bounds__(TH_BLOCK)
-th_init_finish(const __grid_constant__ Params P, const __grid_constant__ Vecs V, ThScalars* S, double* partials, int first_nonlinear) {
+th_init_finish(const __grid_constant__ Params P, const __grid_constant__ Vecs V, ThScalars* S, double* partials, int first_nonlinear,
+               const __grid_constant__ ThPeers R, const __grid_constant__ ThPush H) {
     double acc[1] = {0.0};
     for (long long f = (long long)blockIdx.x * blockDim.x + threadIdx.x; f < TH_NUNK; f += (long long)gridDim.x * blockDim.x) {
-        if (!th_flat_owned(f)) continue;       // ghost entries (graph partition) are the owner's to initialise; p arrives by push
-        if (th_excluded(f, P)) { th_zero_scalar(V, f); continue; }
-        const real rp = th_init_scalar(P, V, f, -V.r[f], V.pre[f], (real)1, first_nonlinear);   // pre := 1 when off, gauss_newton.t:718-722
+        // ghost entries (graph partition) are the owner's to initialise, p arrives by its push; delta is maintained
+        // locally (th_pcg_b) and restarts from zero
+        if (!th_flat_owned(f)) { V.delta[f] = (real)0; continue; }
+        if (th_excluded(f, P)) { th_zero_scalar(V, H, f); continue; }
+        const real rp = th_init_scalar(P, V, H, f, -V.r[f], V.pre[f], (real)1, first_nonlinear);   // pre := 1 when off, gauss_newton.t:718-722
         if (th_flat_counted(f)) acc[0] += (double)rp;
     }
     double tot[1];
-    if (th_grid_reduce<1>(acc, tot, partials, &S->ticket[0])) {
-        if (threadIdx.x == 0) th_begin_linear(S, tot[0]);
-    }
+    if (th_grid_reduce<1>(acc, tot, partials, &S->ticket[0])) th_init_publish(S, tot, R);
 }
 
 // which = 0: finish Ap (LM: += CtC p) and alphaDenominator; which = 1: only mask Adelta
@@ -878,7 +942,8 @@ template <int LANES> __device__ __forceinline__ real th_lanes_sum_real(real v) {
 #define TH_GATHER_KERNEL(SP)                                                                                        \
     extern "C" __global__ void __launch_bounds__(TH_BLOCK)                                                          \
     th_gather_s##SP(const __grid_constant__ Params P, const __grid_constant__ Vecs V,                               \
-                    const __grid_constant__ ThGather G, ThScalars* S, double* partials, int which, int first) {     \
+                    const __grid_constant__ ThGather G, ThScalars* S, double* partials, int which, int first,       \
+                    int reduce_now, const __grid_constant__ ThPeers R) {                                            \
         if (S->done) return;                                                                                        \
         constexpr int LANES = TH_SPACE[SP].lanes;                                                                   \
         constexpr int NS = TH_SPACE[SP].nslots;                                                                     \
@@ -918,9 +983,7 @@ template <int LANES> __device__ __forceinline__ real th_lanes_sum_real(real v) {
         }                                                                                                           \
         if (which) return;                                                                                          \
         double tot[1];                                                                                              \
-        if (th_grid_reduce<1>(acc1, tot, partials, &S->ticket[1])) {                                                \
-            if (threadIdx.x == 0) S->aD = (first ? 0.0 : S->aD) + tot[0];                                           \
-        }                                                                                                           \
+        if (th_grid_reduce<1>(acc1, tot, partials, &S->ticket[1])) th_ad_publish(S, tot, R, !first, reduce_now != 0); \
     }
 TH_SPACE_LIST(TH_GATHER_KERNEL)
 
@@ -961,7 +1024,8 @@ TH_SPACE_LIST(TH_GATHERJTF_KERNEL)
 // partial sums in Ap / Adelta, NCCL summed them over the ranks; finish like the gather kernel does for
 // partitioned unknowns: + CtC p in LM and, on the one rank that counts them, their part of <p, Ap>.
 extern "C" __global__ void __launch_bounds__(TH_BLOCK)
-th_rep_finish(const __grid_constant__ Params P, const __grid_constant__ Vecs V, ThScalars* S, double* partials, int which) {
+th_rep_finish(const __grid_constant__ Params P, const __grid_constant__ Vecs V, ThScalars* S, double* partials, int which,
+              const __grid_constant__ ThPeers R) {
     if (S->done) return;
     const real* __restrict__ in = which ? V.delta : V.p;
     real* __restrict__ out = which ? V.Adelta : V.Ap;
@@ -981,9 +1045,7 @@ th_rep_finish(const __grid_constant__ Params P, const __grid_constant__ Vecs V, 
     }
     if (which) return;
     double tot[1];
-    if (th_grid_reduce<1>(acc1, tot, partials, &S->ticket[1])) {
-        if (threadIdx.x == 0) S->aD += tot[0];
-    }
+    if (th_grid_reduce<1>(acc1, tot, partials, &S->ticket[1])) th_ad_publish(S, tot, R, true, true);
 }
 #endif
 

@@ -74,14 +74,36 @@ struct ThScalars {
     int pad;
 };
 
-// Host-visible progress flags (pinned, mapped).
-struct ThHostFlags { long long progress; int done_epoch; int done_at; };
+// Host-visible progress flags (pinned, mapped): two 64-bit words, each (epoch << 32) | iteration, each
+// published with a single store -- `progress` = the iteration just closed, `exit_word` = the iteration at
+// which the LM early exit was taken (0 in the low half = not taken in this epoch).
+struct ThHostFlags { long long progress; long long exit_word; };
+
+// ---- multi-GPU peer memory (one process per GPU; every rank maps every other rank's solver-vector block with
+// CUDA IPC).  The PCG scalars are all-reduced INSIDE the kernel that produces them: the last CTA of the grid
+// reduction stores this rank's partial sums into a mailbox in every peer's memory over NVLink, then waits for
+// the peers' values in its own mailbox and adds them up in rank order (bit-identical totals on every rank).
+// Boundary layers of z / p are stored straight into the neighbours' ghost layers by the kernel that computes
+// them (ThPush), ordered before the mailbox flag by a system-scope fence.
+#define TH_MAXRANKS 16
+struct ThMail { double v[2]; unsigned long long seq; unsigned long long pad; };
+enum { TH_MAIL_A = 0, TH_MAIL_B = 1, TH_MAIL_INIT = 2, TH_MAIL_KINDS = 4 };
+#define TH_MAIL_BYTES (TH_MAIL_KINDS * 2 * TH_MAXRANKS * (int)sizeof(ThMail))
+struct ThPeers {
+    ThMail* box[TH_MAXRANKS];      // box[r]: rank r's mailbox array (a peer mapping; box[rank] is local memory)
+    int rank, world, fused, epoch; // fused = 0: the host all-reduces over NCCL instead (kept for A/B measurements);
+                                   // epoch = number of the nonlinear step (tags the mailbox sequence numbers)
+};
 
 struct ThUImg { int channels; long long offset; int ptr_slot; int ndim; int dim[TH_MAXD]; long long elements; };
 struct ThGroup { int ndim; int dim[TH_MAXD]; int nterms; int nnz; };
 __device__ constexpr ThUImg TH_UIMG[TH_NUM_UIMG] = TH_UIMG_TABLE;
 __device__ constexpr ThGroup TH_GROUPS[TH_NGROUPS] = TH_GROUP_TABLE;
 __device__ constexpr long long TH_DIMS[TH_NDIMS] = TH_DIM_SIZES;
+// Flat ranges [lo, hi) of a solver vector whose values the neighbours hold as ghosts: a value written at flat
+// index f in segment s is also stored to dst[s][f - lo[s]] (peer memory).  vec4[s]: lo, hi and dst are aligned
+// so that whole real4 chunks can be forwarded with one store.
+struct ThPush { long long lo[2 * TH_NUM_UIMG]; long long hi[2 * TH_NUM_UIMG]; real* dst[2 * TH_NUM_UIMG]; int vec4[2 * TH_NUM_UIMG]; int n; int pad; };
 
 // ---- gather schedule (graph domains / materialised Jacobians): per sparse endpoint the residual
 // elements incident to every unknown element, as CSR offsets + a permutation (nullptr when the

@@ -233,6 +233,15 @@ int ThalloB200_PlanConnectGraph(Thallo_State*, Thallo_Plan* plan, const void* ha
                                 const void* handle_hi, long long extent_hi, long long width_hi) {
     return plan ? plan->plan->connect_graph(handle_lo, extent_lo, width_lo, handle_hi, extent_hi, width_hi) : 1;
 }
+int ThalloB200_PlanPeerInfo(Thallo_State*, Thallo_Plan* plan, long long* info4) {
+    return plan && info4 ? plan->plan->peer_info(info4) : 1;
+}
+int ThalloB200_PlanConnectAll(Thallo_State*, Thallo_Plan* plan, int world, const void* handles64, const long long* infos4) {
+    if (!plan || !handles64 || !infos4) return 1;
+    const int rc = plan->plan->connect_all(world, handles64, infos4);
+    if (rc) set_error(plan->plan->error());
+    return rc;
+}
 int ThalloB200_WarpSelfTest(int which, int nkeys, double* out, int capacity) {
     if (!out || capacity <= 0 || which < 0 || which > 2) return -1;
     if (nkeys < 1 || nkeys > 32) nkeys = 4;

@@ -89,6 +89,10 @@ bool parse_descriptor(const std::string& text, PlanDesc& d, std::string& err) {
     return true;
 }
 
+static const int kNumVecs = 13;
+static const char* kVecNames[kNumVecs] = {"delta", "r", "b", "Adelta", "z", "p", "Ap_X", "CtC", "preconditioner", "SSq", "prevX", "initX", "p2"};
+enum { V_DELTA, V_R, V_B, V_ADELTA, V_Z, V_P, V_AP, V_CTC, V_PRE, V_SSQ, V_PREVX, V_INITX, V_P2 };
+
 // ------------------------------------------------------------------ NCCL (loaded at run time; only multi-GPU plans need it)
 struct NcclId { char internal[128]; };
 struct NcclApi {
@@ -182,14 +186,14 @@ void Plan::allreduce(size_t off, int count) {
 // memory over NVLink (CUDA IPC peer mappings).  Ordering: the push precedes this rank's next
 // all-reduce contribution in stream order, and a neighbour reads its ghost layers only after that
 // all-reduce has completed on its side.
-void Plan::halo_push(int vec, int check_done) {
+int Plan::segments(int vec, Seg* out) const {
     // slab: D layers of the slowest axis, h stencil-halo layers per side; graph: D local vertices, per side as many
     // vertices as the neighbour keeps ghosts of this rank's
+    if (!d_.multi || world_ == 1 || (d_.uw_dims.empty() && !d_.gmulti)) return 0;
     const int nd = (int)d_.uw_dims.size();
+    if (d_.gmulti && d_.part_dim < 0) return 0;       // no ghosted unknown domain (replicated / block-local unknowns only)
     const long long D = d_.gmulti ? d_.part_extent : d_.uw_dims[nd - 1];
     const long long hs[2] = {d_.gmulti ? peer_width_[0] : (long long)d_.halo[nd - 1], d_.gmulti ? peer_width_[1] : (long long)d_.halo[nd - 1]};
-    if ((hs[0] == 0 && hs[1] == 0) || world_ == 1) return;
-    struct Segs { const void* src[8]; void* dst[8]; long long count[8]; } g{};
     int n = 0;
     for (int side = 0; side < 2; ++side) {
         if (!peer_[side] || hs[side] == 0) continue;
@@ -202,30 +206,91 @@ void Plan::halo_push(int vec, int check_done) {
             const long long layer = (u.elements / D) * u.channels;           // scalars per slow-axis layer
             const long long src_row = side == 0 ? d_.ghost_lo : D - d_.ghost_hi - h;
             const long long dst_row = side == 0 ? E - h : 0;
-            g.src[n] = (const char*)vecs_[vec] + (size_t)(u.offset + src_row * layer) * real_size_;
-            g.dst[n] = peer_[side] + peer_stride * vec + (size_t)(peer_off + dst_row * layer) * real_size_;
-            g.count[n] = (long long)h * layer;
+            out[n].lo = u.offset + src_row * layer;
+            out[n].count = (long long)h * layer;
+            out[n].src = (const char*)vecs_[vec] + (size_t)out[n].lo * real_size_;
+            out[n].dst = peer_[side] + peer_stride * vec + (size_t)(peer_off + dst_row * layer) * real_size_;
             peer_off += (u.elements / D) * E * u.channels;
             ++n;
         }
     }
+    return n;
+}
+void Plan::halo_push(int vec, int check_done) {
+    Seg g[8];
+    if (d_.unknowns.size() > 4) { fprintf(stderr, "thallo_b200: more than 4 unknown images in a partitioned plan\n"); exit(1); }
+    int n = segments(vec, g);
     if (!n) return;
     // ThSegs: src[2*NU], dst[2*NU], count[2*NU]
     const size_t nu2 = 2 * d_.unknowns.size();
     std::vector<char> buf(nu2 * 24, 0);
     for (int i = 0; i < n; ++i) {
-        memcpy(buf.data() + 8 * i, &g.src[i], 8);
-        memcpy(buf.data() + 8 * (nu2 + i), &g.dst[i], 8);
-        memcpy(buf.data() + 8 * (2 * nu2 + i), &g.count[i], 8);
+        memcpy(buf.data() + 8 * i, &g[i].src, 8);
+        memcpy(buf.data() + 8 * (nu2 + i), &g[i].dst, 8);
+        memcpy(buf.data() + 8 * (2 * nu2 + i), &g[i].count, 8);
     }
     void* a[] = {buf.data(), &n, &d_scalars_, &check_done};
     launch(fn("th_halo_push"), dim3(32), dim3(256), a);
 }
+// ThPush image (skeleton/thallo_prelude.cuh): lo[2 NU], hi[2 NU], dst[2 NU], vec4[2 NU], n, pad
+void Plan::build_push(int vec, std::vector<char>& image) const {
+    const size_t nu2 = 2 * d_.unknowns.size();
+    image.assign(nu2 * 28 + 8, 0);
+    if (vec < 0 || !fused_) return;
+    Seg g[8];
+    const int n = segments(vec, g);
+    for (int i = 0; i < n; ++i) {
+        const long long hi = g[i].lo + g[i].count;
+        const int v4 = (g[i].lo % 4 == 0 && hi % 4 == 0 && (reinterpret_cast<uintptr_t>(g[i].dst) % (4 * real_size_)) == 0) ? 1 : 0;
+        memcpy(image.data() + 8 * i, &g[i].lo, 8);
+        memcpy(image.data() + 8 * (nu2 + i), &hi, 8);
+        memcpy(image.data() + 8 * (2 * nu2 + i), &g[i].dst, 8);
+        memcpy(image.data() + 24 * nu2 + 4 * i, &v4, 4);
+    }
+    memcpy(image.data() + 28 * nu2, &n, 4);
+}
+int Plan::peer_info(long long* info) {
+    info[0] = d_.gmulti ? d_.part_extent : (d_.uw_dims.empty() ? 0 : d_.uw_dims.back());
+    info[1] = (long long)vec_stride_;
+    info[2] = d_.ghost_lo;
+    info[3] = d_.ghost_hi;
+    return 0;
+}
+// Map every rank's solver-vector block (its tail holds the rank's mailboxes).  From then on the PCG scalars are
+// all-reduced inside the kernels that produce them and boundary layers are pushed by the kernels that compute them
+// (THALLO_B200_MG_NCCL=1 keeps the NCCL all-reduce + th_halo_push + th_mg_close sequence for comparison).
+int Plan::connect_all(int world, const void* handles64, const long long* infos4) {
+    if (!d_.multi) { error_ = "plan was not lowered with a partition"; return 1; }
+    if (world != world_ || world > kMaxRanks) { error_ = "connect_all: world size does not match the communicator (or exceeds 16)"; return 1; }
+    for (int r = 0; r < world; ++r) {
+        peer_stride_[r] = (size_t)infos4[4 * r + 1];
+        if (r == rank_) { peer_all_[r] = vec_block_; continue; }
+        cudaIpcMemHandle_t h;
+        memcpy(&h, (const char*)handles64 + 64 * r, 64);
+        CD(cudaIpcOpenMemHandle((void**)&peer_all_[r], h, cudaIpcMemLazyEnablePeerAccess));
+    }
+    for (int side = 0; side < 2; ++side) {
+        const int r = rank_ + (side ? 1 : -1);
+        if (r < 0 || r >= world) continue;
+        peer_[side] = peer_all_[r];
+        peer_extent_[side] = infos4[4 * r];
+        peer_width_[side] = side ? infos4[4 * r + 2] : infos4[4 * r + 3];     // the neighbour's ghost block facing this rank
+    }
+    if (d_.gmulti && d_.part_dim >= 0) {
+        const long long owned = d_.part_extent - d_.ghost_lo - d_.ghost_hi;
+        if (peer_width_[0] > owned || peer_width_[1] > owned) { error_ = "a neighbour's ghost block is wider than this rank's owned range"; return 1; }
+    }
+    const char* e = getenv("THALLO_B200_MG_NCCL");
+    fused_ = !(e && atoi(e) != 0);
+    peers_ = HPeers{};
+    for (int r = 0; r < world; ++r) peers_.box[r] = peer_all_[r] + peer_stride_[r] * kNumVecs;
+    peers_.rank = rank_; peers_.world = world_; peers_.fused = fused_ ? 1 : 0;
+    build_push(d_.tiled ? V_Z : V_P, push_init_);
+    build_push(V_Z, push_iter_);
+    return 0;
+}
 
 // ------------------------------------------------------------------ plan
-static const int kNumVecs = 13;
-static const char* kVecNames[kNumVecs] = {"delta", "r", "b", "Adelta", "z", "p", "Ap_X", "CtC", "preconditioner", "SSq", "prevX", "initX", "p2"};
-enum { V_DELTA, V_R, V_B, V_ADELTA, V_Z, V_P, V_AP, V_CTC, V_PRE, V_SSQ, V_PREVX, V_INITX, V_P2 };
 
 void Plan::log(const char* fmt, ...) const {
     if (opts_->init.verbosityLevel <= 0) return;
@@ -254,8 +319,9 @@ Plan::Plan(const StateOptions* opts, const PlanDesc& desc, const std::string& so
 
     // solver vectors: one allocation, 12 unknown-sized vectors (gauss_newton.t:1963-2071)
     vec_stride_ = ((size_t)d_.nunk * real_size_ + 255) / 256 * 256;
-    CD(cudaMalloc((void**)&vec_block_, vec_stride_ * kNumVecs));
-    CD(cudaMemsetAsync(vec_block_, 0, vec_stride_ * kNumVecs, stream()));
+    // (+ the mailboxes of the multi-GPU in-kernel all-reduce behind the last vector, so that one IPC handle covers both)
+    CD(cudaMalloc((void**)&vec_block_, vec_stride_ * kNumVecs + kMailBytes));
+    CD(cudaMemsetAsync(vec_block_, 0, vec_stride_ * kNumVecs + kMailBytes, stream()));
     for (int i = 0; i < kNumVecs; ++i) vecs_[i] = vec_block_ + vec_stride_ * i;
     for (auto& c : d_.computed) {     // ComputedArrays: value image + gradient image (ImageTemporary, thallo.t:1806-1815)
         void* v = nullptr; void* g = nullptr;
@@ -276,7 +342,7 @@ Plan::Plan(const StateOptions* opts, const PlanDesc& desc, const std::string& so
     CD(cudaMemsetAsync(d_scalars_, 0, sizeof(HScalars), stream()));
     CD(cudaHostAlloc((void**)&h_scalars_, sizeof(HScalars), cudaHostAllocDefault));
     CD(cudaHostAlloc((void**)&h_flags_, sizeof(HHostFlags), cudaHostAllocMapped));
-    h_flags_->progress = 0; h_flags_->done_epoch = -1; h_flags_->done_at = 0;
+    h_flags_->progress = 0; h_flags_->exit_word = 0;
     CD(cudaHostGetDevicePointer(&d_flags_, (void*)h_flags_, 0));
 
     int sms = 148;
@@ -350,6 +416,10 @@ Plan::Plan(const StateOptions* opts, const PlanDesc& desc, const std::string& so
             tiled_grid_[v] = (unsigned)std::min<long long>(ntiles, (long long)sms * per_sm);
         }
     }
+    peers_ = HPeers{};
+    peers_.world = 1;
+    build_push(-1, push_none_);
+    push_init_ = push_iter_ = push_none_;
     sp_ = SolverParameters();
     ok_ = true;
 }
@@ -405,7 +475,9 @@ void Plan::build_vector_maps() {
 }
 
 Plan::~Plan() {
-    for (int i = 0; i < 2; ++i) if (peer_[i]) cudaIpcCloseMemHandle(peer_[i]);
+    bool all = false;
+    for (int r = 0; r < kMaxRanks; ++r) if (peer_all_[r] && peer_all_[r] != vec_block_) { cudaIpcCloseMemHandle(peer_all_[r]); all = true; }
+    if (!all) for (int i = 0; i < 2; ++i) if (peer_[i]) cudaIpcCloseMemHandle(peer_[i]);
     if (comm_) nccl().CommDestroy(comm_);
     for (auto& a : adj_) { if (a.ptr) cudaFree(a.ptr); if (a.perm) cudaFree(a.perm); }
     for (void* q : jvals_) if (q) cudaFree(q);
@@ -566,14 +638,15 @@ void Plan::launch_gather(int which) {
         }
     for (size_t s = 0; s < d_.spaces.size(); ++s) {
         int first = s == 0;
-        void* a[] = {P, V, G, &d_scalars_, &d_partials_, &which, &first};
+        int reduce_now = s + 1 == d_.spaces.size() && d_.replicated.empty();      // the last contribution to <p, Ap>: all-reduce in-kernel
+        void* a[] = {P, V, G, &d_scalars_, &d_partials_, &which, &first, &reduce_now, &peers_};
         const long long threads = d_.spaces[s].elements * d_.spaces[s].lanes;
         launch(fn("th_gather_s" + std::to_string(s)), dim3((unsigned)((threads + 255) / 256)), dim3(256), a);
     }
     if (!d_.replicated.empty()) {      // replicated unknowns: sum the ranks' partial J^T J p, then + CtC p and the dot product
         long long n = 0;
         for (auto& r : d_.replicated) { allreduce_vec(which ? V_ADELTA : V_AP, r.first, r.second); n += r.second; }
-        void* a[] = {P, V, &d_scalars_, &d_partials_, &which};
+        void* a[] = {P, V, &d_scalars_, &d_partials_, &which, &peers_};
         launch(fn("th_rep_finish"), dim3((unsigned)std::min<long long>((n + 255) / 256, (long long)sms_ * 8)), dim3(256), a);
     }
 }
@@ -743,7 +816,7 @@ double Plan::cost() {   // gauss_newton.t:1787-1793
 }
 
 void Plan::launch_tiled(int mode) {
-    void* a[] = {params_buf_.data(), vecs_buf_.data(), maps_base(maps_buf_), &d_scalars_, &d_partials_, &mode};
+    void* a[] = {params_buf_.data(), vecs_buf_.data(), maps_base(maps_buf_), &d_scalars_, &d_partials_, &mode, &peers_};
     const int v = use_tma_ ? 1 : 0;
     dim3 grid(tiled_grid_[v], 1, 1), block((unsigned)d_.tile[0], (unsigned)d_.tile[1], (unsigned)d_.tile[2]);
     launch(pcg_a_, grid, block, a, tiled_smem_[v]);
@@ -758,15 +831,16 @@ void Plan::linear_iteration(int l) {
     void* qtol = d_.is_double ? (void*)&qd : (void*)&qf;
     const bool reset = d_.lm && ((l + 1) % sp_.residual_reset_period) == 0;   // gauss_newton.t:1653-1660
     // ---- operator: Ap = (JtJ [+CtC]) p and alphaDenominator
+    const bool nccl_scalars = d_.multi && !fused_;      // comparison path: PCG scalars over NCCL, separate push / close kernels
     if (d_.tiled) {
         launch_tiled(0);          // also forms p = z + beta p (PCGStep3 of the previous iteration)
-        if (d_.multi) allreduce(offsetof(HScalars, aD), 1);
+        if (nccl_scalars) allreduce(offsetof(HScalars, aD), 1);
     } else if (d_.at_output) {
         void* a[] = {P, V, &d_scalars_, &d_partials_, &zero};
         launch_uw(fn("th_step1_uw"), a);
     } else if (d_.gather) {
         launch_gather(0);
-        if (d_.multi) allreduce(offsetof(HScalars, aD), 1);
+        if (nccl_scalars) allreduce(offsetof(HScalars, aD), 1);
     } else {
         clear(vecs_[V_AP]);
         for (size_t g = 0; g < d_.groups.size(); ++g) {
@@ -785,19 +859,11 @@ void Plan::linear_iteration(int l) {
         }
         int add_ctc = 0;
         if (d_.tiled) {
-            if (d_.multi) {       // A*delta gathers delta from the ghost layers
-                halo_push(V_DELTA, 1);
-                allreduce(offsetof(HScalars, spare), 1);
-            }
-            launch_tiled(1);
+            launch_tiled(1);      // (multi-GPU: the ghost layers of delta are maintained locally, th_pcg_b)
         } else if (d_.at_output) {
             void* a[] = {P, V, &d_scalars_, &d_partials_, &one};
             launch_uw(fn("th_step1_uw"), a);
         } else if (d_.gather) {
-            if (d_.multi) {       // A*delta reads delta at the ghost vertices
-                halo_push(V_DELTA, 1);
-                allreduce(offsetof(HScalars, spare), 1);
-            }
             launch_gather(1);        // materialised groups contribute nothing to A*delta (gauss_newton.t:1058-1065: no applyJTJ exists for them)
         } else {
             clear(vecs_[V_ADELTA]);
@@ -810,13 +876,13 @@ void Plan::linear_iteration(int l) {
             launch_flat(fn("th_step1_finish"), a);
             add_ctc = 1;
         }
-        void* a[] = {V, &d_scalars_, &d_partials_, &add_ctc, qtol, &d_flags_, &epoch_};
+        void* a[] = {V, &d_scalars_, &d_partials_, &add_ctc, qtol, &d_flags_, &epoch_, &peers_, push_iter_.data()};
         launch_flat(fn("th_step2_second"), a);
     } else {
-        void* a[] = {V, &d_scalars_, &d_partials_, qtol, &d_flags_, &epoch_};
+        void* a[] = {V, &d_scalars_, &d_partials_, qtol, &d_flags_, &epoch_, &peers_, push_iter_.data()};
         launch_flat(fn("th_pcg_b"), a);
     }
-    if (d_.multi) {               // z ghost layers, global <z,r> and q, then close the iteration
+    if (nccl_scalars) {           // z ghost layers, global <z,r> and q, then close the iteration
         halo_push(V_Z, 1);
         allreduce(offsetof(HScalars, red), 2);
         void* a[] = {&d_scalars_, qtol, &d_flags_, &epoch_};
@@ -838,6 +904,8 @@ int Plan::step(void** params) {
     span_begin(cur_iter_);
     span_begin(cur_phase_);
     ++epoch_;
+    peers_.epoch = epoch_;
+    const bool nccl_scalars = d_.multi && !fused_;
     int first = sp_.nIter == 0;
     if (d_.ncoef > 0) {   // PCG-invariant parts of J, once per nonlinear iteration
         void* a[] = {P};
@@ -848,9 +916,9 @@ int Plan::step(void** params) {
         launch(fn("th_precompute_scoef_s" + std::to_string(c.space)), dim3((unsigned)((d_.spaces[c.space].elements + 255) / 256)), dim3(256), a);
     }
     if (d_.at_output) {
-        void* a[] = {P, V, &d_scalars_, &d_partials_, &first};
+        void* a[] = {P, V, &d_scalars_, &d_partials_, &first, &peers_, push_init_.data()};
         launch_uw(fn("th_init_uw"), a);
-        if (d_.multi) {                       // z (= p0) ghost layers, global <r,p>
+        if (nccl_scalars) {                   // z (= p0) ghost layers, global <r,p>
             halo_push(V_Z, 0);
             allreduce(offsetof(HScalars, rz), 1);
         }
@@ -873,9 +941,9 @@ int Plan::step(void** params) {
             allreduce_vec(V_R, r.first, r.second);
             allreduce_vec(V_PRE, r.first, r.second);
         }
-        void* a[] = {P, V, &d_scalars_, &d_partials_, &first};
+        void* a[] = {P, V, &d_scalars_, &d_partials_, &first, &peers_, push_init_.data()};
         launch_flat(fn("th_init_finish"), a);
-        if (d_.multi) {                       // p0 at the ghost vertices, global <r,p>
+        if (nccl_scalars) {                   // p0 at the ghost vertices, global <r,p>
             halo_push(V_P, 0);
             allreduce(offsetof(HScalars, rz), 1);
         }
@@ -899,11 +967,12 @@ int Plan::step(void** params) {
         if (d_.lm && need >= 1) {
             bool stop = false;
             for (unsigned spins = 0;; ++spins) {
+                // the device publishes the exit word before the progress word (each with one 64-bit store)
                 const long long pr = h_flags_->progress;
                 const int done_iters = (int)(pr >> 32) == epoch_ ? (int)(pr & 0xffffffff) : 0;
                 std::atomic_thread_fence(std::memory_order_acquire);
-                const bool done = h_flags_->done_epoch == epoch_;
-                if (done && h_flags_->done_at <= need) { stop = true; break; }
+                const long long ex = h_flags_->exit_word;
+                if ((int)(ex >> 32) == epoch_ && (int)(ex & 0xffffffff) <= need) { stop = true; break; }
                 if (done_iters >= need) break;
                 if ((spins & 1023) == 1023) {          // a faulted kernel never reports progress: surface the error
                     const cudaError_t e = cudaStreamQuery(stream());
@@ -918,10 +987,7 @@ int Plan::step(void** params) {
     span_end(cur_phase_, ev_linear_);
     span_begin(cur_phase_);
     int zero = 0;
-    if (d_.multi) {   // delta ghost layers (model cost and the update read them); the all-reduce orders the exchange
-        halo_push(V_DELTA, 0);
-        allreduce(offsetof(HScalars, spare), 1);
-    }
+    // (multi-GPU: the ghost layers of delta that the model cost and the update read are maintained locally, th_pcg_b)
     if (d_.lm) {   // computeModelCostChange + savePreviousUnknowns, gauss_newton.t:1694-1697
         if (d_.at_output) {
             void* a[] = {P, V, &d_scalars_, &d_partials_};

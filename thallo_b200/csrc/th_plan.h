@@ -91,7 +91,12 @@ struct HScalars {
     unsigned int ticket[8];
     int it, done, lin_done, pad;
 };
-struct HHostFlags { volatile long long progress; volatile int done_epoch; volatile int done_at; };
+struct HHostFlags { volatile long long progress; volatile long long exit_word; };
+// multi-GPU peer memory (mirrors ThMail / ThPeers in skeleton/thallo_prelude.cuh)
+constexpr int kMaxRanks = 16, kMailKinds = 4;
+struct HMail { double v[2]; unsigned long long seq, pad; };
+constexpr size_t kMailBytes = (size_t)kMailKinds * 2 * kMaxRanks * sizeof(HMail);
+struct HPeers { void* box[kMaxRanks]; int rank, world, fused, epoch; };
 
 class Plan {
 public:
@@ -116,6 +121,10 @@ public:
     void allreduce_vec(int vec, long long offset, long long count);
     int connect_graph(const void* handle_lo, long long extent_lo, long long width_lo, const void* handle_hi, long long extent_hi,
                       long long width_hi);
+    // all-to-all peer mapping (mailboxes of the in-kernel all-reduce + the neighbours' ghost layers): info = per rank
+    // {local extent of the partitioned axis, bytes between consecutive solver vectors, ghost_lo, ghost_hi}
+    int peer_info(long long* info4);
+    int connect_all(int world, const void* handles64, const long long* infos4);
     // per-kernel device times (timingLevel >= 2, like util.t:774-790): "name count total_ms\n" lines
     std::string kernel_times();
 
@@ -170,6 +179,14 @@ private:
     long long peer_width_[2] = {0, 0};              // graph partition: width of the neighbour's ghost block this rank fills
     void allreduce(size_t scalars_offset, int count);
     void halo_push(int vec, int check_done);
+    struct Seg { const void* src; void* dst; long long lo, count; };
+    int segments(int vec, Seg* out) const;          // boundary layers of solver vector `vec` -> the neighbours' ghost layers
+    void build_push(int vec, std::vector<char>& image) const;
+    char* peer_all_[kMaxRanks] = {};                // every rank's solver-vector block (CUDA IPC mappings; own = vec_block_)
+    size_t peer_stride_[kMaxRanks] = {};
+    bool fused_ = false;                            // PCG scalars all-reduced inside the kernels over peer memory (default once connect_all ran)
+    HPeers peers_{};
+    std::vector<char> push_init_, push_iter_, push_none_;   // ThPush images: PCGInit (z tiled / p gather), every iteration (z), none
     void* dscalar(size_t off) const { return (char*)d_scalars_ + off; }
     // gather schedule state: adjacency lists of the sparse endpoints (rebuilt when the caller's index array
     // changes), stored partial derivatives and J p of the materialised groups

@@ -53,13 +53,41 @@ def stencil_halo(energy, global_dims, kind="gauss_newton", double=False):
     return int(low.desc["tile"]["halo"][len(global_dims) - 1])
 
 
+def connect_ranks(solver, rank, world, group=None):
+    """Collective over `group`: NCCL communicator (id from rank 0) and the all-to-all CUDA IPC mapping of the ranks'
+    solver-vector blocks (ThalloB200_PlanConnectAll): mailboxes of the in-kernel all-reduce + the neighbours' ghost
+    layers.  Returns the objects that must stay alive as long as the plan."""
+    import torch.distributed as dist
+    from .api import lib
+    L = lib()
+    s = solver
+    idbuf = C.create_string_buffer(128)
+    if rank == 0:
+        assert L.ThalloB200_NcclUniqueId(idbuf, 128) == 0, "ncclGetUniqueId failed"
+    box = [bytes(idbuf.raw)]
+    dist.broadcast_object_list(box, src=0, group=group)
+    assert L.ThalloB200_PlanInitComm(s.state, s.plan, box[0], rank, world) == 0, L.ThalloB200_LastError().decode()
+    h = C.create_string_buffer(64)
+    extent = C.c_longlong(0)
+    assert L.ThalloB200_PlanIpcHandle(s.state, s.plan, h, C.byref(extent)) == 0
+    info = (C.c_longlong * 4)()
+    assert L.ThalloB200_PlanPeerInfo(s.state, s.plan, info) == 0
+    mine = (bytes(h.raw), [int(x) for x in info])
+    everyone = [None] * world
+    dist.all_gather_object(everyone, mine, group=group)
+    handles = C.create_string_buffer(b"".join(e[0] for e in everyone), 64 * world)
+    infos = (C.c_longlong * (4 * world))(*[x for e in everyone for x in e[1]])
+    rc = L.ThalloB200_PlanConnectAll(s.state, s.plan, world, handles, infos)
+    assert rc == 0, L.ThalloB200_LastError().decode()
+    return (box, everyone, handles, infos)
+
+
 class SlabSolver:
     """One rank of a slab-partitioned solve.  `group` is a torch.distributed process group (any
     backend that can move small Python objects: gloo or nccl)."""
 
     def __init__(self, global_dims, energy, kind, rank, world, double=False, group=None, **kw):
-        import torch.distributed as dist
-        from .api import ThalloSolver, lib
+        from .api import ThalloSolver
         self.rank, self.world = rank, world
         self.global_dims = [int(d) for d in global_dims]
         self.halo = stencil_halo(energy, self.global_dims, kind, double)
@@ -71,26 +99,7 @@ class SlabSolver:
         partition = (self.part["ghost_lo"], self.part["ghost_hi"], self.part["start"] - self.part["ghost_lo"]) if world > 1 else None
         self.solver = ThalloSolver(self.local_dims, energy, kind, double=double, partition=partition, **kw)
         if world > 1:
-            L = lib()
-            s = self.solver
-            # NCCL id from rank 0
-            idbuf = C.create_string_buffer(128)
-            if rank == 0:
-                assert L.ThalloB200_NcclUniqueId(idbuf, 128) == 0, "ncclGetUniqueId failed"
-            box = [bytes(idbuf.raw)]
-            dist.broadcast_object_list(box, src=0, group=group)
-            assert L.ThalloB200_PlanInitComm(s.state, s.plan, box[0], rank, world) == 0, L.ThalloB200_LastError().decode()
-            # CUDA IPC handles of the neighbours' solver vectors
-            h = C.create_string_buffer(64)
-            extent = C.c_longlong(0)
-            assert L.ThalloB200_PlanIpcHandle(s.state, s.plan, h, C.byref(extent)) == 0
-            mine = (bytes(h.raw), int(extent.value))
-            everyone = [None] * world
-            dist.all_gather_object(everyone, mine, group=group)
-            lo = everyone[rank - 1] if rank > 0 else (None, 0)
-            hi = everyone[rank + 1] if rank < world - 1 else (None, 0)
-            assert L.ThalloB200_PlanConnect(s.state, s.plan, lo[0], lo[1], hi[0], hi[1]) == 0
-            self._keep = (box, everyone)
+            self._keep = connect_ranks(self.solver, rank, world, group)
 
     def slab(self, global_array):
         return local_slab(global_array, self.layer, self.part)
@@ -177,8 +186,7 @@ class GraphSolver:
 
     def __init__(self, global_dims, energy, kind, rank, world, index_arrays, vertex_dim=0, edge_dim=1, double=False,
                  group=None, **kw):
-        import torch.distributed as dist
-        from .api import ThalloSolver, lib
+        from .api import ThalloSolver
         self.rank, self.world = rank, world
         self.parts = graph_partition(global_dims[vertex_dim], index_arrays, world)
         self.part = p = self.parts[rank]
@@ -190,30 +198,9 @@ class GraphSolver:
             partition = {vertex_dim: (p["ghost_lo"], p["ghost_hi"]), edge_dim: (0, len(p["edges"]) - p["owned_edges"])}
         self.solver = ThalloSolver(self.local_dims, energy, kind, double=double, partition=partition, schedule="gather", **kw)
         if world > 1:
-            L = lib()
-            s = self.solver
-            idbuf = C.create_string_buffer(128)
-            if rank == 0:
-                assert L.ThalloB200_NcclUniqueId(idbuf, 128) == 0, "ncclGetUniqueId failed"
-            box = [bytes(idbuf.raw)]
-            dist.broadcast_object_list(box, src=0, group=group)
-            assert L.ThalloB200_PlanInitComm(s.state, s.plan, box[0], rank, world) == 0, L.ThalloB200_LastError().decode()
-            h = C.create_string_buffer(64)
-            extent = C.c_longlong(0)
-            assert L.ThalloB200_PlanIpcHandle(s.state, s.plan, h, C.byref(extent)) == 0
-            # what a neighbour needs to address this rank's ghost blocks: the handle, the local vertex count
-            # and the width of the ghost block facing it
-            mine = (bytes(h.raw), int(extent.value), p["ghost_lo"], p["ghost_hi"])
-            everyone = [None] * world
-            dist.all_gather_object(everyone, mine, group=group)
-            lo = everyone[rank - 1] if rank > 0 else None
-            hi = everyone[rank + 1] if rank < world - 1 else None
-            rc = L.ThalloB200_PlanConnectGraph(
-                s.state, s.plan,
-                lo[0] if lo else None, lo[1] if lo else 0, lo[3] if lo else 0,       # lower neighbour: its ghost_hi block is filled from here
-                hi[0] if hi else None, hi[1] if hi else 0, hi[2] if hi else 0)       # upper neighbour: its ghost_lo block
-            assert rc == 0, L.ThalloB200_LastError().decode()
-            self._keep = (box, everyone)
+            # (what a neighbour needs to address this rank's ghost blocks -- the handle, the local vertex count and the
+            # widths of the ghost blocks -- travels in ThalloB200_PlanPeerInfo)
+            self._keep = connect_ranks(self.solver, rank, world, group)
 
     def vertex_rows(self, global_array):
         return local_vertex_rows(global_array, self.part)
@@ -251,8 +238,7 @@ class ReplicatedSolver:
 
     def __init__(self, global_dims, energy, kind, rank, world, obs_to_point, rep_dim=0, part_dim=1, res_dim=2, double=False,
                  group=None, **kw):
-        import torch.distributed as dist
-        from .api import ThalloSolver, lib
+        from .api import ThalloSolver
         self.rank, self.world = rank, world
         self.parts = point_partition(global_dims[part_dim], obs_to_point, world)
         self.part = p = self.parts[rank]
@@ -262,14 +248,7 @@ class ReplicatedSolver:
         partition = dict(replicated=(rep_dim,), owner=(rank == 0)) if world > 1 else None
         self.solver = ThalloSolver(self.local_dims, energy, kind, double=double, partition=partition, schedule="gather", **kw)
         if world > 1:
-            L = lib()
-            s = self.solver
-            idbuf = C.create_string_buffer(128)
-            if rank == 0:
-                assert L.ThalloB200_NcclUniqueId(idbuf, 128) == 0, "ncclGetUniqueId failed"
-            box = [bytes(idbuf.raw)]
-            dist.broadcast_object_list(box, src=0, group=group)
-            assert L.ThalloB200_PlanInitComm(s.state, s.plan, box[0], rank, world) == 0, L.ThalloB200_LastError().decode()
+            self._keep = connect_ranks(self.solver, rank, world, group)
 
     def point_rows(self, global_array):
         a = np.asarray(global_array)
