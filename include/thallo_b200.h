@@ -42,6 +42,10 @@ unsigned long long ThalloB200_PlanTotalLinearIterations(Thallo_State* state, Tha
  * (count reals of the plan's precision).  Test hook. Returns number of reals copied. */
 long long ThalloB200_PlanReadVector(Thallo_State* state, Thallo_Plan* plan, const char* name, void* host_dst, long long count);
 
+/* Device pointer of solver vector `name` (nunk reals of the plan's precision; valid until Thallo_PlanFree), or NULL.
+ * Measurement hook: lets a checker form dot products of full-size vectors on the device instead of copying them out. */
+void* ThalloB200_PlanVectorPointer(Thallo_State* state, Thallo_Plan* plan, const char* name);
+
 /* Materialise the Jacobian of residual group `group` at the current unknowns (after Thallo_ProblemInit), in the
  * reference's CSR order (precomputeJ / generateDumpJ, gauss_newton.t:325-487,1019-1025): element-major, within an
  * element row by row, row k holding the descriptor's row_nnz[k] entries; host_vals receives reals of the plan's

@@ -385,6 +385,9 @@ class _SampledImage:
     def __call__(self, x, y):
         L = self.L
         x, y = L._todual(x), L._todual(y)
+        if L.origin:                      # absolute coordinates -> coordinates of the crop
+            ox, oy = L.origin.get(self.im.dims[0].idx, 0), L.origin.get(self.im.dims[1].idx, 0)
+            x, y = Dual(x.val - L.dtype(ox), x.d), Dual(y.val - L.dtype(oy), y.d)
         val = self._sample(self.im, x.val, y.val)
         d = {}
         if x.d or y.d:
@@ -426,7 +429,10 @@ class NumpyL:
     float, float2, float3, float4, float9 = ("f", 1), ("f", 2), ("f", 3), ("f", 4), ("f", 9)
     uint8, int = ("u8", 1), ("i32", 1)
 
-    def __init__(self, dims, params, dtype=np.float32):
+    def __init__(self, dims, params, dtype=np.float32, origin=None):
+        # origin: {dimension index: offset} -- the arrays are a crop of a larger problem that starts at this absolute
+        # index; index VALUES (x:asvalue()) are absolute, sampled images are addressed relative to the crop
+        self.origin = dict(origin or {})
         self.dim_sizes = list(dims)
         self.params = list(params)
         self.dtype = np.dtype(dtype).type
@@ -502,7 +508,7 @@ class NumpyL:
             if any(d is iv.dim for d in im.dims):
                 dims = im.dims
                 break
-        g = self._coords(dims)[iv.dim.name] + iv.off
+        g = self._coords(dims)[iv.dim.name] + iv.off + self.origin.get(iv.dim.idx, 0)
         return Dual(g.astype(self.dtype))
 
     def _todual(self, x):

@@ -33,7 +33,8 @@ DEFAULTS = dict(
 
 class OracleSolver:
     def __init__(self, define, dims, kind="gauss_newton", dtype=np.float32, mode="at_output",
-                 materialized=False, define_kwargs=None):
+                 materialized=False, define_kwargs=None, origin=None):
+        self.origin = origin
         assert kind in ("gauss_newton", "levenberg_marquardt")   # thallo.t:74
         assert mode in ("at_output", "residualwise")
         self.define, self.dims, self.kind = define, list(dims), kind
@@ -58,7 +59,7 @@ class OracleSolver:
         return self.dtype(np.dot(a.astype(np.float64), b.astype(np.float64)))
 
     def _eval(self, params):
-        L = NumpyL(self.dims, params, self.dtype)
+        L = NumpyL(self.dims, params, self.dtype, self.origin)
         self.define(L, **self.kw)
         F, J, self.ranges = L.assemble()
         return L, F, J
@@ -87,6 +88,38 @@ class OracleSolver:
         one = dt(1)
         s = one + np.sqrt(d)
         return (one / (s * s)).astype(dt)
+
+    def setup_vectors(self, params, radius=None):
+        """The set-up of the first nonlinear iteration (PCGInit1 [+ the LM diagonal], the head of `step`) without the
+        PCG loop: r = -J^T F, the preconditioner M, the LM diagonal C and the operator v -> (J^T J [+ C]) v.  Every
+        quantity is local to an unknown and the residuals touching it, which is what lets a crop of a large problem be
+        checked against the corresponding elements of the full-size GPU run (bench.py's parity record)."""
+        dt, P = self.dtype, self.p
+        L, F, J = self._eval(params)
+        keep = (~L.exclude_mask()).astype(dt)
+        usepre = L.usepreconditioner
+        Jk = J.multiply(keep[None, :]).tocsr().astype(dt)
+        JT = Jk.T.tocsr()
+        r = (-(JT @ F)).astype(dt)
+        dtrue = (L.diag_sq * keep).astype(dt)
+        if self.mode == "at_output":
+            M = self._G(dtrue if usepre else np.ones_like(dtrue), dt) * keep
+        else:
+            M = (self._G(dtrue, dt) if usepre else np.ones_like(dtrue)) * keep
+        C = np.zeros_like(r)
+        if self.lm:
+            rho = dt(P["trust_region_radius"] if radius is None else radius)
+            Ct = (dtrue / rho).astype(dt)
+            with np.errstate(divide="ignore", invalid="ignore"):
+                mult = ((dt(1) / M) / rho).astype(dt)              # SSq = M at the first nonlinear iteration
+                C = np.minimum(np.maximum(Ct, dt(P["min_lm_diagonal"]) * mult), dt(P["max_lm_diagonal"]) * mult).astype(dt)
+                M = (dt(1) / (C + rho * Ct)).astype(dt)
+            C = np.where(keep > 0, C, 0).astype(dt)
+            M = np.where(keep > 0, M, 0).astype(dt)
+
+        def applyA(v):
+            return (JT @ (Jk @ v) + C * v).astype(dt)
+        return dict(r=r, M=M, C=C, applyA=applyA, cost=float(0.5 * np.dot(F.astype(np.float64), F.astype(np.float64))), L=L)
 
     # ---- API mirroring thallo.Plan {init, step, cost}
     def init(self, params):

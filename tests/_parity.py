@@ -49,13 +49,25 @@ def gpu_trajectory(name, dims, kind, params, device_slots, dtype, nit, lit, **kw
 
 NOISE_FACTOR = 8.0
 
+# Audit of the tolerance policy: every cost assertion records whether it held at the PLAIN rule (tol relative) or only
+# through the float32 noise allowance; every LM iteration-count comparison whether the counts were identical or the
+# borderline-zeta rule was used.  tests/conftest.py prints the tally at the end of the run, and float64 runs are never
+# allowed the hatch (assert_costs_close(..., strict=True) for them).
+AUDIT = {"cost_plain": 0, "cost_via_noise_factor": 0, "lm_counts_identical": 0, "lm_counts_via_zeta_margin": 0, "hatch_users": []}
 
-def assert_costs_close(c, cref, tol, floor, cref64=None, perturbed=()):
+
+def _test_name():
+    import os
+    return os.environ.get("PYTEST_CURRENT_TEST", "?").split(" ")[0]
+
+
+def assert_costs_close(c, cref, tol, floor, cref64=None, perturbed=(), strict=False):
     """perturbed: float32 oracle trajectories of the same problem with the unknowns' initial values
     moved by one ulp -- a direct measurement of how far float32 rounding alone moves the trajectory
     (truncated PCG far from convergence amplifies rounding differences, and graph-domain sums are
     order-dependent)."""
     assert len(c) == len(cref), (c, cref)
+    strict = strict or tol <= 1e-9          # float64 comparisons (1e-10 rule) never get the noise allowance
     noise = [0.0] * len(cref)
     for other in ([cref64] if cref64 is not None else []) + list(perturbed):
         if len(other) != len(cref):
@@ -63,7 +75,15 @@ def assert_costs_close(c, cref, tol, floor, cref64=None, perturbed=()):
         rel = [abs(a - b) / max(abs(b), floor) for a, b in zip(cref, other)]
         noise = [max(n, max(rel[max(0, i - 1):i + 2])) for i, n in enumerate(noise)]
     for i, (a, b) in enumerate(zip(c, cref)):
+        plain = tol * max(abs(b), floor)
         allowed = max(tol, NOISE_FACTOR * noise[i]) * max(abs(b), floor)
+        if abs(a - b) <= plain:
+            AUDIT["cost_plain"] += 1
+        else:
+            assert not strict, ("float64 / strict comparison needs the noise allowance", i, a, b, plain)
+            AUDIT["cost_via_noise_factor"] += 1
+            if _test_name() not in AUDIT["hatch_users"]:
+                AUDIT["hatch_users"].append(_test_name())
         assert abs(a - b) <= allowed, (i, a, b, allowed, c, cref)
 
 
@@ -93,6 +113,9 @@ def assert_lm_parity(c, lin, make_oracle, make_params, nit, lit, tol, floor, cre
     o, cref = oracle_run(make_oracle, make_params(), nit, lit)
     ref_lin = [it["n_lin"] for it in o.trace]
     if lin != ref_lin[:len(lin)] or len(c) != len(cref):
+        AUDIT["lm_counts_via_zeta_margin"] += 1
+        if _test_name() not in AUDIT["hatch_users"]:
+            AUDIT["hatch_users"].append(_test_name())
         o, cref = oracle_run(make_oracle, make_params(), nit, lit, force_lin=list(lin))
         for i, it in enumerate(o.trace[:len(lin)]):
             free = ref_lin[i] if i < len(ref_lin) else None
@@ -105,6 +128,8 @@ def assert_lm_parity(c, lin, make_oracle, make_params, nit, lit, tol, floor, cre
                 "PCG iteration count differs (gpu %s, oracle %s) and zeta=%g at iteration %d is not borderline" % (lin, ref_lin, z, first)
             break       # later iterations legitimately follow a different trajectory in the free-running oracle
         cref64 = None
+    else:
+        AUDIT["lm_counts_identical"] += 1
     assert_costs_close(c, cref, tol, floor, cref64)
     return o
 

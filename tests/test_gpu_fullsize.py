@@ -1,0 +1,77 @@
+"""Parity at scale.  (1) The configured workloads at sizes well beyond the toy trajectories (1024^2 images, a 64 x 64 x
+96 volume, a 250 k-vertex mesh, 500 k observations): r0 = -J^T F, the preconditioner and A p0 of the GPU's full-size
+vectors against the float64 oracle on three crops (start / middle / end of the partitioned axis), and the solver's
+alpha against a float64 recomputation from its own vectors (oracle/fullsize.py; the crop locality itself is proved
+oracle-against-oracle in tests/test_oracle_crops.py).  bench.py runs the same check at the CONFIGURED sizes and puts
+it into its `parity` record.  (2) The headline 2048^2 LM solve against the plain-C restatement of the reference's
+CPU path, cost by cost.  (3) Run-to-run determinism."""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+
+from thallo_b200 import configs, workloads as wl
+
+pytestmark = pytest.mark.gpu
+
+SIZES = {"3a": dict(dims=(1024, 1024)), "3b": dict(dims=(1024, 1024)), "4a": dict(dims=(64, 64, 96)),
+         "4b": dict(n=500), "5": dict(cameras=400, points=100000), "2": dict(dims=(1024, 1024))}
+
+
+@pytest.mark.parametrize("key", ["2", "3a", "3b", "4a", "4b", "5"])
+def test_first_iteration_matches_the_oracle_on_crops(key):
+    from oracle import fullsize
+    case = configs.case(key, **SIZES[key])
+    dims = [int(x) for x in case.dims]
+    b = case.build(0, 1, "cuda")
+    desc = b.solver.lowered.desc
+    b.solver.close()
+    p = fullsize.first_iteration_parity(lambda: case.make_solver(dims), b.fresh, case.energy, case.kind,
+                                        fullsize.crops_for(case, dims, desc), case.oracle_mode, define_kwargs=case.define_kwargs,
+                                        materialized=case.materialized, solver_params=case.solver_params)
+    assert all(c["elements_compared"] > 0 for c in p["crops"].values()), p
+    # float32 GPU vectors against the float64 oracle, relative to the largest entry of each vector on the crop
+    assert p["operator_max_rel"] <= 2e-5, p
+    assert p["alpha_rel"] <= 1e-5, p
+
+
+def test_headline_solve_matches_the_c_restatement_of_the_reference_cpu_path():
+    """image_warping 2048 x 2048, LM 8 x 100 (the bench headline): every cost and every PCG iteration count."""
+    from oracle import iw_cpu
+    case = configs.case("2")
+    b = case.build(0, 1, "cuda")
+    s = b.solver
+    s.init(b.fresh())
+    costs, lin = [s.current_cost()], []
+    while s.step():
+        costs.append(s.current_cost())
+        lin.append(s.last_linear_iterations())
+    s.close()
+    W, H = case.dims
+    r = iw_cpu.solve(W, H, wl.image_warping_inputs(W, H), "levenberg_marquardt", acc64=True, nIterations=case.nit, lIterations=case.lit)
+    assert lin == r["n_lin"][:len(lin)], (lin, r["n_lin"])
+    assert len(costs) <= len(r["costs"])
+    for i, (a, c) in enumerate(zip(costs, r["costs"])):
+        assert abs(a - c) <= 1e-5 * abs(c), (i, a, c)
+
+
+@pytest.mark.parametrize("key", ["2", "4b"])
+def test_repeated_solves_are_bit_identical(key):
+    """Dot products are summed in a fixed order and the gather schedule uses no atomics: the same solve repeated gives the
+    same costs, the same PCG counts and the same unknowns, bit for bit."""
+    case = configs.case(key, **({"dims": (512, 384)} if key == "2" else {"n": 200}))
+    b = case.build(0, 1, "cuda")
+    s = b.solver
+    runs = []
+    for _ in range(5):
+        p = b.fresh()
+        s.set_parameters(trust_region_radius=1e4)          # a solve leaves its last radius behind (gauss_newton.t:1751)
+        s.init(p)
+        costs, lin = [s.current_cost()], []
+        while s.step():
+            costs.append(s.current_cost())
+            lin.append(s.last_linear_iterations())
+        torch.cuda.synchronize()
+        runs.append((costs, lin, [p[i].cpu().numpy().tobytes() for i in b.unknown_slots]))
+    s.close()
+    assert all(r == runs[0] for r in runs[1:])

@@ -72,7 +72,6 @@ def _run(binary, tmp_path, energy_text):
 
 
 @pytest.mark.gpu
-@pytest.mark.xfail(strict=False, reason="written after the GPU budget of round 1 was spent: not yet run on a GPU")
 @pytest.mark.skipif(not os.path.isfile(os.path.join(BIN, "ref_minimal")), reason="oracle/_ref not built")
 def test_reference_minimal_program_runs_against_this_library(tmp_path):
     import torch
@@ -86,7 +85,6 @@ def test_reference_minimal_program_runs_against_this_library(tmp_path):
 
 
 @pytest.mark.gpu
-@pytest.mark.xfail(strict=False, reason="written after the GPU budget of round 1 was spent: not yet run on a GPU")
 @pytest.mark.skipif(not os.path.isfile(os.path.join(BIN, "ref_minimal_graph")), reason="oracle/_ref not built")
 def test_reference_minimal_graph_program_runs_against_this_library(tmp_path):
     import torch

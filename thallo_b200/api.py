@@ -75,6 +75,7 @@ def lib():
     L.ThalloB200_PlanTotalLinearIterations.restype, L.ThalloB200_PlanTotalLinearIterations.argtypes = C.c_ulonglong, [vp, vp]
     L.ThalloB200_PlanReadVector.restype = C.c_longlong
     L.ThalloB200_PlanReadVector.argtypes = [vp, vp, cp, vp, C.c_longlong]
+    L.ThalloB200_PlanVectorPointer.restype, L.ThalloB200_PlanVectorPointer.argtypes = vp, [vp, vp, cp]
     L.ThalloB200_PlanExportJacobian.restype = C.c_longlong
     L.ThalloB200_PlanExportJacobian.argtypes = [vp, vp, C.c_int, vp, vp, C.c_longlong]
     L.ThalloB200_PlanKernelTimes.restype = C.c_longlong
@@ -274,6 +275,22 @@ class ThalloSolver:
         out = np.zeros(count, np.float64 if self.double else np.float32)
         self.L.ThalloB200_PlanReadVector(self.state, self.plan, name.encode(), out.ctypes.data, count)
         return out
+
+    def vector(self, name):
+        """Zero-copy torch view of solver vector `name` on the device (nunk reals)."""
+        import torch
+        ptr = self.L.ThalloB200_PlanVectorPointer(self.state, self.plan, name.encode())
+        if not ptr:
+            raise KeyError(name)
+        n = int(self.lowered.desc["nunk"]) if self.lowered is not None else None
+        assert n is not None, "vector(): needs a plan lowered in-process"
+
+        class _View:
+            pass
+        v = _View()
+        v.__cuda_array_interface__ = dict(shape=(n,), typestr="<f8" if self.double else "<f4", data=(int(ptr), False), version=3,
+                                          strides=None)
+        return torch.as_tensor(v, device="cuda")
 
     def close(self):
         if getattr(self, "plan", None):

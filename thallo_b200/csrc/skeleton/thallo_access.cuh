@@ -163,8 +163,9 @@ __device__ __forceinline__ double th_warp_sum(double v) {
 // Every thread of every block calls this with K per-thread values.  partials holds
 // K * gridsize doubles.  Returns true (in all threads of exactly one block, the last to
 // arrive) with tot[k] = sum over blocks in block order.
+// `pushed`: this thread stored into peer memory (multi-GPU): the CTA then fences at system scope before its ticket.
 template <int K> __device__ __forceinline__ bool th_grid_reduce(double (&val)[K], double (&tot)[K], double* partials,
-                                                               unsigned int* ticket) {
+                                                               unsigned int* ticket, bool pushed = false) {
     __shared__ double sm[K][32];
     __shared__ bool last;
     const int tid = threadIdx.x + blockDim.x * (threadIdx.y + blockDim.y * threadIdx.z);
@@ -177,7 +178,11 @@ template <int K> __device__ __forceinline__ bool th_grid_reduce(double (&val)[K]
         const double w = th_warp_sum(val[k]);
         if (lane == 0) sm[k][warp] = w;
     }
+#if TH_MULTI
+    const bool cta_pushed = __syncthreads_or(pushed ? 1 : 0) != 0;
+#else
     __syncthreads();
+#endif
     if (warp == 0) {
 #pragma unroll
         for (int k = 0; k < K; ++k) {
@@ -188,7 +193,8 @@ template <int K> __device__ __forceinline__ bool th_grid_reduce(double (&val)[K]
     }
     if (tid == 0) {
 #if TH_MULTI
-        __threadfence_system();      // this CTA's stores into peer memory (ThPush) precede the mailbox flag of the last CTA
+        // this CTA's stores into peer memory (ThPush) must be visible to whoever sees the mailbox pair the last CTA sends
+        if (cta_pushed) __threadfence_system(); else __threadfence();
 #else
         __threadfence();
 #endif
@@ -216,48 +222,54 @@ template <int K> __device__ __forceinline__ bool th_grid_reduce(double (&val)[K]
 
 // ------------------------------------------------------------------ multi-GPU: peer stores and the in-kernel all-reduce
 #if TH_MULTI
-__device__ __forceinline__ unsigned long long th_ld_acquire_sys(const unsigned long long* p) {
-    unsigned long long v;
-    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void th_st_release_sys(unsigned long long* p, unsigned long long v) {
-    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
 __device__ __forceinline__ unsigned long long th_globaltimer() {
     unsigned long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     return t;
+}
+// one 16-byte store / load of a (value, sequence number) pair: a single transaction on NVLink, so a reader that sees
+// the sequence number sees the value that travelled with it (the scheme of NCCL's LL protocols)
+__device__ __forceinline__ void th_st_pair(unsigned long long* p, unsigned long long v, unsigned long long seq) {
+    asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(v), "l"(seq) : "memory");
+}
+__device__ __forceinline__ void th_ld_pair(const unsigned long long* p, unsigned long long& v, unsigned long long& seq) {
+    asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(v), "=l"(seq) : "l"(p) : "memory");
 }
 __device__ __forceinline__ ThMail* th_mail(ThMail* base, int kind, int parity, int src) {
     return base + (kind * 2 + parity) * TH_MAXRANKS + src;
 }
 // Sum K (<= 2) doubles over all ranks.  Called by every thread of warp 0 of ONE CTA per rank (the last CTA of the
 // grid reduction) with this rank's partial sums in v[]; returns the totals in v[] (all lanes), added in rank order so
-// that every rank holds the same bits.  Lane r serves peer r: values, system fence, flag (release) into the peer's
-// mailbox; then it polls this rank's own mailbox entry of rank r (acquire).  `seq` is unique per use of the
-// (kind, parity) slot and identical on all ranks.  A peer that never answers (crashed process) traps after 20 s
-// instead of hanging the GPU.
+// that every rank holds the same bits.  Lane r serves peer r: it stores (value, seq) pairs into the peer's mailbox
+// -- after a system-scope fence, so that everything this rank pushed into peer memory before (its CTAs fence their
+// pushes at system scope before they take their reduction ticket) is visible to whoever sees the pair -- and then
+// polls this rank's own mailbox entry of rank r.  `seq` is unique per use of the (kind, parity) slot and identical
+// on all ranks.  A peer that never answers (crashed process) traps after 20 s instead of hanging the GPU.
 template <int K> __device__ __forceinline__ void th_mail_allreduce(const ThPeers& R, int kind, unsigned long long seq, double (&v)[K]) {
     const int lane = (int)((threadIdx.x + blockDim.x * (threadIdx.y + blockDim.y * threadIdx.z)) & 31u);
     const int par = (int)(seq & 1ull);
     double got[2] = {0.0, 0.0};
     if (lane < R.world) {
         ThMail* out = th_mail(R.box[lane], kind, par, R.rank);
-#pragma unroll
-        for (int k = 0; k < K; ++k) *(volatile double*)&out->v[k] = v[k];
         __threadfence_system();
-        th_st_release_sys(&out->seq, seq);
-        ThMail* in = th_mail(R.box[R.rank], kind, par, lane);
-        const unsigned long long t0 = th_globaltimer();
-        while (th_ld_acquire_sys(&in->seq) != seq) {
-            if (th_globaltimer() - t0 > 20000000000ull) {
-                printf("thallo_b200: rank %d waited 20 s for rank %d (mailbox kind %d, seq %llu): peer lost\n", R.rank, lane, kind, seq);
-                __trap();
-            }
-        }
 #pragma unroll
-        for (int k = 0; k < K; ++k) got[k] = *(volatile double*)&in->v[k];
+        for (int k = 0; k < K; ++k) th_st_pair(&out->q[2 * k], (unsigned long long)__double_as_longlong(v[k]), seq);
+        const ThMail* in = th_mail(R.box[R.rank], kind, par, lane);
+        const unsigned long long t0 = th_globaltimer();
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            unsigned long long bits, sq;
+            for (;;) {
+                th_ld_pair(&in->q[2 * k], bits, sq);
+                if (sq == seq) break;
+                if (th_globaltimer() - t0 > 20000000000ull) {
+                    printf("thallo_b200: rank %d waited 20 s for rank %d (mailbox kind %d, seq %llu): peer lost\n", R.rank, lane, kind, seq);
+                    __trap();
+                }
+            }
+            got[k] = __longlong_as_double((long long)bits);
+        }
+        __threadfence_system();       // acquire: the peers' pushes that preceded their pairs are visible from here on
     }
 #pragma unroll
     for (int k = 0; k < K; ++k) {
@@ -267,22 +279,27 @@ template <int K> __device__ __forceinline__ void th_mail_allreduce(const ThPeers
     }
 }
 // forward a scalar / a real4 chunk just written at flat index f / chunk i of the pushed vector to the neighbours
-__device__ __forceinline__ void th_push_scalar(const ThPush& H, long long f, real val) {
+// (return whether anything was stored: a CTA that pushed fences at system scope before its reduction ticket)
+__device__ __forceinline__ bool th_push_scalar(const ThPush& H, long long f, real val) {
+    bool any = false;
 #pragma unroll
     for (int s = 0; s < 2 * TH_NUM_UIMG; ++s)
-        if (s < H.n && f >= H.lo[s] && f < H.hi[s]) H.dst[s][f - H.lo[s]] = val;
+        if (s < H.n && f >= H.lo[s] && f < H.hi[s]) { H.dst[s][f - H.lo[s]] = val; any = true; }
+    return any;
 }
-__device__ __forceinline__ void th_push_vec4(const ThPush& H, long long i, const real4& val) {
+__device__ __forceinline__ bool th_push_vec4(const ThPush& H, long long i, const real4& val) {
+    bool any = false;
 #pragma unroll
     for (int s = 0; s < 2 * TH_NUM_UIMG; ++s) {
         if (s >= H.n || 4 * i + 3 < H.lo[s] || 4 * i >= H.hi[s]) continue;
-        if (H.vec4[s]) ((real4*)H.dst[s])[i - H.lo[s] / 4] = val;
+        if (H.vec4[s]) { ((real4*)H.dst[s])[i - H.lo[s] / 4] = val; any = true; }
         else {
-            th_push_scalar(H, 4 * i, val.x); th_push_scalar(H, 4 * i + 1, val.y);
-            th_push_scalar(H, 4 * i + 2, val.z); th_push_scalar(H, 4 * i + 3, val.w);
-            return;
+            any = th_push_scalar(H, 4 * i, val.x) | th_push_scalar(H, 4 * i + 1, val.y) |
+                  th_push_scalar(H, 4 * i + 2, val.z) | th_push_scalar(H, 4 * i + 3, val.w);
+            return any;
         }
     }
+    return any;
 }
 #endif
 
@@ -322,7 +339,7 @@ __device__ __forceinline__ real th_beta_prev(const ThScalars* S) {
 // Shared tail of both PCGInit forms: given the gradient entry g (=J^T F) and the true
 // diagonal d (=diag J^T J) of one unknown scalar, produce r, preconditioner, p (and in LM
 // CtC, b, SSq) and return r*p.
-__device__ __forceinline__ real th_init_scalar(const Params& P, const Vecs& V, const ThPush& H, long long off, real g, real d,
+__device__ __forceinline__ real th_init_scalar(const Params& P, const Vecs& V, const ThPush& H, bool& pushed, long long off, real g, real d,
                                                real pre_if_off, int first_nonlinear) {
     const real r = -g;
     real pre = TH_USEPRE ? th_guarded_invert(d) : pre_if_off;
@@ -347,13 +364,13 @@ __device__ __forceinline__ real th_init_scalar(const Params& P, const Vecs& V, c
     V.p[off] = p;
 #endif
 #if TH_MULTI
-    th_push_scalar(H, off, p);      // boundary elements: also into the neighbours' ghost copies
+    pushed |= th_push_scalar(H, off, p);      // boundary elements: also into the neighbours' ghost copies
 #endif
     return r * p;
 }
-__device__ __forceinline__ void th_zero_scalar(const Vecs& V, const ThPush& H, long long off) {
+__device__ __forceinline__ void th_zero_scalar(const Vecs& V, const ThPush& H, bool& pushed, long long off) {
 #if TH_MULTI
-    th_push_scalar(H, off, (real)0);
+    pushed |= th_push_scalar(H, off, (real)0);
 #endif
     V.delta[off] = (real)0; V.r[off] = (real)0; V.pre[off] = (real)0; V.p[off] = (real)0;
     V.z[off] = (real)0; V.Ap[off] = (real)0;

@@ -89,6 +89,7 @@ th_init_uw(const __grid_constant__ Params P, const __grid_constant__ Vecs V, ThS
            const __grid_constant__ ThPeers R, const __grid_constant__ ThPush H) {
     ThIdx<th::dom_uw> idx;
     double acc[1] = {0.0};
+    bool pushed = false;
     const bool inside = th_uw_index(idx);
 #if TH_MULTI
     if (inside && !th_owned_slow(idx.c[th::dom_uw::ND - 1])) {
@@ -112,14 +113,14 @@ th_init_uw(const __grid_constant__ Params P, const __grid_constant__ Vecs V, ThS
 #pragma unroll
             for (int ch = 0; ch < TH_UIMG[k].channels; ++ch, ++j) {
                 const long long off = TH_UIMG[k].offset + idx.lin * TH_UIMG[k].channels + ch;
-                if (ex) th_zero_scalar(V, H, off);
-                else dot += th_init_scalar(P, V, H, off, g[j], d[j], (real)0.25, first_nonlinear);   // d:=1 -> G(1)=0.25, gauss_newton.t:693-696
+                if (ex) th_zero_scalar(V, H, pushed, off);
+                else dot += th_init_scalar(P, V, H, pushed, off, g[j], d[j], (real)0.25, first_nonlinear);   // d:=1 -> G(1)=0.25, gauss_newton.t:693-696
             }
         }
         acc[0] = (double)dot;
     }
     double tot[1];
-    if (th_grid_reduce<1>(acc, tot, partials, &S->ticket[0])) th_init_publish(S, tot, R);
+    if (th_grid_reduce<1>(acc, tot, partials, &S->ticket[0], pushed)) th_init_publish(S, tot, R);
 }
 
 // which = 0: Ap = (JtJ [+CtC]) p with alphaDenominator = <p,Ap>;  which = 1: Adelta = (JtJ [+CtC]) delta
@@ -285,6 +286,7 @@ th_pcg_b(const __grid_constant__ Vecs V, ThScalars* S, double* partials, real q_
     const real* __restrict__ vpre = V.pre;
     const real* __restrict__ vb = V.b;
     double acc[2] = {0.0, 0.0}, accr[2] = {0.0, 0.0};
+    bool pushed = false;
     const long long stride = (long long)gridDim.x * blockDim.x;
     const long long gtid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     auto scalar = [&](long long i) {
@@ -294,7 +296,7 @@ th_pcg_b(const __grid_constant__ Vecs V, ThScalars* S, double* partials, real q_
         const real zv = TH_USEPRE ? vpre[i] * rn : rn;
         vd[i] = dn; vr[i] = rn; vz[i] = zv;
 #if TH_MULTI
-        th_push_scalar(H, i, zv);
+        pushed |= th_push_scalar(H, i, zv);
 #endif
         accr[0] += (double)(zv * rn);
         if (TH_LM) accr[1] += (double)((real)0.5 * (dn * (rn + vb[i])));
@@ -326,7 +328,7 @@ th_pcg_b(const __grid_constant__ Vecs V, ThScalars* S, double* partials, real q_
             ((real4*)vr)[i] = r;
             ((real4*)vz)[i] = zz;
 #if TH_MULTI
-            th_push_vec4(H, i, zz);
+            pushed |= th_push_vec4(H, i, zz);
 #endif
         }
         for (long long i = lo + gtid; i < (v0 * 4 < hi ? v0 * 4 : hi); i += stride) scalar(i);
@@ -335,7 +337,7 @@ th_pcg_b(const __grid_constant__ Vecs V, ThScalars* S, double* partials, real q_
         accr[0] = accr[1] = 0.0;
     }
     double tot[2];
-    if (th_grid_reduce<2>(acc, tot, partials, &S->ticket[2])) th_step2_publish(S, tot, q_tolerance, hf, epoch, R);
+    if (th_grid_reduce<2>(acc, tot, partials, &S->ticket[2], pushed)) th_step2_publish(S, tot, q_tolerance, hf, epoch, R);
 }
 
 extern "C" __global__ void __launch_bounds__(TH_BLOCK)
@@ -371,6 +373,7 @@ th_step2_second(const __grid_constant__ Vecs V, ThScalars* S, double* partials, 
     real* __restrict__ vr = V.r;
     real* __restrict__ vz = V.z;
     double accr[2] = {0.0, 0.0};
+    bool pushed = false;
     auto lane = [&](real delta, real Ax, real ctc, real b, real pre, real& r, real& z) {
         if (add_ctc) Ax += ctc * delta;
         r = b - Ax;
@@ -395,7 +398,7 @@ th_step2_second(const __grid_constant__ Vecs V, ThScalars* S, double* partials, 
                 ((real4*)vr)[i] = r;
                 ((real4*)vz)[i] = z;
 #if TH_MULTI
-                th_push_vec4(H, i, z);
+                pushed |= th_push_vec4(H, i, z);
 #endif
             },
             [&](long long i) {
@@ -404,14 +407,14 @@ th_step2_second(const __grid_constant__ Vecs V, ThScalars* S, double* partials, 
                 vr[i] = r;
                 vz[i] = z;
 #if TH_MULTI
-                th_push_scalar(H, i, z);
+                pushed |= th_push_scalar(H, i, z);
 #endif
             });
         if (th_range_counted(k)) { acc[0] += accr[0]; acc[1] += accr[1]; }     // a replicated range counts on one rank only
         accr[0] = accr[1] = 0.0;
     }
     double tot[2];
-    if (th_grid_reduce<2>(acc, tot, partials, &S->ticket[2])) th_step2_publish(S, tot, q_tolerance, hf, epoch, R);
+    if (th_grid_reduce<2>(acc, tot, partials, &S->ticket[2], pushed)) th_step2_publish(S, tot, q_tolerance, hf, epoch, R);
 }
 
 // PCGStep3 of the untiled schedules: beta = rz_new/rz_old; p = z + beta p; closes the iteration.
@@ -876,16 +879,17 @@ extern "C" __global__ void __launch_bounds__(TH_BLOCK)
 th_init_finish(const __grid_constant__ Params P, const __grid_constant__ Vecs V, ThScalars* S, double* partials, int first_nonlinear,
                const __grid_constant__ ThPeers R, const __grid_constant__ ThPush H) {
     double acc[1] = {0.0};
+    bool pushed = false;
     for (long long f = (long long)blockIdx.x * blockDim.x + threadIdx.x; f < TH_NUNK; f += (long long)gridDim.x * blockDim.x) {
         // ghost entries (graph partition) are the owner's to initialise, p arrives by its push; delta is maintained
         // locally (th_pcg_b) and restarts from zero
         if (!th_flat_owned(f)) { V.delta[f] = (real)0; continue; }
-        if (th_excluded(f, P)) { th_zero_scalar(V, H, f); continue; }
-        const real rp = th_init_scalar(P, V, H, f, -V.r[f], V.pre[f], (real)1, first_nonlinear);   // pre := 1 when off, gauss_newton.t:718-722
+        if (th_excluded(f, P)) { th_zero_scalar(V, H, pushed, f); continue; }
+        const real rp = th_init_scalar(P, V, H, pushed, f, -V.r[f], V.pre[f], (real)1, first_nonlinear);   // pre := 1 when off, gauss_newton.t:718-722
         if (th_flat_counted(f)) acc[0] += (double)rp;
     }
     double tot[1];
-    if (th_grid_reduce<1>(acc, tot, partials, &S->ticket[0])) th_init_publish(S, tot, R);
+    if (th_grid_reduce<1>(acc, tot, partials, &S->ticket[0], pushed)) th_init_publish(S, tot, R);
 }
 
 // which = 0: finish Ap (LM: += CtC p) and alphaDenominator; which = 1: only mask Adelta

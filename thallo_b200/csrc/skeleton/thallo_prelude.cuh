@@ -86,7 +86,7 @@ struct ThHostFlags { long long progress; long long exit_word; };
 // Boundary layers of z / p are stored straight into the neighbours' ghost layers by the kernel that computes
 // them (ThPush), ordered before the mailbox flag by a system-scope fence.
 #define TH_MAXRANKS 16
-struct ThMail { double v[2]; unsigned long long seq; unsigned long long pad; };
+struct ThMail { unsigned long long q[4]; };       // two (value bits, sequence number) pairs, each written with ONE 16-byte store
 enum { TH_MAIL_A = 0, TH_MAIL_B = 1, TH_MAIL_INIT = 2, TH_MAIL_KINDS = 4 };
 #define TH_MAIL_BYTES (TH_MAIL_KINDS * 2 * TH_MAXRANKS * (int)sizeof(ThMail))
 struct ThPeers {

@@ -233,6 +233,9 @@ int ThalloB200_PlanConnectGraph(Thallo_State*, Thallo_Plan* plan, const void* ha
                                 const void* handle_hi, long long extent_hi, long long width_hi) {
     return plan ? plan->plan->connect_graph(handle_lo, extent_lo, width_lo, handle_hi, extent_hi, width_hi) : 1;
 }
+void* ThalloB200_PlanVectorPointer(Thallo_State*, Thallo_Plan* plan, const char* name) {
+    return plan && name ? plan->plan->vector_pointer(name) : nullptr;
+}
 int ThalloB200_PlanPeerInfo(Thallo_State*, Thallo_Plan* plan, long long* info4) {
     return plan && info4 ? plan->plan->peer_info(info4) : 1;
 }

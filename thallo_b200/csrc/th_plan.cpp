@@ -1106,6 +1106,12 @@ long long Plan::read_vector(const char* name, void* dst, long long count) {
     return 0;
 }
 
+void* Plan::vector_pointer(const char* name) {
+    for (int i = 0; i < kNumVecs; ++i)
+        if (strcmp(name, kVecNames[i]) == 0) return vecs_[i];
+    return nullptr;
+}
+
 // The Jacobian of one residual group at the current unknowns, as the reference materialises it (generateDumpJ,
 // gauss_newton.t:325-487): per residual element its rows term by term, row k holding row_nnz[k] (value, column)
 // pairs; column = flat index of the unknown scalar (imageOffset + channels*idx + ch) or -1 outside the domain.

@@ -94,7 +94,7 @@ struct HScalars {
 struct HHostFlags { volatile long long progress; volatile long long exit_word; };
 // multi-GPU peer memory (mirrors ThMail / ThPeers in skeleton/thallo_prelude.cuh)
 constexpr int kMaxRanks = 16, kMailKinds = 4;
-struct HMail { double v[2]; unsigned long long seq, pad; };
+struct HMail { unsigned long long q[4]; };
 constexpr size_t kMailBytes = (size_t)kMailKinds * 2 * kMaxRanks * sizeof(HMail);
 struct HPeers { void* box[kMaxRanks]; int rank, world, fused, epoch; };
 
@@ -113,6 +113,7 @@ public:
     void get_parameter(const char* name, void* value);
     void summary(Thallo_PerformanceSummary* s) const { *s = perf_; }
     long long read_vector(const char* name, void* dst, long long count);
+    void* vector_pointer(const char* name);
     long long export_jacobian(int group, void* host_vals, long long* host_cols, long long capacity);
     // multi-GPU (include/thallo_b200.h "slab partition")
     int comm_init(const void* nccl_id, int rank, int world);

@@ -285,3 +285,115 @@ def sfs_fixture_inputs(path):
                 u_x=float(z["u_x"]), u_y=float(z["u_y"]), light=[float(x) for x in z["light"]],
                 X=z["X"].astype(np.float32), D_i=z["D_i"].astype(np.float32), Im=z["Im"].astype(np.float32),
                 edgeMaskR=z["edgeMaskR"].astype(np.uint8), edgeMaskC=z["edgeMaskC"].astype(np.uint8)), int(z["W"]), int(z["H"])
+
+
+# ---------------------------------------------------------------------------------------------------
+# Device-side generators for the configured FULL sizes (8192^2 images, 25 M observations): the same synthetic shapes
+# as above, written in torch so that a 67 M-pixel field takes milliseconds on the GPU instead of a minute of NumPy
+# per rank.  Every field is a pure function of the absolute element coordinates (and a seed), so a rank of a
+# partitioned solve generates just its rows [y0, y1) and gets the same numbers a single-GPU run sees there.
+def _hash01(t, x, y, seed):
+    """Deterministic uniform(0, 1) field of the integer coordinates (float64 sine hash)."""
+    v = t.sin(x * 12.9898 + y * 78.233 + seed * 37.719) * 43758.5453
+    return v - t.floor(v)
+
+
+def optical_flow_inputs_torch(W, H, device, rows=None, seed=1, w_fit=10.0, w_reg=0.1):
+    """optical_flow_inputs on `device`, restricted to rows [y0, y1) of the W x H image (default: all)."""
+    import torch as t
+    y0, y1 = rows if rows is not None else (0, H)
+    ys = t.arange(y0 - 1, y1 + 1, device=device, dtype=t.float64)[:, None]
+    xs = t.arange(-1, W + 1, device=device, dtype=t.float64)[None, :]
+    r = np.random.RandomState(seed + 7)
+    coef = [(tuple(r.uniform(-0.35, 0.35, 2)), r.uniform(0, 2 * np.pi), r.uniform(0.2, 1.0)) for _ in range(16)]
+
+    def tex(x, y):
+        out = t.zeros((ys.shape[0], xs.shape[1]), device=device, dtype=t.float64)
+        for (fx, fy), ph, am in coef:
+            out += am * t.sin(fx * x + fy * y + ph)
+        return out / 8.0 + 0.5
+    I = tex(xs, ys)[1:-1, 1:-1]
+    Ihp = tex(xs + 0.6, ys - 0.4)                         # rows y0-1 .. y1, columns -1 .. W
+    Ih = Ihp[1:-1, 1:-1]
+    dx = (-Ihp[:-2, :-2] - Ihp[1:-1, :-2] - Ihp[2:, :-2] + Ihp[:-2, 2:] + Ihp[1:-1, 2:] + Ihp[2:, 2:]) / 8.0
+    dy = (-Ihp[:-2, :-2] - Ihp[:-2, 1:-1] - Ihp[:-2, 2:] + Ihp[2:, :-2] + Ihp[2:, 1:-1] + Ihp[2:, 2:]) / 8.0
+    yy = t.arange(y0, y1, device=device)[:, None]
+    xx = t.arange(0, W, device=device)[None, :]
+    border = (yy == 0) | (yy == H - 1) | (xx == 0) | (xx == W - 1)       # zero border of the derivative images
+    dx = t.where(border, t.zeros_like(dx), dx)
+    dy = t.where(border, t.zeros_like(dy), dy)
+    f = lambda a: a.reshape(-1).to(t.float32).contiguous()
+    n = (y1 - y0) * W
+    return dict(w_fitSqrt=np.float32(np.sqrt(w_fit)), w_regSqrt=np.float32(np.sqrt(w_reg)),
+                X=t.zeros((n, 2), device=device, dtype=t.float32), I=f(I), I_hat_im=f(Ih), I_hat_dx=f(dx), I_hat_dy=f(dy))
+
+
+def sfs_inputs_torch(W, H, device, rows=None, seed=1, w_p=100.0, w_s=100.0, w_g=1.0):
+    """sfs_inputs on `device`, rows [y0, y1) (the seeded depth noise is a coordinate hash instead of a NumPy stream)."""
+    import torch as t
+    y0, y1 = rows if rows is not None else (0, H)
+    ys = t.arange(y0, y1, device=device, dtype=t.float64)[:, None]
+    xs = t.arange(0, W, device=device, dtype=t.float64)[None, :]
+    u, v = (xs - W / 2.0) / (W / 2.0), (ys - H / 2.0) / (H / 2.0)
+    r2 = u * u + v * v
+    depth = 0.5 - 0.08 * t.sqrt(t.clamp(1.0 - t.clamp(r2, max=1.0), min=0.0))
+    depth = depth + 0.0005 * t.sin(0.37 * xs + 0.11 * ys) * t.cos(0.23 * ys - 0.05 * xs)
+    valid = r2 < 0.81
+    bad = t.full_like(depth, -10000.0)
+    D = t.where(valid, depth, bad)
+    noise = (_hash01(t, xs, ys, seed) + _hash01(t, xs, ys, seed + 1) + _hash01(t, xs, ys, seed + 2) - 1.5) * 2.0     # ~N(0, 1)
+    X0 = t.where(valid, depth + 0.0008 * noise, bad)
+    Im = 0.5 + 0.2 * t.sin(0.05 * xs + 0.02 * ys) + 0.15 * t.cos(0.031 * ys - 0.017 * xs) + 0.05 * t.sin(0.4 * xs) * t.sin(0.3 * ys)
+    f = lambda a: a.reshape(-1).to(t.float32).contiguous()
+    light = [0.6908317804336548, 0.044598858803510666, 0.01812959648668766, -0.1773163229227066, -0.04067882522940636,
+             0.14467650651931763, 0.02393525093793869, -0.24658696353435516, 0.005797004792839289]
+    n = (y1 - y0) * W
+    return dict(w_p=w_p, w_s=w_s, w_g=w_g, f_x=float(W), f_y=float(W), u_x=W / 2.0, u_y=H / 2.0, light=light,
+                X=f(X0), D_i=f(D), Im=f(Im), edgeMaskR=t.ones(n, device=device, dtype=t.uint8),
+                edgeMaskC=t.ones(n, device=device, dtype=t.uint8))
+
+
+def bundle_adjustment_inputs_torch(C, P, device, obs_per_point=5, seed=1, noise_px=0.5, perturb=0.01):
+    """bundle_adjustment_inputs on `device` (torch's generator instead of NumPy's: same shapes and distributions)."""
+    import torch as t
+    g = t.Generator(device=device)
+    g.manual_seed(seed)
+    k = int(obs_per_point)
+    assert C >= k
+    f64 = dict(device=device, dtype=t.float64)
+    rn = lambda *s: t.randn(*s, generator=g, **f64)
+    theta = 2.0 * np.pi * t.arange(C, **f64) / C
+    cams = t.zeros((C, 9), **f64)
+    cams[:, 1] = theta
+    cams[:, 0] = 0.05 * rn(C)
+    cams[:, 2] = 0.05 * rn(C)
+    cams[:, 3:5] = 0.1 * rn(C, 2)
+    cams[:, 5] = -5.0
+    cams[:, 6] = 800.0 + 20.0 * rn(C)
+    cams[:, 7] = 1e-2 * rn(C)
+    cams[:, 8] = 1e-3 * rn(C)
+    pts = t.rand((P, 3), generator=g, **f64) * 2.0 - 1.0
+    base = t.randint(0, C, (P,), generator=g, device=device)
+    steps = 1 + t.randint(0, max(1, (C - 1) // k), (P, k), generator=g, device=device)
+    steps[:, 0] = 0
+    cam_of = t.sort((base[:, None] + t.cumsum(steps, 1)) % C, 1).values
+    o2c = cam_of.reshape(-1).to(t.int32).contiguous()
+    o2p = t.arange(P, device=device, dtype=t.int32).repeat_interleave(k).contiguous()
+    cam = cams[o2c.long()]
+    X = pts[o2p.long()]
+    aa = cam[:, 0:3]
+    th2 = (aa * aa).sum(-1, keepdim=True)
+    th = t.sqrt(t.clamp(th2, min=1e-30))
+    w = aa / th
+    c, s = t.cos(th), t.sin(th)
+    large = X * c + t.linalg.cross(w, X) * s + w * ((w * X).sum(-1, keepdim=True) * (1.0 - c))
+    small = X + t.linalg.cross(aa, X)
+    p = t.where(th2 > 1e-8, large, small) + cam[:, 3:6]
+    cod = -p[:, 0:2] / p[:, 2:3]
+    r2 = (cod * cod).sum(-1, keepdim=True)
+    obs = cod * cam[:, 6:7] * (1.0 + r2 * (cam[:, 7:8] + cam[:, 8:9] * r2))
+    obs = obs + noise_px * rn(*obs.shape)
+    cams0 = cams * (1.0 + perturb * rn(*cams.shape))
+    pts0 = pts + perturb * rn(*pts.shape)
+    return dict(cameras=cams0.to(t.float32).contiguous(), points=pts0.to(t.float32).contiguous(),
+                observations=obs.to(t.float32).contiguous(), oToC=o2c, oToP=o2p)
