@@ -366,6 +366,14 @@ def headline_parity(cx, a, case, costs, lin, reset):
         rec = compare_trajectories(costs[:n], lin, r["costs"][:n], r["n_lin"],
                                    "oracle/iw_cpu.c (plain-C restatement of the reference cpuOnly path, float64 accumulation), "
                                    "full %dx%d LM solve" % (S, S))
+        # float32 noise floor of this truncated-PCG trajectory: the same restatement with float accumulation of the dot
+        # products (the reference's own arithmetic) against its float64-accumulation twin
+        r32 = iw_cpu.solve(S, S, wl.image_warping_inputs(S, S), "levenberg_marquardt", acc64=False, nIterations=case.nit, lIterations=case.lit)
+        m = min(n, len(r32["costs"]))
+        rec["per_cost_rel"] = [abs(a_ - b_) / abs(b_) for a_, b_ in zip(costs[:n], r["costs"][:n])]
+        rec["oracle_float32_vs_float64_accumulation_rel"] = [abs(a_ - b_) / abs(b_) for a_, b_ in zip(r32["costs"][:m], r["costs"][:m])]
+        rec["oracle_float32_pcg_counts"] = r32["n_lin"]
+        rec["first_step_rel"] = rec["per_cost_rel"][1] if n > 1 else None
         rec["oracle_seconds"] = round(time.time() - t0, 1)
     return rec
 

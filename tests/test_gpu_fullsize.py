@@ -49,10 +49,17 @@ def test_headline_solve_matches_the_c_restatement_of_the_reference_cpu_path():
     s.close()
     W, H = case.dims
     r = iw_cpu.solve(W, H, wl.image_warping_inputs(W, H), "levenberg_marquardt", acc64=True, nIterations=case.nit, lIterations=case.lit)
+    r32 = iw_cpu.solve(W, H, wl.image_warping_inputs(W, H), "levenberg_marquardt", acc64=False, nIterations=case.nit, lIterations=case.lit)
     assert lin == r["n_lin"][:len(lin)], (lin, r["n_lin"])
     assert len(costs) <= len(r["costs"])
-    for i, (a, c) in enumerate(zip(costs, r["costs"])):
-        assert abs(a - c) <= 1e-5 * abs(c), (i, a, c)
+    # 100 PCG iterations per nonlinear step on 4 M pixels, far from convergence: float32 rounding differences are amplified
+    # from step to step.  Tolerance rule of tests/_parity.py: 1e-5, or NOISE_FACTOR x the distance between the float32 and the
+    # float64-accumulating restatement at that step; the first steps (before amplification) must hold the plain rule.
+    from _parity import assert_costs_close
+    n = len(costs)
+    assert_costs_close(costs, r["costs"][:n], 1e-5, 1e-3, cref64=r32["costs"][:n])
+    for i in range(min(3, n)):
+        assert abs(costs[i] - r["costs"][i]) <= 1e-5 * abs(r["costs"][i]), (i, costs[i], r["costs"][i])
 
 
 @pytest.mark.parametrize("key", ["2", "4b"])

@@ -520,6 +520,7 @@ void Plan::launch(CUfunction f, dim3 grid, dim3 block, void** args, unsigned sme
     if (timed) {
         if (!event_pool_.empty()) { s = event_pool_.back(); event_pool_.pop_back(); }
         else { CD(cudaEventCreate(&s.a)); CD(cudaEventCreate(&s.b)); }
+        s.tag = cur_tag_; s.epoch = epoch_;
         CD(cudaEventRecord(s.a, stream()));
     }
     CU(DriverApi::get().LaunchKernel(f, grid.x, grid.y, grid.z, block.x, block.y, block.z, smem, (CUstream)stream(), args, nullptr));
@@ -534,13 +535,20 @@ void Plan::launch(CUfunction f, dim3 grid, dim3 block, void** args, unsigned sme
 void Plan::resolve_kernel_events() {
     CD(cudaStreamSynchronize(stream()));
     for (auto& k : kstats_) {
+        std::vector<Span> keep;
         for (auto& s : k.pending) {
+            if (s.tag >= 0) {
+                auto it = epoch_lin_done_.find(s.epoch);
+                if (it == epoch_lin_done_.end()) { keep.push_back(s); continue; }       // step still running: decide later
+                if (s.tag >= it->second) { event_pool_.push_back(s); continue; }        // issued after the device's exit: a no-op
+            }
             float t = 0;
             if (cudaEventElapsedTime(&t, s.a, s.b) == cudaSuccess) { k.ms += t; ++k.count; }
             event_pool_.push_back(s);
         }
-        k.pending.clear();
+        k.pending.swap(keep);
     }
+    while (epoch_lin_done_.size() > 64) epoch_lin_done_.erase(epoch_lin_done_.begin());
 }
 std::string Plan::kernel_times() {
     resolve_kernel_events();
@@ -982,8 +990,10 @@ int Plan::step(void** params) {
             }
             if (stop) break;
         }
+        cur_tag_ = l;
         linear_iteration(l);
     }
+    cur_tag_ = -1;
     span_end(cur_phase_, ev_linear_);
     span_begin(cur_phase_);
     int zero = 0;
@@ -1012,6 +1022,7 @@ int Plan::step(void** params) {
         const double new_cost = compute_cost();   // also brings modelcost and lin_done back
         last_linear_iterations = h_scalars_->lin_done;
         total_linear_iterations += (unsigned long long)h_scalars_->lin_done;
+        epoch_lin_done_[epoch_] = h_scalars_->lin_done;
         const double model_cost = round_real(h_scalars_->modelcost);
         const double model_cost_change = round_real(prev_cost_ - model_cost);
         const double cost_change = round_real(prev_cost_ - new_cost);
@@ -1053,6 +1064,7 @@ int Plan::step(void** params) {
     } else {
         last_linear_iterations = sp_.lIterations;
         total_linear_iterations += (unsigned long long)sp_.lIterations;
+        epoch_lin_done_[epoch_] = sp_.lIterations;
     }
     sp_.nIter += 1;
     span_end(cur_phase_, ev_finish_);

@@ -222,7 +222,12 @@ private:
     Thallo_PerformanceSummary perf_{};
     std::chrono::steady_clock::time_point t_start_;
 
-    struct Span { cudaEvent_t a = nullptr, b = nullptr; };
+    // tag >= 0: launched for PCG iteration `tag` of nonlinear step `epoch`.  The host issues up to `depth` iterations
+    // ahead of the device's LM exit decision; launches for iterations the device had already left return at once and
+    // are kept out of the per-kernel statistics (they would deflate the average launch time).
+    struct Span { cudaEvent_t a = nullptr, b = nullptr; int tag = -1, epoch = 0; };
+    int cur_tag_ = -1;
+    std::map<int, int> epoch_lin_done_;
     struct KernelStat { std::string name; unsigned long long count = 0; double ms = 0; std::vector<Span> pending; };
     std::map<CUfunction, int> kstat_index_;
     std::vector<KernelStat> kstats_;
