@@ -25,6 +25,17 @@ def _check(name, dims, params, kw=None):
     assert np.abs(g - g0).max() <= 1e-10 * sc
     assert np.abs(d - d0).max() <= 1e-10 * max(1.0, d0.max())
     assert np.abs(out - o0).max() <= 1e-10 * max(1.0, np.abs(o0).max())
+    if gen.tiled:
+        # the two-phase form of the tile operator (J p per residual position first, then the transposed products)
+        import os
+        os.environ["THALLO_B200_TWO_PHASE"] = "1"
+        try:
+            gen2 = codegen.lower(energies.load(name), dims, "gauss_newton", name, True, "at_output", **(kw or {})).generator
+        finally:
+            os.environ.pop("THALLO_B200_TWO_PHASE")
+        assert gen2.two_phase
+        out2 = interp.unknownwise_two_phase(gen2, params, p)
+        assert np.abs(out2 - o0).max() <= 1e-10 * max(1.0, np.abs(o0).max())
 
 
 def test_laplacian_at_output_matches_oracle():

@@ -137,3 +137,57 @@ def test_shape_from_shading_synthetic_f64():
     s, c, lin, dp = _trajectory_gpu("shape_from_shading", [W, H], "gauss_newton", _sfs_params(d, np.float64), range(16, 21), np.float64, 4, 10)
     _close(c, cref, 1e-10, 1e-6)
     assert cref[-1] < cref[0]
+
+
+# ---- the two variants of the tile operator (shifted-instance form / two-phase form with J p in shared memory) and the
+# two specialisations of each (edge tiles with bounds predicates / interior tiles without): same operator, so the same
+# float64 trajectory to 1e-10 and the oracle's float32 trajectory to the usual tolerance, on domains with partial tiles
+# (edge variant only), and on domains large enough to contain interior tiles
+@pytest.mark.parametrize("two_phase", ["0", "1"])
+@pytest.mark.parametrize("case", ["sfs", "volume", "image_warping", "optical_flow"])
+def test_tile_operator_variants_match_oracle_f64(case, two_phase):
+    if case == "sfs":
+        W, H = 150, 61
+        name, dims, kind, slots, nit, lit = "shape_from_shading", [W, H], "gauss_newton", range(16, 21), 3, 10
+        mk = lambda: _sfs_params(wl.sfs_inputs(W, H), np.float64)
+    elif case == "volume":
+        name, dims, kind, slots, nit, lit = "volumetric_mesh_deformation", [28, 27, 14], "gauss_newton", range(4), 2, 15
+        mk = lambda: [np.array(p, np.float64) if np.asarray(p).size > 1 else p for p in wl.volumetric_params(wl.volumetric_inputs(28, 27, 14))]
+    elif case == "image_warping":
+        name, dims, kind, slots, nit, lit = "image_warping", [136, 60], "levenberg_marquardt", range(5), 3, 20
+        mk = lambda: _iw_params(136, 60, np.float64)
+    else:
+        name, dims, kind, slots, nit, lit = "optical_flow", [132, 52], "gauss_newton", range(2, 7), 2, 20
+        mk = lambda: [np.array(p, np.float64) if np.asarray(p).size > 1 else p for p in wl.optical_flow_params(wl.optical_flow_inputs(132, 52))]
+    o, cref = _trajectory_oracle(name, dims, kind, mk(), np.float64, nit, lit)
+    os.environ["THALLO_B200_TWO_PHASE"] = two_phase
+    try:
+        s, c, lin, dp = _trajectory_gpu(name, dims, kind, mk(), slots, np.float64, nit, lit)
+    finally:
+        os.environ.pop("THALLO_B200_TWO_PHASE", None)
+    assert bool(s.lowered.generator.two_phase) == (two_phase == "1")
+    _close(c, cref, 1e-10, 1e-6)
+    if kind == "levenberg_marquardt":
+        assert lin == [it["n_lin"] for it in o.trace][:len(lin)]
+
+
+@pytest.mark.parametrize("case", ["sfs", "volume"])
+def test_interior_tile_specialisation_is_bit_identical(case):
+    """Interior tiles drop the bounds predicates (they are all true there): the arithmetic is unchanged."""
+    outs = []
+    for always_edge in (False, True):
+        if always_edge:
+            os.environ["THALLO_B200_EDGE_ALWAYS"] = "1"
+        try:
+            if case == "sfs":
+                W, H = 150, 61
+                s, c, lin, dp = _trajectory_gpu("shape_from_shading", [W, H], "gauss_newton", _sfs_params(wl.sfs_inputs(W, H), np.float32),
+                                                range(16, 21), np.float32, 3, 10)
+                outs.append((c, dp[16].cpu().numpy().tobytes()))
+            else:
+                p = wl.volumetric_params(wl.volumetric_inputs(28, 27, 14))
+                s, c, lin, dp = _trajectory_gpu("volumetric_mesh_deformation", [28, 27, 14], "gauss_newton", p, range(4), np.float32, 2, 15)
+                outs.append((c, dp[0].cpu().numpy().tobytes()))
+        finally:
+            os.environ.pop("THALLO_B200_EDGE_ALWAYS", None)
+    assert outs[0] == outs[1]

@@ -552,7 +552,9 @@ __device__ __forceinline__ void th_tile_load_es(void* dst, const void* src, int 
 // is read at the element itself straight from global memory.  With UPD the vector argument is the
 // new search direction p = z + beta p_old, formed on the fly from the z and p_old tiles
 // (PCGStep3 fused into the operator; fma() so that every tap and the stored p_new agree bit for bit).
-template <class Dom, bool UPD> struct TAcc {
+// EDGE = false: the tile lies far enough inside the domain (TH_INB_R* elements) that every bounds predicate of the
+// generated code is true; they then fold away at compile time together with the selects they guard.
+template <class Dom, bool UPD, bool EDGE = true> struct TAcc {
     ThIdx<Dom> i;
     const unsigned char* sm;
     int tx, ty, tz;
@@ -561,6 +563,7 @@ template <class Dom, bool UPD> struct TAcc {
         : i(idx), sm(s), tx(x), ty(y), tz(z), beta(b) {}
     template <int D> __device__ __forceinline__ int coord() const { return i.c[D]; }
     template <int L0, int H0, int L1, int H1, int L2, int H2> __device__ __forceinline__ bool inb() const {
+        if (!EDGE) return true;
         bool ok = true;
         if (L0 < 0) ok = ok && (i.c[0] + L0 >= 0);
         if (H0 > 0) ok = ok && (i.c[0] + H0 < Dom::D0);
@@ -684,7 +687,21 @@ __device__ __forceinline__ void th_tile_fill(unsigned char* sm, const Params& P,
 }
 
 // operator applied to one tile from shared-memory stage `sm`; returns this thread's <p, Ap> contribution
-template <bool UPD>
+#ifndef TH_INB_RX
+#define TH_INB_RX 1000000
+#define TH_INB_RY 1000000
+#define TH_INB_RZ 1000000
+#endif
+// does any bounds predicate of the generated code possibly fail on this tile (or on the positions around it)?
+__device__ __forceinline__ bool th_tile_is_edge(int t) {
+    int x0, y0, z0;
+    th_tile_origin(t, x0, y0, z0);
+    bool e = x0 - TH_INB_RX < 0 || x0 + TH_TW + TH_INB_RX > th::dom_uw::D0;
+    e = e || y0 - TH_INB_RY < 0 || y0 + TH_TH + TH_INB_RY > th::dom_uw::D1;
+    if (th::dom_uw::ND > 2) e = e || z0 - TH_INB_RZ < 0 || z0 + TH_TD + TH_INB_RZ > th::dom_uw::D2;
+    return e;
+}
+template <bool UPD, bool EDGE>
 __device__ __forceinline__ real th_tile_apply(const unsigned char* sm, const Params& P, const Vecs& V, int t, int mode, real beta,
                                               real* __restrict__ out, real* __restrict__ pnew, int tx, int ty, int tz) {
     int x0, y0, z0;
@@ -692,7 +709,7 @@ __device__ __forceinline__ real th_tile_apply(const unsigned char* sm, const Par
     ThIdx<th::dom_uw> idx;
     real dot = (real)0;
     if (idx.from_coords(x0 + tx, y0 + ty, z0 + tz)) {
-        TAcc<th::dom_uw, UPD> a(idx, sm, tx, ty, tz, beta);
+        TAcc<th::dom_uw, UPD, EDGE> a(idx, sm, tx, ty, tz, beta);
 #if TH_MULTI
         if (!th_owned_slow(idx.c[th::dom_uw::ND - 1])) {
             // ghost layer: the owner computes Ap there; this rank only keeps its copy of the search
@@ -737,6 +754,109 @@ __device__ __forceinline__ real th_tile_apply(const unsigned char* sm, const Par
     }
     return dot;
 }
+
+#ifndef TH_TWO_PHASE
+#define TH_TWO_PHASE 0
+#endif
+#if TH_TWO_PHASE
+// Two-phase form of the tile operator (front end: Generator.gen_two_phase): J p of every residual term is formed ONCE
+// per residual position into shared-memory planes (phase 1: the tile's own positions, and the positions around the
+// tile whose residuals reach into it -- only the term classes that do), then every unknown multiplies its partial
+// derivative of each residual instance with the stored value (phase 2).  The Jt[Jp] schedule of the reference
+// (PCGStep1_J / PCGStep1_Jt, gauss_newton.t:1027-1047) with J p living in shared memory instead of HBM.
+#define TH_JP_BX (TH_TW + 2 * TH_JP_PHX)
+#define TH_JP_BY (TH_TH + 2 * TH_JP_PHY)
+#define TH_JP_BZ (TH_TD + 2 * TH_JP_PHZ)
+#define TH_JP_NBOX (TH_JP_BX * TH_JP_BY * TH_JP_BZ)
+#define TH_JP_BYTES (TH_JP_NT * TH_JP_NBOX * (int)sizeof(real))
+// halo positions relative to the tile origin: (dx + 8) | (dy + 8) << 4 | (dz + 8) << 8 | class mask << 16
+__device__ const unsigned int TH_JP_POS[TH_JP_NHALO > 0 ? TH_JP_NHALO : 1] = TH_JP_POS_TABLE;
+struct ThJp {
+    real* buf;
+    int tx, ty, tz;
+    static __device__ __forceinline__ int box(int x, int y, int z) {
+        return ((z + TH_JP_PHZ) * TH_JP_BY + (y + TH_JP_PHY)) * TH_JP_BX + (x + TH_JP_PHX);
+    }
+    template <int T, int S0, int S1, int S2> __device__ __forceinline__ real at() const {
+        return buf[T * TH_JP_NBOX + box(tx + S0, ty + S1, tz + S2)];
+    }
+    template <int T> __device__ __forceinline__ void put(real v) { buf[T * TH_JP_NBOX + box(tx, ty, tz)] = v; }
+    __device__ __forceinline__ void sync() { __syncthreads(); }
+};
+template <bool UPD, bool EDGE>
+__device__ __forceinline__ real th_tile_apply2(const unsigned char* sm, real* jpbuf, const Params& P, const Vecs& V, int t, int mode, real beta,
+                                               real* __restrict__ out, real* __restrict__ pnew, int tx, int ty, int tz) {
+    int x0, y0, z0;
+    th_tile_origin(t, x0, y0, z0);
+    const int tid = tx + TH_TW * (ty + TH_TH * tz);
+    __syncthreads();                                   // the previous tile's phase 2 has read its planes
+    // phase 1, positions around the tile
+    for (int q = tid; q < TH_JP_NHALO; q += TH_TILE_THREADS) {
+        const unsigned int e = __ldg(&TH_JP_POS[q]);
+        const int dx = (int)(e & 15u) - 8, dy = (int)((e >> 4) & 15u) - 8, dz = (int)((e >> 8) & 15u) - 8;
+        real jp[TH_JP_NT];
+#pragma unroll
+        for (int k = 0; k < TH_JP_NT; ++k) jp[k] = (real)0;
+        ThIdx<th::dom_uw> idx;
+        if (x0 + dx >= 0 && y0 + dy >= 0 && z0 + dz >= 0 && idx.from_coords(x0 + dx, y0 + dy, z0 + dz)) {
+            TAcc<th::dom_uw, UPD, EDGE> a(idx, sm, dx, dy, dz, beta);
+            th::applyJ_halo(a, P, e >> 16, jp);
+        }
+        const int b = ThJp::box(dx, dy, dz);
+#pragma unroll
+        for (int k = 0; k < TH_JP_NT; ++k) jpbuf[k * TH_JP_NBOX + b] = jp[k];
+    }
+    // phase 1 of the element itself, barrier, phase 2 (threads outside the domain take part with the tile's first
+    // element and publish zeros, so that every thread reaches the barrier)
+    ThIdx<th::dom_uw> idx;
+    const bool inside = idx.from_coords(x0 + tx, y0 + ty, z0 + tz);
+    if (!inside) idx.from_coords(x0, y0, z0);
+    TAcc<th::dom_uw, UPD, EDGE> a(idx, sm, inside ? tx : 0, inside ? ty : 0, inside ? tz : 0, beta);
+    ThJp J{jpbuf, tx, ty, tz};
+    real o[TH_U];
+    th::applyJTJ_tile(a, P, J, inside, o);
+    real dot = (real)0;
+    if (!inside) return dot;
+#if TH_MULTI
+    if (!th_owned_slow(idx.c[th::dom_uw::ND - 1])) {       // ghost layer: keep the local copy of the search direction current
+        if (mode == 0) {
+#pragma unroll
+            for (int k = 0; k < TH_NUM_UIMG; ++k) {
+                const int te = a.template tile_elem<0, 0, 0>(TH_VTILE[k].roww, TH_VTILE[k].padl, TH_UIMG[k].channels);
+#pragma unroll
+                for (int ch = 0; ch < TH_UIMG[k].channels; ++ch)
+                    pnew[TH_UIMG[k].offset + idx.lin * TH_UIMG[k].channels + ch] = a.vec_at(k, te + ch);
+            }
+        }
+        return dot;
+    }
+#endif
+    if (!th::exclude_u0(a, P)) {
+        int j = 0;
+#pragma unroll
+        for (int k = 0; k < TH_NUM_UIMG; ++k) {
+            const int te = a.template tile_elem<0, 0, 0>(TH_VTILE[k].roww, TH_VTILE[k].padl, TH_UIMG[k].channels);
+#pragma unroll
+            for (int ch = 0; ch < TH_UIMG[k].channels; ++ch, ++j) {
+                const long long off = TH_UIMG[k].offset + idx.lin * TH_UIMG[k].channels + ch;
+                const real pv = a.vec_at(k, te + ch);
+                real val = o[j];
+#if TH_LM
+#if TH_STAGE_CTC
+                val += ((const real*)(sm + TH_VTILE[k].coff))[a.center_elem(TH_VTILE[k].croww, TH_UIMG[k].channels) + ch] * pv;
+#else
+                val += V.CtC[off] * pv;
+#endif
+#endif
+                out[off] = val;
+                if (mode == 0) pnew[off] = pv;
+                dot += pv * val;
+            }
+        }
+    }
+    return dot;
+}
+#endif
 
 template <bool TMA>
 __device__ __forceinline__ void th_pcg_a_impl(const Params& P, const Vecs& V, const ThMaps& M, ThScalars* S, double* partials, int mode,
@@ -786,8 +906,20 @@ __device__ __forceinline__ void th_pcg_a_impl(const Params& P, const Vecs& V, co
             th_tile_fill(sm, P, V, t, mode, it, tid);
             __syncthreads();
         }
-        const real dot = upd ? th_tile_apply<true>(sm, P, V, t, mode, beta, out, pnew, tx, ty, tz)
-                             : th_tile_apply<false>(sm, P, V, t, mode, beta, out, pnew, tx, ty, tz);
+        const bool edge = th_tile_is_edge(t);          // uniform over the CTA
+        real dot;
+#if TH_TWO_PHASE
+        real* jpbuf = (real*)(th_sm + (TMA ? TH_PIPE : 1) * TH_SMEM_BYTES);
+        if (edge) dot = upd ? th_tile_apply2<true, true>(sm, jpbuf, P, V, t, mode, beta, out, pnew, tx, ty, tz)
+                            : th_tile_apply2<false, true>(sm, jpbuf, P, V, t, mode, beta, out, pnew, tx, ty, tz);
+        else dot = upd ? th_tile_apply2<true, false>(sm, jpbuf, P, V, t, mode, beta, out, pnew, tx, ty, tz)
+                       : th_tile_apply2<false, false>(sm, jpbuf, P, V, t, mode, beta, out, pnew, tx, ty, tz);
+#else
+        if (edge) dot = upd ? th_tile_apply<true, true>(sm, P, V, t, mode, beta, out, pnew, tx, ty, tz)
+                            : th_tile_apply<false, true>(sm, P, V, t, mode, beta, out, pnew, tx, ty, tz);
+        else dot = upd ? th_tile_apply<true, false>(sm, P, V, t, mode, beta, out, pnew, tx, ty, tz)
+                       : th_tile_apply<false, false>(sm, P, V, t, mode, beta, out, pnew, tx, ty, tz);
+#endif
         acc[0] += (double)dot;
         if (TMA) {
             __syncwarp();

@@ -80,6 +80,7 @@ bool parse_descriptor(const std::string& text, PlanDesc& d, std::string& err) {
             ls >> d.tile[0] >> d.tile[1] >> d.tile[2] >> d.halo[0] >> d.halo[1] >> d.halo[2] >> d.smem_bytes;
             if (!(ls >> d.pipe)) d.pipe = 2;
             d.tiled = true;
+        } else if (key == "jpbytes") { ls >> d.jp_bytes;
         } else if (key == "vtile") { VTileDesc v; ls >> v.roww >> v.zoff >> v.poff >> v.bytes >> v.padl >> v.coff >> v.croww >> v.cbytes; d.vtiles.push_back(v); }
         else if (key == "stage") { StageDesc t; ls >> t.slot >> t.ctype >> t.es >> t.channels >> t.roww >> t.off >> t.bytes >> t.padl >> t.center; d.stages.push_back(t); }
         if (ls.fail() && !ls.eof()) { err = "malformed descriptor line: " + line; return false; }
@@ -405,7 +406,7 @@ Plan::Plan(const StateOptions* opts, const PlanDesc& desc, const std::string& so
         const char* names[2] = {"th_pcg_a_ld", "th_pcg_a"};
         for (int v = 0; v < 2; ++v) {
             CUfunction f = fn(names[v]);
-            tiled_smem_[v] = (unsigned)d_.smem_bytes * (v ? (unsigned)d_.pipe : 1u);
+            tiled_smem_[v] = (unsigned)d_.smem_bytes * (v ? (unsigned)d_.pipe : 1u) + (unsigned)d_.jp_bytes;
             if (tiled_smem_[v] > 48 * 1024 && api.FuncSetAttribute)
                 CU(api.FuncSetAttribute(f, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)tiled_smem_[v]));
             int per_sm = 2;

@@ -47,6 +47,7 @@ struct PlanDesc {
     int tile[3] = {1, 1, 1}, halo[3] = {0, 0, 0};
     std::vector<std::pair<long long, int>> computed;   // ComputedArrays: (elements, gradient channels); ptr_pidx = -(100 + 2k [+ 1 for the gradient image])
     int smem_bytes = 0;
+    int jp_bytes = 0;                       // two-phase tile operator: shared-memory J p planes behind the pipeline stages
     int pipe = 2;                           // shared-memory pipeline stages of th_pcg_a (TMA variant)
     std::vector<VTileDesc> vtiles;
     std::vector<StageDesc> stages;

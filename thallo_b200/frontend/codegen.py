@@ -45,6 +45,15 @@ def JpVal(t):
     return _JpVal("jpval", t)
 
 
+# two-phase tiled operator: (J p) of term t of the residual at offset (s0, s1, s2) from the unknown, read from the
+# shared-memory J p planes the first phase filled
+_JpAt = namedtuple("JpAt", "tag t s0 s1 s2")
+
+
+def JpAt(t, s):
+    return _JpAt("jpat", t, s[0], s[1], s[2])
+
+
 class Lowered:
     """Result of lowering: CUDA source of the per-energy functions and the descriptor."""
 
@@ -176,6 +185,31 @@ class Emitter:
             self.names[n.id] = name
         return [self.ref(r) for r in roots]
 
+    def emit_guarded(self, groups):
+        """groups: list of (condition text or None, roots, outs(refs) -> statements).  Nodes needed by more than one
+        group (or by an unconditional group) are emitted at function scope, the others inside `if (condition) { }`
+        together with the group's output statements."""
+        users = {}
+        for gi, (cond, roots, _) in enumerate(groups):
+            for n in ad.toposort(roots):
+                users.setdefault(n.id, set()).add(gi if cond is not None else -1)
+        allroots = [r for _, roots, _ in groups for r in roots]
+        shared = [n for n in ad.toposort(allroots) if len(users[n.id]) > 1 or -1 in users[n.id]]
+        self.emit(shared)
+        for gi, (cond, roots, outs) in enumerate(groups):
+            if cond is None:
+                self.lines.extend(outs([self.ref(r) for r in roots]))
+                continue
+            outer = dict(self.names)
+            mark = len(self.lines)
+            refs = self.emit(roots)
+            inner = self.lines[mark:]
+            del self.lines[mark:]
+            self.lines.append("if (%s) {" % cond)
+            self.lines.extend("    " + ln for ln in inner + outs(refs))
+            self.lines.append("}")
+            self.names = outer          # block-scoped names are not visible to later groups
+
     def rhs(self, n):
         g = self.gen
         if n.kind == "var":
@@ -290,6 +324,10 @@ class Generator:
         gl = os.environ.get("THALLO_B200_GATHER_LANES")                          # tuning switch: lanes per unknown element (1..16)
         self.gather_lanes = int(gl) if gl else None
         self.gather_unroll = int(os.environ.get("THALLO_B200_GATHER_UNROLL", "1"))   # tuning switch: unroll of the adjacency walk
+        # two-phase tiled operator (see gen_two_phase): "auto" = where the shifted-instance form re-forms J p of many
+        # residuals per unknown (shape_from_shading: 26 instances of 6 terms, the 3-D volume: 39 of 21)
+        self.two_phase_request = os.environ.get("THALLO_B200_TWO_PHASE", "auto")
+        self.two_phase = False
         self.coef_exprs = []          # hoisted PCG-invariant per-element expressions (channels of the __coef image)
         self._coef_index = {}
 
@@ -344,6 +382,8 @@ class Generator:
             return "jq%d.%s" % (k.i // 4, "xyzw"[k.i % 4])
         if isinstance(k, _JpVal):
             return "jpv[%d]" % k.t
+        if isinstance(k, _JpAt):
+            return "J.template at<%d, %d, %d, %d>()" % (k.t, k.s0, k.s1, k.s2)
         raise NotImplementedError(k)
 
     def _fn(self, sig, roots, outs, dom, pre_lines=()):
@@ -624,6 +664,101 @@ class Generator:
         if self.tiled:
             excl = [im.exclude for im in self.unknowns if im.exclude is not None]
             self._tile_layout(out + excl)
+            nterms = len(set(id(t) for t, _, _ in self.inst))
+            want = self.two_phase_request
+            self.two_phase = (want == "1") or (want == "auto" and len(self.inst) >= 2 * nterms + 8)
+            if self.two_phase:
+                src.append(self.gen_two_phase())
+        return "\n".join(src)
+
+    # ---- two-phase form of the tiled operator
+    # The shifted-instance form above lets every unknown re-form J p of every residual instance that touches it: a term
+    # with k unknowns in its support is evaluated (with all k of its partial derivatives) from k different unknowns.
+    # Where that dominates (many instances per term), the tile kernel instead runs the reference's Jt[Jp] idea inside
+    # shared memory: phase 1, every residual position of the tile and of the positions around it that reach into the
+    # tile forms J p of its terms ONCE into shared-memory planes; phase 2, every unknown multiplies its own partial
+    # derivative of each instance with the stored value.  Halo positions evaluate only the term classes that reach
+    # into the tile from there (the volume: one direction's three terms per face).
+    def gen_two_phase(self):
+        dom = self.udomain
+        nd = len(dom)
+        U = self.U
+        zero = ad.const(0.0)
+        terms, tindex = [], {}
+        for t, s, lst in self.inst:
+            if id(t) not in tindex:
+                tindex[id(t)] = len(terms)
+                terms.append(t)
+        NT = len(terms)
+
+        def svec(s):
+            return tuple(s.get(d, 0) for d in dom) + (0,) * (MAXD - nd)
+        shifts_of = {}
+        for t, s, lst in self.inst:
+            shifts_of.setdefault(tindex[id(t)], set()).add(svec(s))
+        # term classes: terms with the same set of non-zero shifts are needed at the same halo positions
+        cls_of, classes = {}, []
+        for k in range(NT):
+            key = frozenset(x for x in shifts_of[k] if any(x))
+            if key not in classes:
+                classes.append(key)
+            cls_of[k] = classes.index(key)
+        assert len(classes) <= 16, "two-phase tile: more than 16 term classes"
+        tile = self.tl["tile"]
+        PH = [max(abs(x[d]) for k in shifts_of for x in shifts_of[k]) for d in range(MAXD)]
+        assert all(PH[d] <= self.tl["halo"][d] for d in range(MAXD)) and max(PH) <= 7
+        box = [tile[d] + 2 * PH[d] for d in range(MAXD)]
+        # halo positions (relative to the tile origin) and the classes needed there
+        pos = []
+        for qz in range(-PH[2], tile[2] + PH[2]):
+            for qy in range(-PH[1], tile[1] + PH[1]):
+                for qx in range(-PH[0], tile[0] + PH[0]):
+                    q = (qx, qy, qz)
+                    if all(0 <= q[d] < tile[d] for d in range(MAXD)):
+                        continue
+                    need = 0
+                    for ci, key in enumerate(classes):
+                        if any(all(0 <= q[d] - x[d] < tile[d] for d in range(MAXD)) for x in key):
+                            need |= 1 << ci
+                    if need:
+                        pos.append((need, q))
+        pos.sort(key=lambda e: e[0])          # equal class masks next to each other: warps diverge less
+        packed = [(q[0] + 8) | ((q[1] + 8) << 4) | ((q[2] + 8) << 8) | (need << 16) for need, q in pos]
+        jp_exprs = [self.jp_h[id(t)] if self.hoist_enabled else t.jp("P") for t in terms]
+        # phase 2 roots
+        out = [zero] * U
+        for t, s, lst in self.inst_h:
+            memo = {}
+            cond = _inb(s)
+            jpv = ad.var(JpAt(tindex[id(t)], svec(s)))
+            for j, p in lst:
+                out[j] = out[j] + ad.select(cond, shift(p, s, memo) * jpv, 0.0)
+        self.two_phase_roots = dict(jp=jp_exprs, out=out, tindex=tindex, terms=terms)
+        self.tp = dict(nt=NT, ph=PH, box=box, nbox=box[0] * box[1] * box[2], pos=packed, nclasses=len(classes))
+        src = []
+        # halo positions: guarded by class
+        self._dom = dom
+        em = Emitter(self)
+        groups = []
+        for ci in range(len(classes)):
+            ks = [k for k in range(NT) if cls_of[k] == ci]
+            if not classes[ci]:
+                continue                  # terms that touch only their own element are never needed outside the tile
+            groups.append(("need & %du" % (1 << ci), [jp_exprs[k] for k in ks],
+                           lambda r, ks=ks: ["jp[%d] = %s;" % (k, x) for k, x in zip(ks, r)]))
+        em.emit_guarded(groups)
+        src.append("template <class A> __device__ __forceinline__ void applyJ_halo(const A& a, const Params& P, unsigned need, real* __restrict__ jp) {\n    "
+                   + "\n    ".join(em.lines) + "\n}\n")
+        # the element itself: J p of its own residuals -> planes, barrier, transposed products (one scope: the partial
+        # derivatives of the element's own residuals are shared between the two phases)
+        em = Emitter(self)
+        refs = em.emit(jp_exprs)
+        lines = list(em.lines) + ["J.template put<%d>(inside ? %s : (real)0);" % (k, x) for k, x in enumerate(refs)] + ["J.sync();"]
+        mark = len(em.lines)
+        refs2 = em.emit(out)
+        lines += em.lines[mark:] + ["out[%d] = %s;" % (j, refs2[j]) for j in range(U)]
+        src.append("template <class A, class JT> __device__ __forceinline__ void applyJTJ_tile(const A& a, const Params& P, JT& J, bool inside, real* __restrict__ out) {\n    "
+                   + "\n    ".join(lines) + "\n}\n")
         return "\n".join(src)
 
     def _halos(self, roots):
@@ -1195,6 +1330,28 @@ class Generator:
                     "{%d, %d, %d, %d, %d, %d, %d, %d}" % (v["roww"], v["zoff"], v["poff"], v["bytes"], v["padl"], v["coff"],
                                                           v["croww"], v["cbytes"]) for v in tl["vt"]))
                 hdr.append("#define TH_STAGE_CTC %d" % int(all(v["coff"] >= 0 for v in tl["vt"])))
+                # reach of the bounds predicates (tiles further than this from the domain border skip them)
+                R = [0] * MAXD
+                roots = list(self.uw_roots["out"]) + [im.exclude for im in self.unknowns if im.exclude is not None]
+                if self.two_phase:
+                    roots += self.two_phase_roots["jp"] + self.two_phase_roots["out"]
+                for e in roots:
+                    for v in ad.variables(e, lambda v: isinstance(v.key, Bounds)):
+                        for (dd, lo, hi) in v.key.ranges:
+                            pos = self.udomain.index(dd)
+                            R[pos] = max(R[pos], abs(lo), abs(hi))
+                if self.two_phase:
+                    R = [r + ph for r, ph in zip(R, self.tp["ph"])]      # predicates are also evaluated at the positions around the tile
+                if os.environ.get("THALLO_B200_EDGE_ALWAYS"):
+                    R = [1000000] * MAXD
+                hdr.append("#define TH_INB_RX %d\n#define TH_INB_RY %d\n#define TH_INB_RZ %d" % tuple(R))
+                hdr.append("#define TH_TWO_PHASE %d" % int(self.two_phase))
+                if self.two_phase:
+                    tp = self.tp
+                    hdr.append("#define TH_JP_NT %d" % tp["nt"])
+                    hdr.append("#define TH_JP_PHX %d\n#define TH_JP_PHY %d\n#define TH_JP_PHZ %d" % tuple(tp["ph"]))
+                    hdr.append("#define TH_JP_NHALO %d" % len(tp["pos"]))
+                    hdr.append("#define TH_JP_POS_TABLE {%s}" % (", ".join("%du" % x for x in tp["pos"]) or "0u"))
         gl = []
         for gi, g in enumerate(self.groups):
             body.append(self.gen_group(gi, g))
@@ -1308,6 +1465,7 @@ class Generator:
             d["tiled"] = int(self.tiled)
             if self.tiled:
                 d["tile"] = self.tl
+                d["jp_bytes"] = (self.tp["nt"] * self.tp["nbox"] * (8 if self.double else 4)) if self.two_phase else 0
         out.desc = d
         return out
 
@@ -1364,6 +1522,8 @@ def descriptor_text(d):
         if d.get("tiled"):
             tl = d["tile"]
             ln.append("tile %s %s %d %d" % (" ".join(map(str, tl["tile"])), " ".join(map(str, tl["halo"])), max(128, tl["smem"]), tl["pipe"]))
+            if d.get("jp_bytes"):
+                ln.append("jpbytes %d" % d["jp_bytes"])
             for v in tl["vt"]:
                 ln.append("vtile %d %d %d %d %d %d %d %d" % (v["roww"], v["zoff"], v["poff"], v["bytes"], v["padl"], v["coff"],
                                                              v["croww"], v["cbytes"]))

@@ -108,6 +108,9 @@ class Interp:
             return self.jvals[k.i]
         if type(k).__name__ == "JpVal":
             return self.jp[k.t]
+        if type(k).__name__ == "JpAt":          # two-phase tile operator: J p of term t of the residual at offset s (0 outside the domain)
+            nd = len(self.dom)
+            return _shifted(self.jp_planes[k.t], [k.s0, k.s1, k.s2][:nd])
         raise NotImplementedError(k)
 
     def _sparse(self, name):
@@ -181,6 +184,22 @@ def unknownwise(gen, params, vec=None, dtype=np.float64):
     g, d = pack(vals[:U]), pack(vals[U:2 * U])
     out = pack(vals[2 * U:]) if vec is not None else None
     return g, d, out
+
+
+def unknownwise_two_phase(gen, params, vec, dtype=np.float64):
+    """The two-phase form of the tiled operator (codegen.gen_two_phase): phase 1, J p of every term at every residual
+    position; phase 2, every unknown applies its partial derivatives to the stored values.  Returns J^T J vec (flat)."""
+    it = Interp(gen, params, gen.udomain, vec, dtype)
+    tp = gen.two_phase_roots
+    it.jp_planes = [np.array(v, dtype) for v in it.eval(tp["jp"])]
+    vals = it.eval(tp["out"])
+    flat = np.zeros(gen.nunk, dtype)
+    j = 0
+    for im in gen.unknowns:
+        a = np.stack([vals[j + ch] for ch in range(im.channels)], axis=-1)
+        flat[gen.uoff[im.name]:gen.uoff[im.name] + im.cardinality] = a.reshape(-1)
+        j += im.channels
+    return flat
 
 
 def gather_apply(gen, params, vec, dtype=np.float64, materialised=False):
