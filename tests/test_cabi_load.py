@@ -95,6 +95,17 @@ def test_problem_define_rejects_unknown_solver_kinds_and_plan_fails_loudly_witho
     bp = L.Thallo_ProblemDefine(st, str(broken).encode(), b"gauss_newton")
     assert bp and not L.Thallo_ProblemPlan(st, bp, dims)
     assert b"broken.t:3" in L.ThalloB200_LastError()                        # syntax error reported with file and line
+    # the front end is started with an argument vector, not through a shell: quotes and spaces in a path are just characters
+    odd = tmp_path / "it's an \"energy\" $(file).t"
+    odd.write_text("local W,H = Dims('W','H')\nInputs { X = Unknown(float,{W,H},0), A = Array(float,{W,H},1) }\n"
+                   "r = Residuals { fit = X(W(),H()) - A(W(),H()) }\n")
+    op = L.Thallo_ProblemDefine(st, str(odd).encode(), b"gauss_newton")
+    plan = L.Thallo_ProblemPlan(st, op, dims)
+    if torch.cuda.is_available():
+        assert plan
+        L.Thallo_PlanFree(st, plan)
+    else:
+        assert not plan and b"no CUDA device" in L.ThalloB200_LastError()     # i.e. the lowering itself succeeded
     if not torch.cuda.is_available():
         assert not L.Thallo_ProblemPlan(st, p, dims)                          # no CPU fallback: NULL + message, never a silent CPU path
         assert b"no CUDA device" in L.ThalloB200_LastError() and b"no CPU fallback" in L.ThalloB200_LastError()

@@ -158,3 +158,20 @@ int main(void) {
     from thallo_b200 import api
     assert C.sizeof(api.InitializationParameters) == 24
     assert ("summary %d" % C.sizeof(api.PerformanceSummary)) in outs[0] and ("entry %d" % C.sizeof(api.PerformanceEntry)) in outs[0]
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not os.path.isfile(os.path.join(BIN, "ref_create_delete_cycle")), reason="oracle/_ref not built")
+def test_reference_create_delete_cycle_program_runs_against_this_library(tmp_path):
+    """tests/create_delete_cycle/main.cpp:22-26: Thallo_ProblemPlan / Thallo_PlanFree ten times on the same problem, then a
+    solve.  The front end is started once (posix_spawn, no shell) and the other ten plans come out of the in-process
+    lowering cache; the run must finish well within the time ten interpreter start-ups would take."""
+    import time
+    (tmp_path / "laplacian.t").write_text(IMAGE_LAPLACIAN_T)
+    t0 = time.time()
+    r = subprocess.run([os.path.join(BIN, "ref_create_delete_cycle")], cwd=str(tmp_path), capture_output=True, text=True, timeout=300)
+    dt = time.time() - t0
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert "Iteration: 9" in r.stdout
+    assert (tmp_path / "result.png").exists()
+    assert dt < 60, dt

@@ -1083,39 +1083,44 @@ template <int LANES> __device__ __forceinline__ real th_lanes_sum_real(real v) {
         if (S->done) return;                                                                                        \
         constexpr int LANES = TH_SPACE[SP].lanes;                                                                   \
         constexpr int NS = TH_SPACE[SP].nslots;                                                                     \
-        const long long gt = (long long)blockIdx.x * blockDim.x + threadIdx.x;                                      \
         const int lane = (int)(threadIdx.x % LANES);                                                                \
         const real* __restrict__ in = which ? V.delta : V.p;                                                        \
         real* __restrict__ out = which ? V.Adelta : V.Ap;                                                           \
         double acc1[1] = {0.0};                                                                                     \
-        ThIdx<th::dom_s##SP> t;                                                                                     \
-        const bool valid = t.from_linear(gt / LANES) && th_owned(t);   /* ghost vertices: the owner computes Ap */  \
-        bool ex = true;                                                                                             \
-        real acc[NS];                                                                                               \
-        _Pragma("unroll") for (int j = 0; j < NS; ++j) acc[j] = (real)0;                                            \
-        if (valid) {                                                                                                \
-            GAcc<th::dom_s##SP> ta(t, nullptr);                                                                     \
-            ex = th::exclude_s##SP(ta, P);                                                                          \
-            if (!ex) {                                                                                              \
-                if (which) th::gather_s##SP<1, LANES>(t, lane, P, G, in, acc);                                      \
-                else th::gather_s##SP<0, LANES>(t, lane, P, G, in, acc);                                            \
+        /* persistent blocks (grid = SMs x resident blocks): one grid reduction per block instead of one per 256 */ \
+        /* elements; whole warps stay in the loop together (the lane sums below shuffle)                         */ \
+        const long long total = (TH_SPACE[SP].elements * LANES + 31) / 32 * 32;                                     \
+        for (long long gt = (long long)blockIdx.x * blockDim.x + threadIdx.x; gt < total;                           \
+             gt += (long long)gridDim.x * blockDim.x) {                                                             \
+            ThIdx<th::dom_s##SP> t;                                                                                 \
+            const bool valid = t.from_linear(gt / LANES) && th_owned(t);   /* ghost vertices: the owner computes Ap */ \
+            bool ex = true;                                                                                         \
+            real acc[NS];                                                                                           \
+            _Pragma("unroll") for (int j = 0; j < NS; ++j) acc[j] = (real)0;                                        \
+            if (valid) {                                                                                            \
+                GAcc<th::dom_s##SP> ta(t, nullptr);                                                                 \
+                ex = th::exclude_s##SP(ta, P);                                                                      \
+                if (!ex) {                                                                                          \
+                    if (which) th::gather_s##SP<1, LANES>(t, lane, P, G, in, acc);                                  \
+                    else th::gather_s##SP<0, LANES>(t, lane, P, G, in, acc);                                        \
+                }                                                                                                   \
             }                                                                                                       \
-        }                                                                                                           \
-        if (LANES > 1) { _Pragma("unroll") for (int j = 0; j < NS; ++j) acc[j] = th_lanes_sum_real<LANES>(acc[j]); } \
-        if (valid && lane == 0) {                                                                                   \
-            real dot = (real)0;                                                                                     \
-            _Pragma("unroll") for (int j = 0; j < NS; ++j) {                                                        \
-                const int k = TH_SLOT[SP][j].image;                                                                 \
-                const long long off = TH_UIMG[k].offset + t.lin * TH_UIMG[k].channels + TH_SLOT[SP][j].channel;     \
-                if (ex) { out[off] = (real)0; continue; }                                                           \
-                if (TH_SPACE_IS_REP(SP)) { out[off] = acc[j]; continue; }   /* summed over the ranks, then th_rep_finish */ \
-                const real pv = in[off];                                                                            \
-                real val = acc[j];                                                                                  \
-                if (TH_LM) val += V.CtC[off] * pv;                                                                  \
-                out[off] = val;                                                                                     \
-                dot += pv * val;                                                                                    \
+            if (LANES > 1) { _Pragma("unroll") for (int j = 0; j < NS; ++j) acc[j] = th_lanes_sum_real<LANES>(acc[j]); } \
+            if (valid && lane == 0) {                                                                               \
+                real dot = (real)0;                                                                                 \
+                _Pragma("unroll") for (int j = 0; j < NS; ++j) {                                                    \
+                    const int k = TH_SLOT[SP][j].image;                                                             \
+                    const long long off = TH_UIMG[k].offset + t.lin * TH_UIMG[k].channels + TH_SLOT[SP][j].channel; \
+                    if (ex) { out[off] = (real)0; continue; }                                                       \
+                    if (TH_SPACE_IS_REP(SP)) { out[off] = acc[j]; continue; }   /* summed over the ranks, then th_rep_finish */ \
+                    const real pv = in[off];                                                                        \
+                    real val = acc[j];                                                                              \
+                    if (TH_LM) val += V.CtC[off] * pv;                                                              \
+                    out[off] = val;                                                                                 \
+                    dot += pv * val;                                                                                \
+                }                                                                                                   \
+                acc1[0] += (double)dot;                                                                             \
             }                                                                                                       \
-            acc1[0] = (double)dot;                                                                                  \
         }                                                                                                           \
         if (which) return;                                                                                          \
         double tot[1];                                                                                              \

@@ -1,8 +1,14 @@
 // C ABI of thallo_b200: the twelve Thallo.h entry points (reference
 // API/release/include/Thallo.h:41-106, forwarders createwrapper.t:226-232) plus the
 // extension seam declared in include/thallo_b200.h.
+#include <fcntl.h>
+#include <spawn.h>
 #include <sys/stat.h>
+#include <sys/wait.h>
 #include <unistd.h>
+
+#include <cerrno>
+#include <map>
 
 #include <algorithm>
 #include <cstdio>
@@ -45,42 +51,122 @@ static std::string read_all(const std::string& path) {
     return ss.str();
 }
 
-// Runs the energy front end as a child process:  <python> -m thallo_b200.frontend ...
+// Runs the energy front end as a child process:  <python> -m thallo_b200.frontend --dims-on-stdin ...
 // (the reference evaluates the .t file inside its embedded Lua VM at ProblemPlan time,
 // thallo.t:1359-1373,1384-1434; we have no VM in the library, so the front end is a tool).
-static bool run_frontend(const Thallo_Problem* pr, const StateOptions& o, const unsigned int* dims, int ndims,
-                         std::string& desc, std::string& src, int* ndims_out) {
+// ONE process per plan, started with posix_spawnp and an argument vector (no shell: a quote or a space in the caller's
+// path is just a character); the child reports how many dimensions the energy declares, the library answers with that
+// many entries of the caller's array, the child lowers.  Results are cached in-process by (path, mtime, size, dims,
+// kind, precision, mode), so re-planning the same energy -- the reference's tests/create_delete_cycle -- starts no
+// interpreter at all.
+struct LoweredEnergy { std::string desc, src; };
+static std::map<std::string, LoweredEnergy>& lowering_cache() {
+    static std::map<std::string, LoweredEnergy> c;
+    return c;
+}
+static std::map<std::string, int>& ndims_cache() {
+    static std::map<std::string, int> c;
+    return c;
+}
+static std::string file_stamp(const std::string& path) {
+    struct stat st;
+    if (stat(path.c_str(), &st) != 0) return path + "|absent";
+    std::ostringstream o;
+    o << path << "|" << (long long)st.st_mtime << "|" << (long long)st.st_size;
+    return o.str();
+}
+static void rm_rf_dir(const std::string& dir) {       // the temporary directory holds plain files only
+    for (const char* f : {"/plan.desc", "/energy.cu", "/log.txt", "/ndims.txt"}) unlink((dir + f).c_str());
+    rmdir(dir.c_str());
+}
+extern char** environ;
+static bool run_frontend(const Thallo_Problem* pr, const StateOptions& o, const unsigned int* dims, std::string& desc, std::string& src) {
+    const bool as_committed = getenv("THALLO_LM_AS_COMMITTED") != nullptr;
+    const std::string stamp = file_stamp(pr->filename) + "|" + pr->kind + "|" + (o.init.doublePrecision ? "d" : "f") + (as_committed ? "|gn" : "");
+    auto nd_it = ndims_cache().find(stamp);
+    if (nd_it != ndims_cache().end()) {
+        std::ostringstream key;
+        key << stamp;
+        for (int i = 0; i < nd_it->second; ++i) key << "|" << dims[i];
+        auto hit = lowering_cache().find(key.str());
+        if (hit != lowering_cache().end()) { desc = hit->second.desc; src = hit->second.src; return true; }
+    }
     const char* py = getenv("THALLO_B200_PYTHON");
-    std::string root = getenv("THALLO_B200_ROOT") ? getenv("THALLO_B200_ROOT") : library_dir() + "/../..";
+    const std::string root = getenv("THALLO_B200_ROOT") ? getenv("THALLO_B200_ROOT") : library_dir() + "/../..";
     char tmpl[] = "/tmp/thallo_b200_XXXXXX";
     if (!mkdtemp(tmpl)) { set_error("mkdtemp failed"); return false; }
-    std::string out(tmpl);
-    std::ostringstream cmd;
-    cmd << "PYTHONPATH='" << root << "':\"$PYTHONPATH\" " << (py ? py : "python3") << " -m thallo_b200.frontend"
-        << " --energy '" << pr->filename << "' --kind " << pr->kind << " --double " << (o.init.doublePrecision ? 1 : 0)
-        << " --out '" << out << "'";
-    if (ndims_out) cmd << " --query-ndims";
-    else {
-        cmd << " --dims ";
-        for (int i = 0; i < ndims; ++i) cmd << (i ? "," : "") << dims[i];
+    const std::string out(tmpl), logf = out + "/log.txt";
+    int to_child[2], from_child[2];
+    if (pipe(to_child) != 0 || pipe(from_child) != 0) { set_error("pipe failed"); rm_rf_dir(out); return false; }
+    std::vector<std::string> args = {py ? py : "python3", "-m", "thallo_b200.frontend", "--energy", pr->filename, "--kind", pr->kind,
+                                     "--double", o.init.doublePrecision ? "1" : "0", "--out", out, "--dims-on-stdin"};
+    if (as_committed) args.push_back("--lm-as-committed");
+    std::vector<char*> argv;
+    for (auto& a : args) argv.push_back(const_cast<char*>(a.c_str()));
+    argv.push_back(nullptr);
+    // environment: the caller's, with the package root in front of PYTHONPATH
+    std::vector<std::string> envs;
+    std::string pp = "PYTHONPATH=" + root;
+    for (char** e = environ; e && *e; ++e) {
+        if (strncmp(*e, "PYTHONPATH=", 11) == 0) { if ((*e)[11]) pp += std::string(":") + (*e + 11); }
+        else envs.push_back(*e);
     }
-    if (getenv("THALLO_LM_AS_COMMITTED")) cmd << " --lm-as-committed";
-    cmd << " > '" << out << "/log.txt' 2>&1";
-    int rc = system(cmd.str().c_str());
+    envs.push_back(pp);
+    std::vector<char*> envp;
+    for (auto& e : envs) envp.push_back(const_cast<char*>(e.c_str()));
+    envp.push_back(nullptr);
+    posix_spawn_file_actions_t fa;
+    posix_spawn_file_actions_init(&fa);
+    posix_spawn_file_actions_adddup2(&fa, to_child[0], 0);
+    posix_spawn_file_actions_adddup2(&fa, from_child[1], 1);
+    posix_spawn_file_actions_addopen(&fa, 2, logf.c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0600);
+    for (int fd : {to_child[0], to_child[1], from_child[0], from_child[1]}) posix_spawn_file_actions_addclose(&fa, fd);
+    pid_t pid = 0;
+    const int rc = posix_spawnp(&pid, argv[0], &fa, nullptr, argv.data(), envp.data());
+    posix_spawn_file_actions_destroy(&fa);
+    close(to_child[0]);
+    close(from_child[1]);
     bool ok = false;
+    int nd = 0;
     if (rc != 0) {
-        set_error("energy front end failed for '" + pr->filename + "':\n" + read_all(out + "/log.txt"));
-    } else if (ndims_out) {
-        *ndims_out = atoi(read_all(out + "/ndims.txt").c_str());
-        ok = *ndims_out > 0;
+        set_error(std::string("could not start the energy front end (") + argv[0] + "): " + strerror(rc));
+        close(to_child[1]); close(from_child[0]);
+        rm_rf_dir(out);
+        return false;
+    }
+    {   // "ndims N\n" from the child (EOF = it failed before getting there)
+        std::string line;
+        char c;
+        while (read(from_child[0], &c, 1) == 1 && c != '\n') line.push_back(c);
+        if (line.compare(0, 6, "ndims ") == 0) nd = atoi(line.c_str() + 6);
+    }
+    if (nd > 0) {
+        std::ostringstream d;
+        for (int i = 0; i < nd; ++i) d << (i ? "," : "") << dims[i];
+        d << "\n";
+        const std::string ds = d.str();
+        if (write(to_child[1], ds.data(), ds.size()) != (ssize_t)ds.size()) nd = 0;
+    }
+    close(to_child[1]);
+    close(from_child[0]);
+    int status = 0;
+    while (waitpid(pid, &status, 0) < 0 && errno == EINTR) {}
+    if (nd <= 0 || !WIFEXITED(status) || WEXITSTATUS(status) != 0) {
+        set_error("energy front end failed for '" + pr->filename + "':\n" + read_all(logf));
     } else {
         desc = read_all(out + "/plan.desc");
         src = read_all(out + "/energy.cu");
         ok = !desc.empty() && !src.empty();
         if (!ok) set_error("energy front end produced no output for '" + pr->filename + "'");
     }
-    std::string rm = "rm -rf '" + out + "'";
-    if (system(rm.c_str()) != 0) {}
+    rm_rf_dir(out);
+    if (ok) {
+        ndims_cache()[stamp] = nd;
+        std::ostringstream key;
+        key << stamp;
+        for (int i = 0; i < nd; ++i) key << "|" << dims[i];
+        lowering_cache()[key.str()] = LoweredEnergy{desc, src};
+    }
     return ok;
 }
 
@@ -130,9 +216,8 @@ Thallo_Plan* Thallo_ProblemPlan(Thallo_State* state, Thallo_Problem* problem, un
         desc_text = problem->descriptor;
         src = problem->source;
     } else {
-        int nd = 0;
-        if (!run_frontend(problem, state->opts, nullptr, 0, desc_text, src, &nd)) return nullptr;
-        if (!run_frontend(problem, state->opts, dimensions, nd, desc_text, src, nullptr)) return nullptr;
+        if (!dimensions) { set_error("Thallo_ProblemPlan: dimensions is NULL"); return nullptr; }
+        if (!run_frontend(problem, state->opts, dimensions, desc_text, src)) return nullptr;
     }
     PlanDesc d;
     std::string err;

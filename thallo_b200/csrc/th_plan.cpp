@@ -368,6 +368,7 @@ Plan::Plan(const StateOptions* opts, const PlanDesc& desc, const std::string& so
     CD(cudaMalloc((void**)&d_partials_, sizeof(double) * 2 * (size_t)maxblocks));
     if (d_.gather) {
         if (const char* e = getenv("THALLO_B200_SCATTER_JTF")) gather_jtf_ = atoi(e) == 0;
+        if (const char* e = getenv("THALLO_B200_GATHER_BLOCKS_PER_SM")) gather_persistent_ = atoi(e);     // 0: one block per 256 threads of work
         adj_.resize(d_.seps.size());
         jvals_.assign(d_.groups.size(), nullptr);
         jp_.assign(d_.groups.size(), nullptr);
@@ -650,7 +651,9 @@ void Plan::launch_gather(int which) {
         int reduce_now = s + 1 == d_.spaces.size() && d_.replicated.empty();      // the last contribution to <p, Ap>: all-reduce in-kernel
         void* a[] = {P, V, G, &d_scalars_, &d_partials_, &which, &first, &reduce_now, &peers_};
         const long long threads = d_.spaces[s].elements * d_.spaces[s].lanes;
-        launch(fn("th_gather_s" + std::to_string(s)), dim3((unsigned)((threads + 255) / 256)), dim3(256), a);
+        long long blocks = (threads + 255) / 256;
+        if (gather_persistent_) blocks = std::min<long long>(blocks, (long long)sms_ * gather_persistent_);
+        launch(fn("th_gather_s" + std::to_string(s)), dim3((unsigned)blocks), dim3(256), a);
     }
     if (!d_.replicated.empty()) {      // replicated unknowns: sum the ranks' partial J^T J p, then + CtC p and the dot product
         long long n = 0;

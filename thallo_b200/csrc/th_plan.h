@@ -195,6 +195,7 @@ private:
     struct Adjacency { const void* src = nullptr; unsigned long long checksum = 0; bool valid = false; int* ptr = nullptr; int* perm = nullptr; };
     std::vector<Adjacency> adj_;
     std::vector<void*> jvals_, jp_, scoef_;
+    int gather_persistent_ = 8;       // th_gather_s<i>: persistent grid of SMs x this many blocks (grid-stride loop, one reduction per block)
     bool gather_jtf_ = true;          // PCGInit1 gathered over the adjacency lists (THALLO_B200_SCATTER_JTF=1: the atomic scatter form)
     std::vector<void*> computed_;  // value image, gradient image per ComputedArray (2 entries each)
     void run_precompute();         // gpu.precompute, gauss_newton.t:979-986
