@@ -153,6 +153,9 @@ template <class Dom> struct GScatter {
     }
 };
 
+#ifndef TH_FENCE_ALL
+#define TH_FENCE_ALL 0        // 1: every CTA fences at system scope before its reduction ticket (debug / comparison)
+#endif
 // ------------------------------------------------------------------ deterministic block/grid reduction
 __device__ __forceinline__ double th_warp_sum(double v) {
 #pragma unroll
@@ -194,7 +197,7 @@ template <int K> __device__ __forceinline__ bool th_grid_reduce(double (&val)[K]
     if (tid == 0) {
 #if TH_MULTI
         // this CTA's stores into peer memory (ThPush) must be visible to whoever sees the mailbox pair the last CTA sends
-        if (cta_pushed) __threadfence_system(); else __threadfence();
+        if (cta_pushed || TH_FENCE_ALL) __threadfence_system(); else __threadfence();
 #else
         __threadfence();
 #endif
@@ -222,6 +225,9 @@ template <int K> __device__ __forceinline__ bool th_grid_reduce(double (&val)[K]
 
 // ------------------------------------------------------------------ multi-GPU: peer stores and the in-kernel all-reduce
 #if TH_MULTI
+#ifndef TH_MAIL_PAIR
+#define TH_MAIL_PAIR 1        // 0: values, system fence, then a separate release store of the sequence number (debug / comparison)
+#endif
 __device__ __forceinline__ unsigned long long th_globaltimer() {
     unsigned long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -252,15 +258,28 @@ template <int K> __device__ __forceinline__ void th_mail_allreduce(const ThPeers
     if (lane < R.world) {
         ThMail* out = th_mail(R.box[lane], kind, par, R.rank);
         __threadfence_system();
+#if TH_MAIL_PAIR
 #pragma unroll
         for (int k = 0; k < K; ++k) th_st_pair(&out->q[2 * k], (unsigned long long)__double_as_longlong(v[k]), seq);
+#else
+#pragma unroll
+        for (int k = 0; k < K; ++k) *(volatile unsigned long long*)&out->q[2 * k] = (unsigned long long)__double_as_longlong(v[k]);
+        __threadfence_system();
+#pragma unroll
+        for (int k = 0; k < K; ++k) *(volatile unsigned long long*)&out->q[2 * k + 1] = seq;
+#endif
         const ThMail* in = th_mail(R.box[R.rank], kind, par, lane);
         const unsigned long long t0 = th_globaltimer();
 #pragma unroll
         for (int k = 0; k < K; ++k) {
             unsigned long long bits, sq;
             for (;;) {
+#if TH_MAIL_PAIR
                 th_ld_pair(&in->q[2 * k], bits, sq);
+#else
+                sq = *(volatile const unsigned long long*)&in->q[2 * k + 1];
+                if (sq == seq) { __threadfence_system(); bits = *(volatile const unsigned long long*)&in->q[2 * k]; }
+#endif
                 if (sq == seq) break;
                 if (th_globaltimer() - t0 > 20000000000ull) {
                     printf("thallo_b200: rank %d waited 20 s for rank %d (mailbox kind %d, seq %llu): peer lost\n", R.rank, lane, kind, seq);
