@@ -82,3 +82,53 @@ def test_repeated_solves_are_bit_identical(key):
         runs.append((costs, lin, [p[i].cpu().numpy().tobytes() for i in b.unknown_slots]))
     s.close()
     assert all(r == runs[0] for r in runs[1:])
+
+
+@pytest.mark.parametrize("key", ["1", "2", "4b"])
+def test_graph_replayed_iterations_are_bit_identical_to_plain_launches(key):
+    """The PCG iterations are replayed from CUDA graphs (chunks of 10 on the plan's private stream); the same kernels
+    with the same arguments in the same order: identical bits, identical LM exit decisions."""
+    import os
+    over = {"1": {}, "2": {"dims": (256, 192)}, "4b": {"n": 150}}[key]
+    runs = []
+    for graph in ("1", "0"):
+        os.environ["THALLO_B200_GRAPH"] = graph
+        try:
+            case = configs.case(key, **over)
+            case.nit = min(case.nit, 4)
+            b = case.build(0, 1, "cuda")
+        finally:
+            os.environ.pop("THALLO_B200_GRAPH", None)
+        s = b.solver
+        s.set_parameters(**case.params_for_solver())
+        p = b.fresh()
+        s.init(p)
+        costs, lin = [s.current_cost()], []
+        while s.step():
+            costs.append(s.current_cost())
+            lin.append(s.last_linear_iterations())
+        torch.cuda.synchronize()
+        runs.append((costs, lin, [p[i].cpu().numpy().tobytes() for i in b.unknown_slots]))
+        s.close()
+    assert runs[0] == runs[1]
+
+
+def test_solver_is_stream_ordered_with_the_callers_default_stream():
+    """The plan works on a private stream; API entry and exit order it with the caller's (legacy default) stream, so a
+    caller may enqueue work on its inputs right before a call and on the results right after it without synchronising."""
+    case = configs.case("1")
+    b = case.build(0, 1, "cuda")
+    s = b.solver
+    ref = None
+    for trial in range(3):
+        p = b.fresh()
+        big = torch.zeros(64 << 20, device="cuda")
+        for _ in range(8):
+            big.add_(1.0)                      # keeps the default stream busy ...
+        p[0].mul_(1.0)                         # ... right up to the last write of the unknowns before the solve
+        s.solve(p)
+        out = p[0] * 1.0                       # consumer on the default stream, no synchronisation in between
+        torch.cuda.synchronize()
+        ref = out.clone() if ref is None else ref
+        assert torch.equal(out, ref)
+    s.close()

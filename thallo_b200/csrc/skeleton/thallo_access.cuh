@@ -404,8 +404,8 @@ __device__ __forceinline__ void th_zero_scalar(const Vecs& V, const ThPush& H, b
 __device__ __forceinline__ unsigned long long th_seq(int epoch, int it1) {
     return ((unsigned long long)(unsigned int)epoch << 32) | (unsigned long long)(unsigned int)it1;
 }
-__device__ __forceinline__ void th_begin_linear(ThScalars* S, double rz0) {
+__device__ __forceinline__ void th_begin_linear(ThScalars* S, double rz0, int epoch) {
     S->rz[0] = rz0; S->rz[1] = 0.0; S->aD = 0.0; S->q = 0.0; S->Q0 = 0.0;
-    S->it = 0; S->done = 0; S->lin_done = 0;
+    S->it = 0; S->done = 0; S->lin_done = 0; S->epoch = epoch;
 }
 

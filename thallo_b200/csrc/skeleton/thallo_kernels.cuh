@@ -69,7 +69,7 @@ __device__ __forceinline__ void th_init_publish(ThScalars* S, double (&tot)[1], 
 #if TH_MULTI
     if (R.fused && th_tid() < 32) th_mail_allreduce<1>(R, TH_MAIL_INIT, th_seq(R.epoch, 1), tot);
 #endif
-    if (th_tid() == 0) th_begin_linear(S, tot[0]);
+    if (th_tid() == 0) th_begin_linear(S, tot[0], R.epoch);
 }
 // <p, Ap> at the end of the operator kernels, same scheme (sequence number = PCG iteration + 1)
 __device__ __forceinline__ void th_ad_publish(ThScalars* S, double (&tot)[1], const ThPeers& R, bool accumulate, bool reduce_now) {
@@ -77,7 +77,7 @@ __device__ __forceinline__ void th_ad_publish(ThScalars* S, double (&tot)[1], co
     if (accumulate) tot[0] += S->aD;
     __syncwarp();
 #if TH_MULTI
-    if (R.fused && reduce_now) th_mail_allreduce<1>(R, TH_MAIL_A, th_seq(R.epoch, S->it + 1), tot);
+    if (R.fused && reduce_now) th_mail_allreduce<1>(R, TH_MAIL_A, th_seq(S->epoch, S->it + 1), tot);
 #endif
     if (th_tid() == 0) S->aD = tot[0];
 }
@@ -182,8 +182,9 @@ __device__ __forceinline__ real* th_pcur(const Vecs& V, const ThScalars* S) {
 // and the progress report to the host through mapped pinned memory, which lets the host stop
 // issuing iterations after an LM early exit without ever synchronising (the reference blocks on
 // a 4-byte cudaMemcpy every iteration, gauss_newton.t:1667).
-__device__ __forceinline__ void th_close_iteration(ThScalars* S, real q_tolerance, ThHostFlags* hf, int epoch) {
+__device__ __forceinline__ void th_close_iteration(ThScalars* S, real q_tolerance, ThHostFlags* hf) {
     const int it = S->it;
+    const int epoch = S->epoch;
     S->it = it + 1;
     S->lin_done = it + 1;
 #if TH_LM
@@ -236,28 +237,27 @@ __device__ __forceinline__ void th_for_owned(long long lo, long long hi, FV&& fv
 // Called by every thread of the last block.  Fused multi-GPU plans all-reduce the two sums right here over the
 // peers' mailboxes (the z boundary layers this rank pushed are ordered before its flag, so a rank that has the
 // totals also has its ghost copies of z) and close the iteration like the tiled single-GPU schedule does.
-__device__ __forceinline__ void th_step2_publish(ThScalars* S, double (&tot)[2], real q_tolerance, ThHostFlags* hf, int epoch,
-                                                 const ThPeers& R) {
+__device__ __forceinline__ void th_step2_publish(ThScalars* S, double (&tot)[2], real q_tolerance, ThHostFlags* hf, const ThPeers& R) {
     if (th_tid() >= 32) return;
 #if TH_MULTI
     if (!R.fused) {
         if (th_tid() == 0) { S->red[0] = tot[0]; S->red[1] = tot[1]; }
         return;
     }
-    th_mail_allreduce<2>(R, TH_MAIL_B, th_seq(epoch, S->it + 1), tot);
+    th_mail_allreduce<2>(R, TH_MAIL_B, th_seq(S->epoch, S->it + 1), tot);
 #endif
     if (th_tid() == 0) {
         S->rz[(S->it + 1) & 1] = tot[0]; S->q = tot[1];
 #if TH_TILED || TH_MULTI
-        th_close_iteration(S, q_tolerance, hf, epoch);
+        th_close_iteration(S, q_tolerance, hf);
 #endif
     }
 }
 #if TH_MULTI
-extern "C" __global__ void th_mg_close(ThScalars* S, real q_tolerance, ThHostFlags* hf, int epoch) {
+extern "C" __global__ void th_mg_close(ThScalars* S, real q_tolerance, ThHostFlags* hf) {
     if (S->done) return;
     S->rz[(S->it + 1) & 1] = S->red[0]; S->q = S->red[1];
-    th_close_iteration(S, q_tolerance, hf, epoch);
+    th_close_iteration(S, q_tolerance, hf);
 }
 // halo push: copy contiguous segments (boundary layers of every unknown image) into the
 // neighbours' ghost layers over NVLink peer mappings
@@ -274,7 +274,7 @@ th_halo_push(const __grid_constant__ ThSegs G, int nseg, const ThScalars* S, int
 #endif
 
 extern "C" __global__ void __launch_bounds__(TH_BLOCK)
-th_pcg_b(const __grid_constant__ Vecs V, ThScalars* S, double* partials, real q_tolerance, ThHostFlags* hf, int epoch,
+th_pcg_b(const __grid_constant__ Vecs V, ThScalars* S, double* partials, real q_tolerance, ThHostFlags* hf,
          const __grid_constant__ ThPeers R, const __grid_constant__ ThPush H) {
     if (S->done) return;
     const real alpha = th_alpha(S);
@@ -337,7 +337,7 @@ th_pcg_b(const __grid_constant__ Vecs V, ThScalars* S, double* partials, real q_
         accr[0] = accr[1] = 0.0;
     }
     double tot[2];
-    if (th_grid_reduce<2>(acc, tot, partials, &S->ticket[2], pushed)) th_step2_publish(S, tot, q_tolerance, hf, epoch, R);
+    if (th_grid_reduce<2>(acc, tot, partials, &S->ticket[2], pushed)) th_step2_publish(S, tot, q_tolerance, hf, R);
 }
 
 extern "C" __global__ void __launch_bounds__(TH_BLOCK)
@@ -361,7 +361,7 @@ th_step2_first(const __grid_constant__ Vecs V, ThScalars* S) {
 
 // r = b - A delta; add_ctc: A delta still lacks the CtC*delta term (residualwise / materialized schedules)
 extern "C" __global__ void __launch_bounds__(TH_BLOCK)
-th_step2_second(const __grid_constant__ Vecs V, ThScalars* S, double* partials, int add_ctc, real q_tolerance, ThHostFlags* hf, int epoch,
+th_step2_second(const __grid_constant__ Vecs V, ThScalars* S, double* partials, int add_ctc, real q_tolerance, ThHostFlags* hf,
                 const __grid_constant__ ThPeers R, const __grid_constant__ ThPush H) {
     if (S->done) return;
     double acc[2] = {0.0, 0.0};
@@ -414,12 +414,12 @@ th_step2_second(const __grid_constant__ Vecs V, ThScalars* S, double* partials, 
         accr[0] = accr[1] = 0.0;
     }
     double tot[2];
-    if (th_grid_reduce<2>(acc, tot, partials, &S->ticket[2], pushed)) th_step2_publish(S, tot, q_tolerance, hf, epoch, R);
+    if (th_grid_reduce<2>(acc, tot, partials, &S->ticket[2], pushed)) th_step2_publish(S, tot, q_tolerance, hf, R);
 }
 
 // PCGStep3 of the untiled schedules: beta = rz_new/rz_old; p = z + beta p; closes the iteration.
 extern "C" __global__ void __launch_bounds__(TH_BLOCK)
-th_step3(const __grid_constant__ Vecs V, ThScalars* S, real q_tolerance, ThHostFlags* hf, int epoch) {
+th_step3(const __grid_constant__ Vecs V, ThScalars* S, real q_tolerance, ThHostFlags* hf) {
     if (S->done) return;
 #if TH_MULTI
     const real beta = th_beta_prev(S);       // th_pcg_b (fused) / th_mg_close has already closed the iteration (after the all-reduce of <z,r>)
@@ -446,7 +446,7 @@ th_step3(const __grid_constant__ Vecs V, ThScalars* S, real q_tolerance, ThHostF
     __syncthreads();
     if (last && threadIdx.x == 0) {
         S->ticket[3] = 0u;
-        th_close_iteration(S, q_tolerance, hf, epoch);
+        th_close_iteration(S, q_tolerance, hf);
     }
 #endif
 }

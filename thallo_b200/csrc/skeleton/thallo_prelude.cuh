@@ -71,7 +71,8 @@ struct ThScalars {
     int it;
     int done;
     int lin_done;
-    int pad;
+    int epoch;            // number of the nonlinear step, set by the PCGInit kernel: the kernels of the PCG iteration take no
+                          // per-step argument, so a captured CUDA graph of the iteration can be replayed in every step
 };
 
 // Host-visible progress flags (pinned, mapped): two 64-bit words, each (epoch << 32) | iteration, each

@@ -318,6 +318,14 @@ Plan::Plan(const StateOptions* opts, const PlanDesc& desc, const std::string& so
     CUresult r = api.ModuleLoadData(&module_, cubin.data());
     if (r != CUDA_SUCCESS) { error_ = "cuModuleLoadData failed (" + std::to_string((int)r) + ")"; return; }
 
+    if (!getenv("THALLO_B200_NO_PRIVATE_STREAM")) {
+        CD(cudaStreamCreateWithFlags(&work_, cudaStreamNonBlocking));
+        CD(cudaEventCreateWithFlags(&ev_enter_, cudaEventDisableTiming));
+        CD(cudaEventCreateWithFlags(&ev_leave_, cudaEventDisableTiming));
+    }
+    if (const char* e = getenv("THALLO_B200_GRAPH")) graphs_enabled_ = atoi(e) != 0;
+    if (const char* e = getenv("THALLO_B200_GRAPH_CHUNK")) graph_chunk_ = std::max(1, atoi(e));
+    Scope scope(this);
     // solver vectors: one allocation, 12 unknown-sized vectors (gauss_newton.t:1963-2071)
     vec_stride_ = ((size_t)d_.nunk * real_size_ + 255) / 256 * 256;
     // (+ the mailboxes of the multi-GPU in-kernel all-reduce behind the last vector, so that one IPC handle covers both)
@@ -476,7 +484,58 @@ void Plan::build_vector_maps() {
         }
 }
 
+void Plan::enter() {
+    if (!work_ || entered_++ > 0) return;
+    CD(cudaEventRecord(ev_enter_, caller()));
+    CD(cudaStreamWaitEvent(work_, ev_enter_, 0));
+}
+void Plan::leave() {
+    if (!work_ || --entered_ > 0) return;
+    CD(cudaEventRecord(ev_leave_, work_));
+    CD(cudaStreamWaitEvent(caller(), ev_leave_, 0));
+}
+bool Plan::use_graphs() const {
+    // per-kernel event pairs (timingLevel >= 2) and NCCL calls inside the iteration keep the plain launch sequence
+    return graphs_enabled_ && work_ && opts_->init.timingLevel < 2 && !(d_.multi && !fused_) && d_.replicated.empty();
+}
+// Iterations l0 .. l0+n-1 of the linear solve as one graph launch.
+void Plan::run_chunk(int l0, int n) {
+    std::string key;
+    for (int k = 0; k < n; ++k) key.push_back(d_.lm && ((l0 + k + 1) % sp_.residual_reset_period) == 0 ? 'R' : '.');
+    const size_t nptr = std::max<size_t>(1, d_.ptr_pidx.size()), nsc = std::max<size_t>(1, d_.scalars.size());
+    key.append(params_buf_.data(), 8 * nptr + real_size_ * nsc);        // (the LM scalars behind them are read by PCGInit only)
+    key.append(vecs_buf_.data(), vecs_buf_.size());
+    key.append(gather_buf_.data(), gather_buf_.size());
+    key.append((const char*)&peers_, sizeof(void*) * kMaxRanks + 3 * sizeof(int));
+    key.append(push_iter_.data(), push_iter_.size());
+    key.append((const char*)&sp_.q_tolerance, sizeof(float));
+    key.push_back(use_tma_ ? 'T' : 'L');
+    if (d_.tiled) key.append(maps_base(maps_buf_), 128 * (5 * d_.unknowns.size() + std::max<size_t>(1, d_.stages.size())));
+    auto it = graphs_.find(key);
+    if (it == graphs_.end()) {
+        if (graphs_.size() >= 16) {                                          // callers that keep changing buffers: start over
+            for (auto& g : graphs_) cudaGraphExecDestroy(g.second.exec);
+            graphs_.clear();
+        }
+        const unsigned long long before = launches;
+        cudaGraph_t graph = nullptr;
+        CD(cudaStreamBeginCapture(work_, cudaStreamCaptureModeThreadLocal));
+        for (int k = 0; k < n; ++k) linear_iteration(l0 + k);
+        CD(cudaStreamEndCapture(work_, &graph));
+        GraphEntry e;
+        e.launches = launches - before;
+        launches = before;
+        CD(cudaGraphInstantiate(&e.exec, graph, 0));
+        CD(cudaGraphDestroy(graph));
+        it = graphs_.emplace(key, e).first;
+    }
+    CD(cudaGraphLaunch(it->second.exec, work_));
+    launches += it->second.launches;
+}
+
 Plan::~Plan() {
+    if (work_) cudaStreamSynchronize(work_);
+    for (auto& g : graphs_) cudaGraphExecDestroy(g.second.exec);
     bool all = false;
     for (int r = 0; r < kMaxRanks; ++r) if (peer_all_[r] && peer_all_[r] != vec_block_) { cudaIpcCloseMemHandle(peer_all_[r]); all = true; }
     if (!all) for (int i = 0; i < 2; ++i) if (peer_[i]) cudaIpcCloseMemHandle(peer_[i]);
@@ -498,6 +557,9 @@ Plan::~Plan() {
     for (auto& k : kstats_) for (auto& s : k.pending) { cudaEventDestroy(s.a); cudaEventDestroy(s.b); }
     for (auto& s : event_pool_) { cudaEventDestroy(s.a); cudaEventDestroy(s.b); }
     if (module_ && DriverApi::get().ok) DriverApi::get().ModuleUnload(module_);
+    if (ev_enter_) cudaEventDestroy(ev_enter_);
+    if (ev_leave_) cudaEventDestroy(ev_leave_);
+    if (work_) cudaStreamDestroy(work_);
 }
 
 CUfunction Plan::fn(const std::string& name) {
@@ -785,6 +847,7 @@ void Plan::evaluate_timers() {
 
 // init, gauss_newton.t:1166-1198
 void Plan::init(void** params) {
+    Scope scope(this);
     finalized_ = false;
     initialized_ = true;
     t_start_ = std::chrono::steady_clock::now();
@@ -823,6 +886,7 @@ void Plan::finalize() {
 }
 
 double Plan::cost() {   // gauss_newton.t:1787-1793
+    Scope scope(this);
     if (!finalized_) prev_cost_ = compute_cost();
     return prev_cost_;
 }
@@ -888,27 +952,28 @@ void Plan::linear_iteration(int l) {
             launch_flat(fn("th_step1_finish"), a);
             add_ctc = 1;
         }
-        void* a[] = {V, &d_scalars_, &d_partials_, &add_ctc, qtol, &d_flags_, &epoch_, &peers_, push_iter_.data()};
+        void* a[] = {V, &d_scalars_, &d_partials_, &add_ctc, qtol, &d_flags_, &peers_, push_iter_.data()};
         launch_flat(fn("th_step2_second"), a);
     } else {
-        void* a[] = {V, &d_scalars_, &d_partials_, qtol, &d_flags_, &epoch_, &peers_, push_iter_.data()};
+        void* a[] = {V, &d_scalars_, &d_partials_, qtol, &d_flags_, &peers_, push_iter_.data()};
         launch_flat(fn("th_pcg_b"), a);
     }
     if (nccl_scalars) {           // z ghost layers, global <z,r> and q, then close the iteration
         halo_push(V_Z, 1);
         allreduce(offsetof(HScalars, red), 2);
-        void* a[] = {&d_scalars_, qtol, &d_flags_, &epoch_};
+        void* a[] = {&d_scalars_, qtol, &d_flags_};
         launch(fn("th_mg_close"), dim3(1), dim3(1), a);
     }
     // ---- p = z + beta p (fused into the next th_pcg_a in the tiled schedule)
     if (!d_.tiled) {
-        void* a[] = {V, &d_scalars_, qtol, &d_flags_, &epoch_};
+        void* a[] = {V, &d_scalars_, qtol, &d_flags_};
         launch_flat(fn("th_step3"), a);
     }
 }
 
 // step, gauss_newton.t:1545-1785
 int Plan::step(void** params) {
+    Scope scope(this);
     bind(params);
     if (sp_.nIter >= sp_.nIterations) { finalize(); return 0; }
     void* P = params_buf_.data();
@@ -974,6 +1039,33 @@ int Plan::step(void** params) {
     // before that iteration -- a function of device data only, so every rank of a multi-GPU solve
     // issues exactly the same sequence of kernels and collectives.
     const int depth = 4;
+    if (use_graphs()) {
+        // chunks of graph_chunk_ iterations, one graph launch each; at most two chunks in flight.  After the device's LM
+        // exit the remaining kernels of a chunk return at once, and the host stops launching chunks as soon as it sees
+        // the exit word (the fused multi-GPU kernels need no matching launch counts on the ranks).
+        const int G = graph_chunk_;
+        for (int l0 = 0; l0 < sp_.lIterations; l0 += G) {
+            const int need = l0 - G;
+            if (d_.lm && need >= 1) {
+                bool stop = false;
+                for (unsigned spins = 0;; ++spins) {
+                    const long long pr = h_flags_->progress;
+                    const int done_iters = (int)(pr >> 32) == epoch_ ? (int)(pr & 0xffffffff) : 0;
+                    std::atomic_thread_fence(std::memory_order_acquire);
+                    const long long ex = h_flags_->exit_word;
+                    if ((int)(ex >> 32) == epoch_) { stop = true; break; }
+                    if (done_iters >= need) break;
+                    if ((spins & 1023) == 1023) {
+                        const cudaError_t e = cudaStreamQuery(stream());
+                        if (e != cudaSuccess && e != cudaErrorNotReady) fatal_cuda(e, "PCG iteration (asynchronous kernel failure)");
+                    }
+                    sched_yield();
+                }
+                if (stop) break;
+            }
+            run_chunk(l0, std::min(G, sp_.lIterations - l0));
+        }
+    } else
     for (int l = 0; l < sp_.lIterations; ++l) {
         const int need = l - depth + 1;
         if (d_.lm && need >= 1) {
@@ -1086,6 +1178,7 @@ int Plan::step(void** params) {
 }
 
 void Plan::solve(void** params) {   // thallo.t:5980-5983
+    Scope scope(this);
     init(params);
     while (step(params)) {}
 }
@@ -1111,6 +1204,7 @@ void Plan::get_parameter(const char* name, void* value) {
 }
 
 long long Plan::read_vector(const char* name, void* dst, long long count) {
+    Scope scope(this);
     for (int i = 0; i < kNumVecs; ++i) {
         if (strcmp(name, kVecNames[i]) == 0) {
             const long long n = std::min<long long>(count, d_.nunk);
@@ -1136,6 +1230,7 @@ long long Plan::export_jacobian(int g, void* host_vals, long long* host_cols, lo
     const long long n = d_.groups[g].count * (long long)d_.groups[g].nnz;
     if (n > capacity) return -1;
     if (n == 0) return 0;
+    Scope scope(this);
     void* dv = nullptr; long long* dc = nullptr;
     CD(cudaMalloc(&dv, (size_t)n * real_size_));
     CD(cudaMalloc((void**)&dc, (size_t)n * sizeof(long long)));

@@ -162,7 +162,25 @@ private:
     CUmodule module_ = nullptr;
     std::map<std::string, CUfunction> fns_;
     size_t real_size_ = 4;
-    cudaStream_t stream() const { return opts_->stream; }
+    // All solver work runs on a private stream (the legacy default stream the reference uses, util.t:769-772, cannot be
+    // captured into a CUDA graph), ordered with the caller's stream by events at every API entry and exit: the caller
+    // sees the same stream-ordered behaviour as with the reference (SURVEY 8b "Threading / streams").
+    cudaStream_t caller() const { return opts_->stream; }
+    cudaStream_t stream() const { return work_ ? work_ : opts_->stream; }
+    cudaStream_t work_ = nullptr;
+    cudaEvent_t ev_enter_ = nullptr, ev_leave_ = nullptr;
+    int entered_ = 0;
+    void enter();
+    void leave();
+    struct Scope { Plan* p; explicit Scope(Plan* q) : p(q) { p->enter(); } ~Scope() { p->leave(); } };
+    // CUDA graphs of chunks of PCG iterations (the kernels take no per-step argument), keyed by the reset pattern of
+    // the chunk and the kernel-argument images
+    struct GraphEntry { cudaGraphExec_t exec = nullptr; unsigned long long launches = 0; };
+    std::map<std::string, GraphEntry> graphs_;
+    bool graphs_enabled_ = true;
+    int graph_chunk_ = 10;
+    bool use_graphs() const;
+    void run_chunk(int l0, int n);
 
     // device state
     char* vec_block_ = nullptr;
