@@ -153,9 +153,18 @@ template <class Dom> struct GScatter {
     }
 };
 
-#ifndef TH_FENCE_ALL
-#define TH_FENCE_ALL 0        // 1: every CTA fences at system scope before its reduction ticket (debug / comparison)
+// How boundary values reach the neighbours' ghost copies (multi-GPU):
+//   TH_PUSH_MODE 1 (default)  the LAST CTA of the kernel's grid reduction copies the boundary segments from local memory
+//                             into the peers' memory, fences once at system scope and sends the mailbox pairs: every
+//                             other CTA is exactly the single-GPU kernel (device-scope fences, no remote traffic)
+//   TH_PUSH_MODE 0            every thread forwards the boundary values it computes, and EVERY CTA fences at system
+//                             scope before its reduction ticket (measured: +12 us per kernel at 2048^2; and mixing
+//                             device-scope and system-scope ticket fences between the CTAs of one grid hung both GPUs
+//                             on B200, profiles/r02d_*)
+#ifndef TH_PUSH_MODE
+#define TH_PUSH_MODE 1
 #endif
+#define TH_FENCE_ALL (TH_MULTI && TH_PUSH_MODE == 0)
 // ------------------------------------------------------------------ deterministic block/grid reduction
 __device__ __forceinline__ double th_warp_sum(double v) {
 #pragma unroll
@@ -181,11 +190,8 @@ template <int K> __device__ __forceinline__ bool th_grid_reduce(double (&val)[K]
         const double w = th_warp_sum(val[k]);
         if (lane == 0) sm[k][warp] = w;
     }
-#if TH_MULTI
-    const bool cta_pushed = __syncthreads_or(pushed ? 1 : 0) != 0;
-#else
+    (void)pushed;
     __syncthreads();
-#endif
     if (warp == 0) {
 #pragma unroll
         for (int k = 0; k < K; ++k) {
@@ -195,12 +201,8 @@ template <int K> __device__ __forceinline__ bool th_grid_reduce(double (&val)[K]
         }
     }
     if (tid == 0) {
-#if TH_MULTI
-        // this CTA's stores into peer memory (ThPush) must be visible to whoever sees the mailbox pair the last CTA sends
-        if (cta_pushed || TH_FENCE_ALL) __threadfence_system(); else __threadfence();
-#else
-        __threadfence();
-#endif
+        // (TH_PUSH_MODE 0: this CTA's stores into peer memory must be visible to whoever sees the mailbox pair the last CTA sends)
+        if (TH_FENCE_ALL) __threadfence_system(); else __threadfence();
         const unsigned int t = atomicAdd(ticket, 1u);
         last = (t == nblocks - 1);
     }
@@ -297,17 +299,40 @@ template <int K> __device__ __forceinline__ void th_mail_allreduce(const ThPeers
         v[k] = tot;
     }
 }
-// forward a scalar / a real4 chunk just written at flat index f / chunk i of the pushed vector to the neighbours
-// (return whether anything was stored: a CTA that pushed fences at system scope before its reduction ticket)
+// TH_PUSH_MODE 1: called by every thread of the last CTA after the grid reduction (all CTAs' values are in local memory
+// and visible): boundary segments of `src` -> the neighbours' ghost copies; ends with a barrier, after which one
+// system-scope fence by the thread that sends the mailbox pairs orders all of it.
+__device__ __forceinline__ void th_push_segments(const ThPush& H, const real* __restrict__ src) {
+#if TH_PUSH_MODE == 1
+    const int tid = (int)(threadIdx.x + blockDim.x * (threadIdx.y + blockDim.y * threadIdx.z));
+    const int nthreads = (int)(blockDim.x * blockDim.y * blockDim.z);
+    for (int s = 0; s < 2 * TH_NUM_UIMG; ++s) {
+        if (s >= H.n) break;
+        const long long lo = H.lo[s], n = H.hi[s] - H.lo[s];
+        if (H.vec4[s]) {
+            const real4* __restrict__ a = (const real4*)(src + lo);
+            real4* __restrict__ b = (real4*)H.dst[s];
+            for (long long i = tid; i < n / 4; i += nthreads) b[i] = __ldcg(a + i);
+        } else {
+            for (long long i = tid; i < n; i += nthreads) H.dst[s][i] = __ldcg(src + lo + i);
+        }
+    }
+    __syncthreads();
+#endif
+}
+// TH_PUSH_MODE 0: forward a scalar / a real4 chunk just written at flat index f / chunk i of the pushed vector
 __device__ __forceinline__ bool th_push_scalar(const ThPush& H, long long f, real val) {
     bool any = false;
+#if TH_PUSH_MODE == 0
 #pragma unroll
     for (int s = 0; s < 2 * TH_NUM_UIMG; ++s)
         if (s < H.n && f >= H.lo[s] && f < H.hi[s]) { H.dst[s][f - H.lo[s]] = val; any = true; }
+#endif
     return any;
 }
 __device__ __forceinline__ bool th_push_vec4(const ThPush& H, long long i, const real4& val) {
     bool any = false;
+#if TH_PUSH_MODE == 0
 #pragma unroll
     for (int s = 0; s < 2 * TH_NUM_UIMG; ++s) {
         if (s >= H.n || 4 * i + 3 < H.lo[s] || 4 * i >= H.hi[s]) continue;
@@ -318,6 +343,7 @@ __device__ __forceinline__ bool th_push_vec4(const ThPush& H, long long i, const
             return any;
         }
     }
+#endif
     return any;
 }
 #endif

@@ -65,8 +65,9 @@ __device__ __forceinline__ int th_tid() { return (int)(threadIdx.x + blockDim.x 
 
 // End of PCGInit in the last block: <r, p> (all ranks' parts) opens the linear solve.  Non-fused multi-GPU plans
 // publish the rank's part; the host all-reduces S->rz[0] over NCCL.
-__device__ __forceinline__ void th_init_publish(ThScalars* S, double (&tot)[1], const ThPeers& R) {
+__device__ __forceinline__ void th_init_publish(ThScalars* S, double (&tot)[1], const ThPeers& R, const ThPush& H, const real* pushed_vec) {
 #if TH_MULTI
+    if (R.fused) th_push_segments(H, pushed_vec);       // p0 (z in the tiled schedule) of the boundary elements -> the neighbours' ghost copies
     if (R.fused && th_tid() < 32) th_mail_allreduce<1>(R, TH_MAIL_INIT, th_seq(R.epoch, 1), tot);
 #endif
     if (th_tid() == 0) th_begin_linear(S, tot[0], R.epoch);
@@ -120,7 +121,7 @@ th_init_uw(const __grid_constant__ Params P, const __grid_constant__ Vecs V, ThS
         acc[0] = (double)dot;
     }
     double tot[1];
-    if (th_grid_reduce<1>(acc, tot, partials, &S->ticket[0], pushed)) th_init_publish(S, tot, R);
+    if (th_grid_reduce<1>(acc, tot, partials, &S->ticket[0], pushed)) th_init_publish(S, tot, R, H, TH_TILED ? V.z : V.p);
 }
 
 // which = 0: Ap = (JtJ [+CtC]) p with alphaDenominator = <p,Ap>;  which = 1: Adelta = (JtJ [+CtC]) delta
@@ -237,7 +238,11 @@ __device__ __forceinline__ void th_for_owned(long long lo, long long hi, FV&& fv
 // Called by every thread of the last block.  Fused multi-GPU plans all-reduce the two sums right here over the
 // peers' mailboxes (the z boundary layers this rank pushed are ordered before its flag, so a rank that has the
 // totals also has its ghost copies of z) and close the iteration like the tiled single-GPU schedule does.
-__device__ __forceinline__ void th_step2_publish(ThScalars* S, double (&tot)[2], real q_tolerance, ThHostFlags* hf, const ThPeers& R) {
+__device__ __forceinline__ void th_step2_publish(ThScalars* S, double (&tot)[2], real q_tolerance, ThHostFlags* hf, const ThPeers& R,
+                                                 const ThPush& H, const real* z) {
+#if TH_MULTI
+    if (R.fused) th_push_segments(H, z);                // z of the boundary elements -> the neighbours' ghost copies
+#endif
     if (th_tid() >= 32) return;
 #if TH_MULTI
     if (!R.fused) {
@@ -337,7 +342,7 @@ th_pcg_b(const __grid_constant__ Vecs V, ThScalars* S, double* partials, real q_
         accr[0] = accr[1] = 0.0;
     }
     double tot[2];
-    if (th_grid_reduce<2>(acc, tot, partials, &S->ticket[2], pushed)) th_step2_publish(S, tot, q_tolerance, hf, R);
+    if (th_grid_reduce<2>(acc, tot, partials, &S->ticket[2], pushed)) th_step2_publish(S, tot, q_tolerance, hf, R, H, V.z);
 }
 
 extern "C" __global__ void __launch_bounds__(TH_BLOCK)
@@ -414,7 +419,7 @@ th_step2_second(const __grid_constant__ Vecs V, ThScalars* S, double* partials, 
         accr[0] = accr[1] = 0.0;
     }
     double tot[2];
-    if (th_grid_reduce<2>(acc, tot, partials, &S->ticket[2], pushed)) th_step2_publish(S, tot, q_tolerance, hf, R);
+    if (th_grid_reduce<2>(acc, tot, partials, &S->ticket[2], pushed)) th_step2_publish(S, tot, q_tolerance, hf, R, H, V.z);
 }
 
 // PCGStep3 of the untiled schedules: beta = rz_new/rz_old; p = z + beta p; closes the iteration.
@@ -1021,7 +1026,7 @@ th_init_finish(const __grid_constant__ Params P, const __grid_constant__ Vecs V,
         if (th_flat_counted(f)) acc[0] += (double)rp;
     }
     double tot[1];
-    if (th_grid_reduce<1>(acc, tot, partials, &S->ticket[0], pushed)) th_init_publish(S, tot, R);
+    if (th_grid_reduce<1>(acc, tot, partials, &S->ticket[0], pushed)) th_init_publish(S, tot, R, H, TH_TILED ? V.z : V.p);
 }
 
 // which = 0: finish Ap (LM: += CtC p) and alphaDenominator; which = 1: only mask Adelta
