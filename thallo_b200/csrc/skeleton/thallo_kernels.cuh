@@ -774,7 +774,7 @@ __device__ __forceinline__ real th_tile_apply(const unsigned char* sm, const Par
 #define TH_JP_BZ (TH_TD + 2 * TH_JP_PHZ)
 #define TH_JP_NBOX (TH_JP_BX * TH_JP_BY * TH_JP_BZ)
 #define TH_JP_BYTES (TH_JP_NT * TH_JP_NBOX * (int)sizeof(real))
-// halo positions relative to the tile origin: (dx + 8) | (dy + 8) << 4 | (dz + 8) << 8 | class mask << 16
+// halo positions relative to the tile origin: (dx + 8) | (dy + 8) << 8 | (dz + 8) << 16 | class mask << 24
 __device__ const unsigned int TH_JP_POS[TH_JP_NHALO > 0 ? TH_JP_NHALO : 1] = TH_JP_POS_TABLE;
 struct ThJp {
     real* buf;
@@ -798,14 +798,14 @@ __device__ __forceinline__ real th_tile_apply2(const unsigned char* sm, real* jp
     // phase 1, positions around the tile
     for (int q = tid; q < TH_JP_NHALO; q += TH_TILE_THREADS) {
         const unsigned int e = __ldg(&TH_JP_POS[q]);
-        const int dx = (int)(e & 15u) - 8, dy = (int)((e >> 4) & 15u) - 8, dz = (int)((e >> 8) & 15u) - 8;
+        const int dx = (int)(e & 255u) - 8, dy = (int)((e >> 8) & 255u) - 8, dz = (int)((e >> 16) & 255u) - 8;
         real jp[TH_JP_NT];
 #pragma unroll
         for (int k = 0; k < TH_JP_NT; ++k) jp[k] = (real)0;
         ThIdx<th::dom_uw> idx;
         if (x0 + dx >= 0 && y0 + dy >= 0 && z0 + dz >= 0 && idx.from_coords(x0 + dx, y0 + dy, z0 + dz)) {
             TAcc<th::dom_uw, UPD, EDGE> a(idx, sm, dx, dy, dz, beta);
-            th::applyJ_halo(a, P, e >> 16, jp);
+            th::applyJ_halo(a, P, e >> 24, jp);
         }
         const int b = ThJp::box(dx, dy, dz);
 #pragma unroll

@@ -703,7 +703,7 @@ class Generator:
             if key not in classes:
                 classes.append(key)
             cls_of[k] = classes.index(key)
-        assert len(classes) <= 16, "two-phase tile: more than 16 term classes"
+        assert len(classes) <= 8, "two-phase tile: more than 8 term classes"
         tile = self.tl["tile"]
         PH = [max(abs(x[d]) for k in shifts_of for x in shifts_of[k]) for d in range(MAXD)]
         assert all(PH[d] <= self.tl["halo"][d] for d in range(MAXD)) and max(PH) <= 7
@@ -723,7 +723,8 @@ class Generator:
                     if need:
                         pos.append((need, q))
         pos.sort(key=lambda e: e[0])          # equal class masks next to each other: warps diverge less
-        packed = [(q[0] + 8) | ((q[1] + 8) << 4) | ((q[2] + 8) << 8) | (need << 16) for need, q in pos]
+        assert all(0 <= q[d] + 8 < 256 for _, q in pos for d in range(MAXD))
+        packed = [(q[0] + 8) | ((q[1] + 8) << 8) | ((q[2] + 8) << 16) | (need << 24) for need, q in pos]
         jp_exprs = [self.jp_h[id(t)] if self.hoist_enabled else t.jp("P") for t in terms]
         # phase 2 roots
         out = [zero] * U
