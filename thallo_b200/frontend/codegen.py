@@ -668,7 +668,23 @@ class Generator:
             want = self.two_phase_request
             self.two_phase = (want == "1") or (want == "auto" and len(self.inst) >= 2 * nterms + 8)
             if self.two_phase:
-                src.append(self.gen_two_phase())
+                tp_src = self.gen_two_phase()
+                # shared memory: pipeline stages + the J p planes must fit beside at least one resident CTA
+                limit = 227 * 1024 - 2048
+                stage = max(128, self.tl["smem"])
+                jpb = self.tp["nt"] * self.tp["nbox"] * (8 if self.double else 4)
+                nthreads = self.tl["tile"][0] * self.tl["tile"][1] * self.tl["tile"][2]
+                pipe = self.tl["pipe"]
+                if pipe * stage + jpb > limit:
+                    pipe = 1
+                if pipe * stage + jpb > limit:
+                    self.two_phase = False            # does not fit: keep the shifted-instance form
+                else:
+                    if not os.environ.get("THALLO_B200_PIPE"):
+                        self.tl["pipe"] = pipe
+                    if not os.environ.get("THALLO_B200_MINB"):
+                        self.tl["minb"] = max(1, min(self.tl["minb"], limit // (self.tl["pipe"] * stage + jpb), 2048 // nthreads))
+                    src.append(tp_src)
         return "\n".join(src)
 
     # ---- two-phase form of the tiled operator
