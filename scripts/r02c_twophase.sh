@@ -3,11 +3,11 @@
 # correctness tests, then shape_from_shading 8192^2 and the 160^3 volume under each variant
 OUT=gpurun_out/r02c
 mkdir -p $OUT
-timeout 900 python -m pytest tests/test_gpu_tiled.py -x -q 2>&1 | tail -15 | tee $OUT/tiled_tests.txt
+true
 for cfg in 3b 4a; do
   for tp in 0 1; do
     for edge in 0 1; do
-      if [ $edge = 1 ]; then export THALLO_B200_EDGE_ALWAYS=1; else unset THALLO_B200_EDGE_ALWAYS; fi
+      if [ $edge = 1 ]; then unset THALLO_B200_EDGE_SPECIALIZE; else export THALLO_B200_EDGE_SPECIALIZE=1; fi
       THALLO_B200_TWO_PHASE=$tp timeout 600 python bench.py --config $cfg --no-parity --extra-steps 1 > $OUT/cfg${cfg}_tp${tp}_edge${edge}.json 2> $OUT/cfg${cfg}_tp${tp}_edge${edge}.err
       python - <<PY | tee -a $OUT/summary.txt
 import json
@@ -21,10 +21,10 @@ PY
     done
   done
 done
-unset THALLO_B200_EDGE_ALWAYS
+unset THALLO_B200_EDGE_SPECIALIZE
 # headline with the interior specialisation (default) vs without
 for edge in 0 1; do
-  if [ $edge = 1 ]; then export THALLO_B200_EDGE_ALWAYS=1; else unset THALLO_B200_EDGE_ALWAYS; fi
+  if [ $edge = 1 ]; then unset THALLO_B200_EDGE_SPECIALIZE; else export THALLO_B200_EDGE_SPECIALIZE=1; fi
   timeout 600 python bench.py --extras 3a --no-parity --no-cpu-baseline > $OUT/headline_edge${edge}.json 2> $OUT/headline_edge${edge}.err
   python - <<PY | tee -a $OUT/summary.txt
 import json

@@ -172,22 +172,26 @@ def test_tile_operator_variants_match_oracle_f64(case, two_phase):
 
 
 @pytest.mark.parametrize("case", ["sfs", "volume"])
-def test_interior_tile_specialisation_is_bit_identical(case):
-    """Interior tiles drop the bounds predicates (they are all true there): the arithmetic is unchanged."""
+def test_interior_tile_specialisation_matches(case):
+    """THALLO_B200_EDGE_SPECIALIZE=1: interior tiles drop the bounds predicates (all true there).  The selects they guard
+    fold away, which changes how the compiler contracts the sums into fused multiply-adds: same trajectory to float32
+    rounding, not bit for bit (measured, profiles/r02g_*)."""
     outs = []
-    for always_edge in (False, True):
-        if always_edge:
-            os.environ["THALLO_B200_EDGE_ALWAYS"] = "1"
+    for specialise in (False, True):
+        if specialise:
+            os.environ["THALLO_B200_EDGE_SPECIALIZE"] = "1"
         try:
             if case == "sfs":
                 W, H = 150, 61
                 s, c, lin, dp = _trajectory_gpu("shape_from_shading", [W, H], "gauss_newton", _sfs_params(wl.sfs_inputs(W, H), np.float32),
                                                 range(16, 21), np.float32, 3, 10)
-                outs.append((c, dp[16].cpu().numpy().tobytes()))
+                outs.append((c, dp[16].cpu().numpy()))
             else:
                 p = wl.volumetric_params(wl.volumetric_inputs(28, 27, 14))
                 s, c, lin, dp = _trajectory_gpu("volumetric_mesh_deformation", [28, 27, 14], "gauss_newton", p, range(4), np.float32, 2, 15)
-                outs.append((c, dp[0].cpu().numpy().tobytes()))
+                outs.append((c, dp[0].cpu().numpy()))
         finally:
-            os.environ.pop("THALLO_B200_EDGE_ALWAYS", None)
-    assert outs[0] == outs[1]
+            os.environ.pop("THALLO_B200_EDGE_SPECIALIZE", None)
+    for a, b in zip(outs[0][0], outs[1][0]):
+        assert abs(a - b) <= 1e-5 * max(abs(a), 1e-3), (outs[0][0], outs[1][0])
+    assert np.abs(outs[0][1] - outs[1][1]).max() <= 1e-4 * max(1.0, np.abs(outs[0][1]).max())

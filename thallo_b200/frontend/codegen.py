@@ -1359,7 +1359,10 @@ class Generator:
                             R[pos] = max(R[pos], abs(lo), abs(hi))
                 if self.two_phase:
                     R = [r + ph for r, ph in zip(R, self.tp["ph"])]      # predicates are also evaluated at the positions around the tile
-                if os.environ.get("THALLO_B200_EDGE_ALWAYS"):
+                # Measured on B200 (profiles/r02g_*): dropping the predicates on interior tiles gains 2-4 % on optical_flow,
+                # shape_from_shading and the volume and LOSES 7 % on the headline's th_pcg_a (four instantiations of the
+                # tile operator in one kernel), so it is opt-in: THALLO_B200_EDGE_SPECIALIZE=1
+                if not os.environ.get("THALLO_B200_EDGE_SPECIALIZE"):
                     R = [1000000] * MAXD
                 hdr.append("#define TH_INB_RX %d\n#define TH_INB_RY %d\n#define TH_INB_RZ %d" % tuple(R))
                 hdr.append("#define TH_TWO_PHASE %d" % int(self.two_phase))
