@@ -1270,13 +1270,19 @@ __device__ constexpr int TH_SCOEF_PTR[TH_NSPACES] = TH_SCOEF_SLOT;
     }
 TH_SCOEF_LIST(TH_SCOEF_KERNEL)
 
-// 64-bit position-weighted checksum of an index array: lets the plan notice that a caller changed
+// 64-bit checksum of an index array (sum of a mixing hash of every (position, value) pair): lets the plan notice that a caller changed
 // the contents of a sparse index array between solves (the adjacency lists are then rebuilt)
 extern "C" __global__ void __launch_bounds__(TH_BLOCK)
 th_index_checksum(const int* __restrict__ a, long long n, unsigned long long* out) {
     unsigned long long h = 0;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
-        h += ((unsigned long long)(unsigned int)__ldg(a + i) + 0x9E3779B97F4A7C15ull) * (2ull * (unsigned long long)i + 1ull);
+    {   // splitmix64 of (position, value): no linear relation between entries survives (a_1 += 5, a_7 -= 1 changed nothing before)
+        unsigned long long x = ((unsigned long long)i << 32) ^ (unsigned long long)(unsigned int)__ldg(a + i);
+        x += 0x9E3779B97F4A7C15ull;
+        x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+        x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+        h += x ^ (x >> 31);
+    }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) h += __shfl_down_sync(0xffffffffu, h, o);
     if ((threadIdx.x & 31) == 0) atomicAdd(out, h);

@@ -222,6 +222,14 @@ Thallo_Plan* Thallo_ProblemPlan(Thallo_State* state, Thallo_Problem* problem, un
     PlanDesc d;
     std::string err;
     if (!parse_descriptor(desc_text, d, err)) { set_error(err); return nullptr; }
+    if (d.lm && state->opts.init.verbosityLevel > 0) {
+        static bool told = false;
+        if (!told) {
+            told = true;
+            fprintf(stderr, "thallo_b200: note: \"levenberg_marquardt\" runs Levenberg-Marquardt as written in gauss_newton.t; the reference snapshot "
+                            "runs Gauss-Newton for this kind string (thallo.t:463). THALLO_LM_AS_COMMITTED=1 reproduces the snapshot.\n");
+        }
+    }
     if (problem->from_source && dimensions) {
         for (size_t i = 0; i < d.dims.size(); ++i)
             if ((long long)dimensions[i] != d.dims[i]) {

@@ -422,7 +422,7 @@ Plan::Plan(const StateOptions* opts, const PlanDesc& desc, const std::string& so
             const int threads = d_.tile[0] * d_.tile[1] * d_.tile[2];
             if (api.OccupancyMaxActiveBlocks && api.OccupancyMaxActiveBlocks(&per_sm, f, threads, tiled_smem_[v]) != CUDA_SUCCESS) per_sm = 2;
             per_sm = std::max(1, std::min(per_sm, 32));
-            if (const char* e = getenv("THALLO_B200_CTAS_PER_SM")) per_sm = std::max(1, atoi(e));
+            if (const char* e = getenv("THALLO_B200_CTAS_PER_SM")) per_sm = std::max(1, std::min(atoi(e), 32));   // d_partials_ holds SMs x 32 blocks
             tiled_grid_[v] = (unsigned)std::min<long long>(ntiles, (long long)sms * per_sm);
         }
     }
