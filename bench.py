@@ -52,7 +52,7 @@ def parse():
     ap.add_argument("--config", default="2", help="headline workload (default: 2, the configured image_warping 2048^2)")
     ap.add_argument("--extras", default="all", help="other configured workloads measured into the line's `configs`: all | none | 3a,4b,...")
     ap.add_argument("--extra-steps", type=int, default=2, help="timed solves per extra workload")
-    ap.add_argument("--budget-s", type=float, default=900.0, help="wall-clock budget after which remaining extras are skipped")
+    ap.add_argument("--budget-s", type=float, default=480.0, help="wall-clock budget after which remaining extras are skipped")
     ap.add_argument("--size", type=int, default=2048, help="headline image side (default: the configured 2048)")
     ap.add_argument("--cpu-sample-pcg", type=int, default=0, help="PCG iterations in the CPU sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
