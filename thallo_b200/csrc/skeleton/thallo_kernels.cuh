@@ -240,16 +240,11 @@ __device__ __forceinline__ void th_for_owned(long long lo, long long hi, FV&& fv
 // totals also has its ghost copies of z) and close the iteration like the tiled single-GPU schedule does.
 __device__ __forceinline__ void th_step2_publish(ThScalars* S, double (&tot)[2], real q_tolerance, ThHostFlags* hf, const ThPeers& R,
                                                  const ThPush& H, const real* z) {
-#if TH_MULTI
-    if (R.fused) th_push_segments(H, z);                // z of the boundary elements -> the neighbours' ghost copies
-#endif
     if (th_tid() >= 32) return;
 #if TH_MULTI
-    if (!R.fused) {
-        if (th_tid() == 0) { S->red[0] = tot[0]; S->red[1] = tot[1]; }
-        return;
-    }
-    th_mail_allreduce<2>(R, TH_MAIL_B, th_seq(S->epoch, S->it + 1), tot);
+    // multi-GPU: this rank's parts only; th_push_close (fused) or NCCL + th_mg_close (comparison path) finish the iteration
+    if (th_tid() == 0) { S->red[0] = tot[0]; S->red[1] = tot[1]; }
+    return;
 #endif
     if (th_tid() == 0) {
         S->rz[(S->it + 1) & 1] = tot[0]; S->q = tot[1];
@@ -259,6 +254,46 @@ __device__ __forceinline__ void th_step2_publish(ThScalars* S, double (&tot)[2],
     }
 }
 #if TH_MULTI
+// Fused multi-GPU end of PCGStep2: a few CTAs copy the boundary layers of z into the neighbours' ghost layers (a single
+// CTA takes ~100 us for the 1.2 MB faces of a 160^3 slab, measured: profiles/r02h_n8_*_last_cta_push.*), EVERY CTA fences
+// at system scope before its ticket, and the last one all-reduces this rank's <z,r> and q with the peers' over the
+// mailboxes and closes the iteration: whoever has the totals also has its ghost copies of z.
+extern "C" __global__ void __launch_bounds__(TH_BLOCK)
+th_push_close(const __grid_constant__ Vecs V, ThScalars* S, real q_tolerance, ThHostFlags* hf,
+              const __grid_constant__ ThPeers R, const __grid_constant__ ThPush H) {
+    if (S->done) return;
+    const real* __restrict__ src = V.z;
+    const long long gtid = (long long)blockIdx.x * blockDim.x + threadIdx.x, stride = (long long)gridDim.x * blockDim.x;
+    for (int s = 0; s < 2 * TH_NUM_UIMG; ++s) {
+        if (s >= H.n) break;
+        const long long lo = H.lo[s], n = H.hi[s] - H.lo[s];
+        if (H.vec4[s]) {
+            const real4* __restrict__ a = (const real4*)(src + lo);
+            real4* __restrict__ b = (real4*)H.dst[s];
+            for (long long i = gtid; i < n / 4; i += stride) b[i] = __ldcg(a + i);
+        } else {
+            for (long long i = gtid; i < n; i += stride) H.dst[s][i] = __ldcg(src + lo + i);
+        }
+    }
+    __shared__ bool last;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence_system();
+        last = atomicAdd(&S->ticket[5], 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
+    if (threadIdx.x < 32) {
+        double tot[2] = {S->red[0], S->red[1]};
+        th_mail_allreduce<2>(R, TH_MAIL_B, th_seq(S->epoch, S->it + 1), tot);
+        if (threadIdx.x == 0) {
+            S->ticket[5] = 0u;
+            S->rz[(S->it + 1) & 1] = tot[0]; S->q = tot[1];
+            th_close_iteration(S, q_tolerance, hf);
+        }
+    }
+}
 extern "C" __global__ void th_mg_close(ThScalars* S, real q_tolerance, ThHostFlags* hf) {
     if (S->done) return;
     S->rz[(S->it + 1) & 1] = S->red[0]; S->q = S->red[1];

@@ -288,6 +288,13 @@ int Plan::connect_all(int world, const void* handles64, const long long* infos4)
     peers_.rank = rank_; peers_.world = world_; peers_.fused = fused_ ? 1 : 0;
     build_push(d_.tiled ? V_Z : V_P, push_init_);
     build_push(V_Z, push_iter_);
+    {   // CTAs of th_push_close: one per 8 KB of boundary values, at most 64
+        Seg g[8];
+        const int n = fused_ ? segments(V_Z, g) : 0;
+        long long bytes = 0;
+        for (int i = 0; i < n; ++i) bytes += g[i].count * (long long)real_size_;
+        push_grid_ = (unsigned)std::max<long long>(1, std::min<long long>(64, (bytes + 8191) / 8192));
+    }
     return 0;
 }
 
@@ -957,6 +964,10 @@ void Plan::linear_iteration(int l) {
     } else {
         void* a[] = {V, &d_scalars_, &d_partials_, qtol, &d_flags_, &peers_, push_iter_.data()};
         launch_flat(fn("th_pcg_b"), a);
+    }
+    if (d_.multi && fused_) {     // boundary layers of z -> the neighbours, in-kernel all-reduce of <z,r> and q, close
+        void* a[] = {V, &d_scalars_, qtol, &d_flags_, &peers_, push_iter_.data()};
+        launch(fn("th_push_close"), dim3(push_grid_), dim3(256), a);
     }
     if (nccl_scalars) {           // z ghost layers, global <z,r> and q, then close the iteration
         halo_push(V_Z, 1);
