@@ -16,9 +16,14 @@ run_group() {
 }
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1"
 run_group 45 $OUT/debug_gn.txt $TR --master-port 29801 tests/mgpu_debug.py levenberg_marquardt; rc=$?
-echo "debug LM rc=$rc" | tee -a $OUT/summary.txt
+echo "debug LM (push kernel) rc=$rc" | tee -a $OUT/summary.txt
 grep -hE "^\[rank 0|TIMEOUT|rror" $OUT/debug_gn.txt | tail -5
-[ $rc = 0 ] || exit 1
+if [ $rc != 0 ]; then      # fall back to the pushes by the last CTA (validated at N = 2 and 8)
+  export THALLO_B200_PUSH_KERNEL=0
+  run_group 45 $OUT/debug_gn_fallback.txt $TR --master-port 29803 tests/mgpu_debug.py levenberg_marquardt; rc=$?
+  echo "debug LM (last-CTA push) rc=$rc" | tee -a $OUT/summary.txt
+  [ $rc = 0 ] || exit 1
+fi
 run_group ${2:-330} $OUT/bench.txt $TR --master-port 29802 bench.py --gpus $N --steps 5 --warmup 3 --budget-s ${3:-230}; rc=$?
 echo "bench rc=$rc" | tee -a $OUT/summary.txt
 python - <<PY | tee -a $OUT/summary.txt

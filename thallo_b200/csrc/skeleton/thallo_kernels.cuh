@@ -240,11 +240,18 @@ __device__ __forceinline__ void th_for_owned(long long lo, long long hi, FV&& fv
 // totals also has its ghost copies of z) and close the iteration like the tiled single-GPU schedule does.
 __device__ __forceinline__ void th_step2_publish(ThScalars* S, double (&tot)[2], real q_tolerance, ThHostFlags* hf, const ThPeers& R,
                                                  const ThPush& H, const real* z) {
-    if (th_tid() >= 32) return;
 #if TH_MULTI
-    // multi-GPU: this rank's parts only; th_push_close (fused) or NCCL + th_mg_close (comparison path) finish the iteration
-    if (th_tid() == 0) { S->red[0] = tot[0]; S->red[1] = tot[1]; }
-    return;
+    // R.fused == 2 (default) / 0: this rank's parts only; th_push_close (fused) or NCCL + th_mg_close (comparison path)
+    // finish the iteration.  R.fused == 1: the last CTA pushes the boundary layers itself (fine for thin boundaries).
+    if (R.fused != 1) {
+        if (th_tid() == 0) { S->red[0] = tot[0]; S->red[1] = tot[1]; }
+        return;
+    }
+    th_push_segments(H, z);
+    if (th_tid() >= 32) return;
+    th_mail_allreduce<2>(R, TH_MAIL_B, th_seq(S->epoch, S->it + 1), tot);
+#else
+    if (th_tid() >= 32) return;
 #endif
     if (th_tid() == 0) {
         S->rz[(S->it + 1) & 1] = tot[0]; S->q = tot[1];

@@ -285,7 +285,9 @@ int Plan::connect_all(int world, const void* handles64, const long long* infos4)
     fused_ = !(e && atoi(e) != 0);
     peers_ = HPeers{};
     for (int r = 0; r < world; ++r) peers_.box[r] = peer_all_[r] + peer_stride_[r] * kNumVecs;
-    peers_.rank = rank_; peers_.world = world_; peers_.fused = fused_ ? 1 : 0;
+    // fused: 2 = boundary layers pushed by the small th_push_close kernel (default), 1 = by the last CTA of th_pcg_b
+    push_kernel_ = !(getenv("THALLO_B200_PUSH_KERNEL") && atoi(getenv("THALLO_B200_PUSH_KERNEL")) == 0);
+    peers_.rank = rank_; peers_.world = world_; peers_.fused = fused_ ? (push_kernel_ ? 2 : 1) : 0;
     build_push(d_.tiled ? V_Z : V_P, push_init_);
     build_push(V_Z, push_iter_);
     {   // CTAs of th_push_close: one per 8 KB of boundary values, at most 64
@@ -965,7 +967,7 @@ void Plan::linear_iteration(int l) {
         void* a[] = {V, &d_scalars_, &d_partials_, qtol, &d_flags_, &peers_, push_iter_.data()};
         launch_flat(fn("th_pcg_b"), a);
     }
-    if (d_.multi && fused_) {     // boundary layers of z -> the neighbours, in-kernel all-reduce of <z,r> and q, close
+    if (d_.multi && fused_ && push_kernel_) {     // boundary layers of z -> the neighbours, in-kernel all-reduce of <z,r> and q, close
         void* a[] = {V, &d_scalars_, qtol, &d_flags_, &peers_, push_iter_.data()};
         launch(fn("th_push_close"), dim3(push_grid_), dim3(256), a);
     }

@@ -204,6 +204,7 @@ private:
     void build_push(int vec, std::vector<char>& image) const;
     char* peer_all_[kMaxRanks] = {};                // every rank's solver-vector block (CUDA IPC mappings; own = vec_block_)
     size_t peer_stride_[kMaxRanks] = {};
+    bool push_kernel_ = true;
     unsigned push_grid_ = 1;                        // CTAs of th_push_close
     bool fused_ = false;                            // PCG scalars all-reduced inside the kernels over peer memory (default once connect_all ran)
     HPeers peers_{};
