@@ -285,18 +285,22 @@ int Plan::connect_all(int world, const void* handles64, const long long* infos4)
     fused_ = !(e && atoi(e) != 0);
     peers_ = HPeers{};
     for (int r = 0; r < world; ++r) peers_.box[r] = peer_all_[r] + peer_stride_[r] * kNumVecs;
-    // fused: 2 = boundary layers pushed by the small th_push_close kernel (default), 1 = by the last CTA of th_pcg_b
-    push_kernel_ = !(getenv("THALLO_B200_PUSH_KERNEL") && atoi(getenv("THALLO_B200_PUSH_KERNEL")) == 0);
+    long long push_bytes = 0;
+    {
+        Seg g[8];
+        const int n = fused_ ? segments(V_Z, g) : 0;
+        for (int i = 0; i < n; ++i) push_bytes += g[i].count * (long long)real_size_;
+    }
+    // fused: 1 = the boundary layers of z are pushed by the last CTA of th_pcg_b, 2 = by the small th_push_close kernel.
+    // Measured at 8 GPUs (profiles/r02h_n8_*): a single CTA needs ~100 us for the 1.2 MB faces of a 160^3 slab (the
+    // kernel: 10.5 k instead of 6.4 k iterations/s), while for the 48-128 KB rows of the 2-D slabs and the graph the extra
+    // launch costs 1-6 %.  THALLO_B200_PUSH_KERNEL=0/1 forces one or the other.
+    push_kernel_ = push_bytes > 256 * 1024;
+    if (const char* pk = getenv("THALLO_B200_PUSH_KERNEL")) push_kernel_ = atoi(pk) != 0;
     peers_.rank = rank_; peers_.world = world_; peers_.fused = fused_ ? (push_kernel_ ? 2 : 1) : 0;
     build_push(d_.tiled ? V_Z : V_P, push_init_);
     build_push(V_Z, push_iter_);
-    {   // CTAs of th_push_close: one per 8 KB of boundary values, at most 64
-        Seg g[8];
-        const int n = fused_ ? segments(V_Z, g) : 0;
-        long long bytes = 0;
-        for (int i = 0; i < n; ++i) bytes += g[i].count * (long long)real_size_;
-        push_grid_ = (unsigned)std::max<long long>(1, std::min<long long>(64, (bytes + 8191) / 8192));
-    }
+    push_grid_ = (unsigned)std::max<long long>(1, std::min<long long>(64, (push_bytes + 8191) / 8192));      // CTAs of th_push_close
     return 0;
 }
 
