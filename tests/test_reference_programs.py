@@ -54,10 +54,10 @@ def test_reference_callers_compile_and_link_unmodified():
         assert "libThallo.so" in ldd and "not found" not in ldd.split("libThallo.so")[1].splitlines()[0]
 
 
-def _libc_uniform(n):
-    """What the programs fill their input with: glibc rand() / RAND_MAX from the default seed."""
+def _libc_uniform(n, seed=1):
+    """What the programs fill their input with: glibc rand() / RAND_MAX from the default seed (or the one they set)."""
     libc = ctypes.CDLL("libc.so.6")
-    libc.srand(1)
+    libc.srand(ctypes.c_uint(seed))
     return np.array([libc.rand() / 2147483647.0 for _ in range(n)], np.float64).astype(np.float32)
 
 
@@ -175,3 +175,47 @@ def test_reference_create_delete_cycle_program_runs_against_this_library(tmp_pat
     assert "Iteration: 9" in r.stdout
     assert (tmp_path / "result.png").exists()
     assert dt < 60, dt
+
+
+MINIMAL_EXCLUDE_T = """
+-- fit to A plus unguarded forward differences (out-of-bounds reads are zero, thallo.t:876-882)
+W,H = Dims("W","H")
+Inputs { X = Unknown(float,{W,H},0), A = Array(float,{W,H},1) }
+w_fit = .2
+x,y = W(), H()
+r = Residuals { fit = w_fit*(X(x,y) - A(x,y)), reg = { (X(x,y) - X(x+1,y)), (X(x,y) - X(x,y+1)) } }
+"""
+
+MINIMAL_MATERIALIZE_T = """
+-- the x-difference goes through a ComputedArray (v:get), so its values and gradient image are stored by `precompute`
+W,H = Dims("W","H")
+Inputs { X = Unknown(float,{W,H},0), A = Array(float,{W,H},1) }
+x,y = W(),H()
+v = X(x,y) - X(x+1,y)
+v = Select(InBounds(x+1,y), v, 0.0)
+local reg = v:get(x,y)
+r = Residuals { fit = (X(x,y) - A(x,y)), reg = reg }
+"""
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("binary,fname,text,seed", [("ref_minimal_exclude", "minimal_exclude.t", MINIMAL_EXCLUDE_T, 1),
+                                                   ("ref_minimal_materialize", "minimal_materialize.t", MINIMAL_MATERIALIZE_T, 0xF8127324)])
+def test_more_reference_programs_run_against_this_library(tmp_path, binary, fname, text, seed):
+    """tests/minimal_exclude and tests/minimal_materialize (a ComputedArray), unmodified, 512 x 512, GN 10 x 10: the cost the
+    program prints equals the cost of the same solve driven through the Python mirror of the C ABI from the same file."""
+    if not os.path.isfile(os.path.join(BIN, binary)):
+        pytest.skip("oracle/_ref not built")
+    import torch
+    from thallo_b200.api import ThalloSolver
+    (tmp_path / fname).write_text(text)
+    r = subprocess.run([os.path.join(BIN, binary)], cwd=str(tmp_path), capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    m = re.search(r"%s ([-+0-9.eE]+|nan|inf)" % binary[len("ref_"):], r.stdout)
+    assert m, r.stdout[-2000:]
+    cost = float(m.group(1))
+    A = _libc_uniform(512 * 512, seed)
+    dX, dA = torch.from_numpy(A.copy()).cuda(), torch.from_numpy(A.copy()).cuda()
+    s = ThalloSolver([512, 512], str(tmp_path / fname), "gauss_newton", via_file=True)
+    want = s.solve([dX, dA])
+    assert np.isfinite(cost) and abs(cost - want) <= 1e-5 * abs(want), (cost, want)
