@@ -200,7 +200,8 @@ r = Residuals { fit = (X(x,y) - A(x,y)), reg = reg }
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("binary,fname,text,seed", [("ref_minimal_exclude", "minimal_exclude.t", MINIMAL_EXCLUDE_T, 1),
-                                                   ("ref_minimal_materialize", "minimal_materialize.t", MINIMAL_MATERIALIZE_T, 0xF8127324)])
+                                                   ("ref_minimal_materialize", "minimal_materialize.t", MINIMAL_MATERIALIZE_T, 0xF8127324)],
+                         ids=["minimal_exclude", "minimal_materialize"])
 def test_more_reference_programs_run_against_this_library(tmp_path, binary, fname, text, seed):
     """tests/minimal_exclude and tests/minimal_materialize (a ComputedArray), unmodified, 512 x 512, GN 10 x 10: the cost the
     program prints equals the cost of the same solve driven through the Python mirror of the C ABI from the same file."""
