@@ -836,7 +836,10 @@ __device__ __forceinline__ real th_tile_apply2(const unsigned char* sm, real* jp
     int x0, y0, z0;
     th_tile_origin(t, x0, y0, z0);
     const int tid = tx + TH_TW * (ty + TH_TH * tz);
-    __syncthreads();                                   // the previous tile's phase 2 has read its planes
+    // one set of planes: wait until the previous tile's phase 2 has read them.  Two sets alternate per tile: a warp
+    // that starts phase 1 of tile k+1 has passed the barrier of tile k, which every warp reaches only after its own
+    // phase 2 of tile k-1 -- the set being overwritten is no longer read.
+    if (TH_JP_BUFS == 1) __syncthreads();
     // phase 1, positions around the tile
     for (int q = tid; q < TH_JP_NHALO; q += TH_TILE_THREADS) {
         const unsigned int e = __ldg(&TH_JP_POS[q]);
@@ -933,6 +936,8 @@ __device__ __forceinline__ void th_pcg_a_impl(const Params& P, const Vecs& V, co
         }
     }
     double acc[1] = {0.0};
+    int tile_k = 0;
+    (void)tile_k;
     unsigned phase = 0;                   // bit s: parity of the next completion of full[s] (and of empty[s])
     int stage = 0;
     for (int t = blockIdx.x; t < TH_NTILES; t += gridDim.x) {
@@ -956,7 +961,8 @@ __device__ __forceinline__ void th_pcg_a_impl(const Params& P, const Vecs& V, co
         const bool edge = th_tile_is_edge(t);          // uniform over the CTA
         real dot;
 #if TH_TWO_PHASE
-        real* jpbuf = (real*)(th_sm + (TMA ? TH_PIPE : 1) * TH_SMEM_BYTES);
+        real* jpbuf = (real*)(th_sm + (TMA ? TH_PIPE : 1) * TH_SMEM_BYTES) + (TH_JP_BUFS == 2 ? (tile_k & 1) * (TH_JP_NT * TH_JP_NBOX) : 0);
+        ++tile_k;
         if (edge) dot = upd ? th_tile_apply2<true, true>(sm, jpbuf, P, V, t, mode, beta, out, pnew, tx, ty, tz)
                             : th_tile_apply2<false, true>(sm, jpbuf, P, V, t, mode, beta, out, pnew, tx, ty, tz);
         else dot = upd ? th_tile_apply2<true, false>(sm, jpbuf, P, V, t, mode, beta, out, pnew, tx, ty, tz)

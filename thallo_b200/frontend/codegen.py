@@ -684,6 +684,12 @@ class Generator:
                         self.tl["pipe"] = pipe
                     if not os.environ.get("THALLO_B200_MINB"):
                         self.tl["minb"] = max(1, min(self.tl["minb"], limit // (self.tl["pipe"] * stage + jpb), 2048 // nthreads))
+                    # two sets of planes (alternating per tile) save the barrier at the start of a tile -- the previous
+                    # tile's phase 2 may still be reading -- when they fit beside the same number of resident CTAs
+                    bufs = 2 if (self.tl["pipe"] * stage + 2 * jpb) * self.tl["minb"] <= limit else 1
+                    if os.environ.get("THALLO_B200_JP_BUFS"):
+                        bufs = int(os.environ["THALLO_B200_JP_BUFS"])
+                    self.tp["bufs"] = bufs
                     src.append(tp_src)
         return "\n".join(src)
 
@@ -1369,6 +1375,7 @@ class Generator:
                 if self.two_phase:
                     tp = self.tp
                     hdr.append("#define TH_JP_NT %d" % tp["nt"])
+                    hdr.append("#define TH_JP_BUFS %d" % tp["bufs"])
                     hdr.append("#define TH_JP_PHX %d\n#define TH_JP_PHY %d\n#define TH_JP_PHZ %d" % tuple(tp["ph"]))
                     hdr.append("#define TH_JP_NHALO %d" % len(tp["pos"]))
                     hdr.append("#define TH_JP_POS_TABLE {%s}" % (", ".join("%du" % x for x in tp["pos"]) or "0u"))
@@ -1485,7 +1492,7 @@ class Generator:
             d["tiled"] = int(self.tiled)
             if self.tiled:
                 d["tile"] = self.tl
-                d["jp_bytes"] = (self.tp["nt"] * self.tp["nbox"] * (8 if self.double else 4)) if self.two_phase else 0
+                d["jp_bytes"] = (self.tp["nt"] * self.tp["nbox"] * (8 if self.double else 4) * self.tp["bufs"]) if self.two_phase else 0
         out.desc = d
         return out
 
