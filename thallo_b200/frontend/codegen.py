@@ -684,11 +684,13 @@ class Generator:
                         self.tl["pipe"] = pipe
                     if not os.environ.get("THALLO_B200_MINB"):
                         self.tl["minb"] = max(1, min(self.tl["minb"], limit // (self.tl["pipe"] * stage + jpb), 2048 // nthreads))
-                    # two sets of planes (alternating per tile) save the barrier at the start of a tile -- the previous
-                    # tile's phase 2 may still be reading -- when they fit beside the same number of resident CTAs
-                    bufs = 2 if (self.tl["pipe"] * stage + 2 * jpb) * self.tl["minb"] <= limit else 1
-                    if os.environ.get("THALLO_B200_JP_BUFS"):
-                        bufs = int(os.environ["THALLO_B200_JP_BUFS"])
+                    # Two sets of planes (alternating per tile) would save the barrier at the start of a tile -- the previous
+                    # tile's phase 2 may still be reading.  Built, correct, and measured on shape_from_shading 8192^2: 1.430 ms
+                    # against 1.400 ms with one set (profiles/r02l_summary.txt), so one set stays the default
+                    # (THALLO_B200_JP_BUFS=2 selects two where they fit).
+                    bufs = 1
+                    if os.environ.get("THALLO_B200_JP_BUFS") == "2" and (self.tl["pipe"] * stage + 2 * jpb) * self.tl["minb"] <= limit:
+                        bufs = 2
                     self.tp["bufs"] = bufs
                     src.append(tp_src)
         return "\n".join(src)
