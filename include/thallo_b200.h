@@ -27,8 +27,10 @@ Thallo_Problem* ThalloB200_ProblemDefineFromSource(Thallo_State* state, const ch
  * (up to log_capacity bytes).  Used by the CPU-side build check. */
 int ThalloB200_CompileOnly(const char* cuda_source, char* log, unsigned long log_capacity, unsigned long* cubin_size);
 
-/* Stream all solver work is issued on (a cudaStream_t); default is the legacy default
- * stream like the reference (util.t:769-772). */
+/* The caller's stream (a cudaStream_t) the solver is ordered with; default is the legacy default stream like the
+ * reference (util.t:769-772).  The solver's own work runs on a private stream per plan (so that the PCG iterations can
+ * be captured into CUDA graphs): every entry point makes that stream wait for the caller's stream and every exit makes
+ * the caller's stream wait for it, i.e. the caller sees plain stream-ordered behaviour on its stream. */
 void ThalloB200_SetStream(Thallo_State* state, void* cuda_stream);
 
 /* Number of kernel launches issued by this plan since creation (for bench accounting). */
